@@ -1,0 +1,207 @@
+/*
+ * poserisk_b200.h -- C ABI of the B200-native PoseRisk body-model -> risk-score path.
+ *
+ * The reference (hygenie1228/PoseRisk_RELEASE) has no FFI: its boundary for this
+ * path is a Python call surface.  Each entry point below names the reference
+ * interface it stands behind (paths relative to the reference root).  The Python
+ * drop-ins in poserisk_release_b200/ (SMPL_Layer, REBA, RULA, get_joint_cam,
+ * axis_angle_to_euler_angle) bind these symbols with ctypes; see INTEGRATION.md.
+ *
+ * Conventions
+ *  - plain C types only; every `d_` pointer is caller-owned DEVICE memory on the
+ *    model's device, every `h_` pointer is HOST memory;
+ *  - nothing is allocated inside a hot call: scratch comes from the caller's
+ *    workspace (prk_workspace_bytes);
+ *  - calls are asynchronous on `stream` (a cudaStream_t passed as void*);
+ *  - no exceptions cross the ABI: int status, 0 = PRK_OK, text via prk_strerror;
+ *  - a handle belongs to one device; use one host thread per handle or lock.
+ */
+#ifndef POSERISK_B200_H
+#define POSERISK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define PRK_ABI_VERSION 1
+
+#define PRK_NUM_VERTS 6890
+#define PRK_NUM_JOINTS 24
+#define PRK_NUM_BETAS 10
+#define PRK_NUM_POSE_FEATS 207
+
+enum prk_status {
+    PRK_OK = 0,
+    PRK_ERR_INVALID_ARG = 1,
+    PRK_ERR_CUDA = 2,
+    PRK_ERR_WORKSPACE = 3,   /* workspace too small or misaligned */
+    PRK_ERR_UNSUPPORTED = 4,
+    PRK_ERR_DRIVER = 5       /* cuTensorMapEncodeTiled unavailable / failed */
+};
+
+/* additional_information.json (example/additional_information.json:1-25), one per track.
+ * reba[7]: Legs_bilateral_weight_bearing/walking, Sitting, Load/Force Score,
+ *          Arm_supported_leaning_L, Arm_supported_leaning_R, Coupling, Activity_Score
+ *          (the keys lib/utils/reba.py:59,64,69,113,190,221,240 read)
+ * rula[9]: Arm_supported_leaning_L, Arm_supported_leaning_R, A_Muscle_use_L,
+ *          A_Muscle_use_R, A_Load/Force_L, A_Load/Force_R, Legs_bilateral_weight_bearing,
+ *          B_Muscle_use, B_Load/Force   (lib/utils/rula.py:75-76,81,151,177,196) */
+typedef struct prk_addinfo {
+    int32_t reba[7];
+    int32_t rula[9];
+} prk_addinfo;
+
+/* One scored frame, 32 bytes.  Holds what REBA.__call__ / RULA.__call__ return per
+ * frame (`score`, flattened `log_score`; lib/utils/reba.py:71-75, rula.py:88-92).
+ * reba_parts: trunk, neck, leg, upper_arm L,R, lower_arm L,R, wrist L,R
+ * rula_parts: upper_arm L,R, lower_arm L,R, wrist L,R, wrist_twist L,R, neck, trunk, leg
+ * flags bit0: a scored joint's rotation matrix is not finite, i.e. the reference
+ *             would stop at assert(isRotationMatrix(R)) (lib/utils/coord_utils.py:70). */
+typedef struct prk_score_rec {
+    int16_t reba_score;
+    int16_t rula_score;
+    uint8_t reba_parts[9];
+    uint8_t rula_parts[11];
+    uint8_t flags;
+    uint8_t pad[7];
+} prk_score_rec;
+
+#define PRK_SCORE_REBA 1u
+#define PRK_SCORE_RULA 2u
+
+/* pose element type of the scoring front-end: cv2.Rodrigues returns a matrix of the
+ * input's dtype (lib/utils/coord_utils.py:86), so float32 poses give float32-rounded R. */
+#define PRK_DTYPE_F32 0
+#define PRK_DTYPE_F64 1
+
+/* prk_workspace_bytes / prk_smpl_forward flags */
+#define PRK_FLAG_JOINTS_ONLY 1u   /* no vertex output: blend GEMM and skinning are skipped */
+
+typedef struct prk_model prk_model;
+
+int prk_abi_version(void);
+const char* prk_strerror(int status);
+/* text of the last CUDA/driver error seen by this thread's calls ("" if none) */
+const char* prk_last_error_detail(void);
+
+/* SMPL_Layer.__init__ (lib/smplpytorch/smplpytorch/pytorch/smpl_layer.py:15-63): takes the
+ * arrays that constructor registers as buffers (HOST pointers, float32, C order) and builds
+ * the device-side operands: bf16 split-precision blend matrix for the tcgen05 GEMM,
+ * compacted skinning weights, folded joint regressor.
+ *   h_v_template [6890*3]      th_v_template   (:46-48)
+ *   h_shapedirs  [6890*3*10]   th_shapedirs    (:42-43)
+ *   h_posedirs   [6890*3*207]  th_posedirs     (:44-45)
+ *   h_J_regressor[24*6890]     th_J_regressor  (:49-51, dense)
+ *   h_weights    [6890*24]     th_weights      (:52-53)
+ *   h_parents    [24]          kintree_table[0] (:60-62); entry 0 is ignored
+ *   h_betas      [10] or NULL  th_betas        (:40-41); NULL = zeros */
+int prk_model_create(prk_model** out, int device, const float* h_v_template,
+                     const float* h_shapedirs, const float* h_posedirs,
+                     const float* h_J_regressor, const float* h_weights,
+                     const int32_t* h_parents, const float* h_betas);
+void prk_model_destroy(prk_model* model);
+int prk_model_device(const prk_model* model);
+/* max non-zero skinning weights per vertex found at create time (4 for SMPL) */
+int prk_model_max_weights(const prk_model* model);
+
+/* Scratch needed by prk_smpl_forward / prk_pipeline for a batch of B frames.  Any size
+ * >= prk_workspace_bytes(model, 1, flags) works: frames are processed in chunks that fit. */
+size_t prk_workspace_bytes(const prk_model* model, int64_t B, uint32_t flags);
+
+/* SMPL_Layer.forward(th_pose_axisang, th_betas, th_trans) (smpl_layer.py:65-158).
+ *   d_pose  [B*72] float32 axis-angle
+ *   d_betas [B*10] or NULL; NULL or an all-zero batch selects the model's betas (:87-91)
+ *   d_trans [B*3]  or NULL; NULL or an all-zero batch: no translation, and the
+ *           `center_idx` joint is subtracted when center_idx >= 0 (:148-152)
+ *   center_idx  -1 = None
+ *   d_verts [B*6890*3] float32, or NULL for the joints-only path
+ *   d_joints[B*24*3]  float32 (chain translations, :145)
+ * Both whole-batch tests are evaluated on the device (no host sync). */
+int prk_smpl_forward(prk_model* model, const float* d_pose, const float* d_betas,
+                     const float* d_trans, int center_idx, int64_t B, float* d_verts,
+                     float* d_joints, void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* axis_angle_to_euler_angle (lib/utils/coord_utils.py:83-95) + REBA.__call__ /
+ * RULA.__call__ (lib/utils/reba.py:50-81, lib/utils/rula.py:66-98) per frame, i.e. the
+ * loop body of lib/core/base.py:225-229 followed by :151 and :168.
+ *   d_pose  [B*72] axis-angle, float32 or float64 (pose_dtype)
+ *   d_info  [n_tracks]; d_track_of_frame [B] int32 or NULL (every frame uses d_info[0])
+ *   which   PRK_SCORE_REBA | PRK_SCORE_RULA
+ *   d_out   [B] records
+ *   d_euler_out [B][n_debug][3] float64 degrees or NULL: Euler angles of the joints
+ *           listed in h_debug_joint_ids (the --debug_joints sequences, base.py:144-146) */
+int prk_score_pose(const void* d_pose, int pose_dtype, const prk_addinfo* d_info,
+                   const int32_t* d_track_of_frame, int64_t B, uint32_t which,
+                   prk_score_rec* d_out, double* d_euler_out, const int32_t* h_debug_joint_ids,
+                   int n_debug, void* stream);
+
+/* REBA.__call__(poses, joint_cams, add_info) / RULA.__call__ on Euler degrees
+ * (reba.py:50, rula.py:66): d_euler [B*24*3] float64.  joint_cams is never read by the
+ * reference (only inside dead string literals, reba.py:262-290) and has no parameter. */
+int prk_score_euler(const double* d_euler, const prk_addinfo* d_info,
+                    const int32_t* d_track_of_frame, int64_t B, uint32_t which,
+                    prk_score_rec* d_out, void* stream);
+
+/* axis_angle_to_euler_angle alone (coord_utils.py:83-95): n_rot 3-vectors ->
+ * float64 degrees [n_rot*3]; d_bad [n_rot] uint8 (1 = the isRotationMatrix assert would
+ * fire) or NULL. */
+int prk_euler(const void* d_pose, int pose_dtype, int64_t n_rot, double* d_euler,
+              uint8_t* d_bad, void* stream);
+
+/* The whole per-frame path of lib/core/base.py:225-239,151,168 in one call on device
+ * buffers: prk_smpl_forward + prk_score_pose on the same float32 pose. */
+int prk_pipeline(prk_model* model, const float* d_pose, const float* d_betas,
+                 const float* d_trans, int center_idx, const prk_addinfo* d_info,
+                 const int32_t* d_track_of_frame, int64_t B, float* d_verts, float* d_joints,
+                 prk_score_rec* d_scores, void* d_workspace, size_t workspace_bytes,
+                 void* stream);
+
+/* Same, from HOST buffers (what a reference caller holds, base.py:222): copies pose /
+ * betas / trans host->device, runs prk_pipeline, copies scores and joints device->host.
+ * Vertices stay in device memory (d_verts, may be NULL).  Staging buffers live in the
+ * workspace: size it with prk_host_workspace_bytes.  Host buffers should be pinned for
+ * the copies to be asynchronous. */
+size_t prk_host_workspace_bytes(const prk_model* model, int64_t B, uint32_t flags);
+int prk_pipeline_host(prk_model* model, const float* h_pose, const float* h_betas,
+                      const float* h_trans, int center_idx, const prk_addinfo* h_info,
+                      int32_t n_tracks, const int32_t* h_track_of_frame, int64_t B,
+                      float* d_verts, float* h_joints, prk_score_rec* h_scores,
+                      void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* Predictor.post_processing aggregation (lib/core/base.py:260-271) over one scorer's
+ * score sequence: d_hist receives a 64-bin histogram of score values clamped to
+ * [-16, 47] (bin = score + 16); mean / top-50% / top-10% / max / mode follow from it on
+ * the host.  which = PRK_SCORE_REBA or PRK_SCORE_RULA.  d_hist is zeroed by the call. */
+int prk_score_histogram(const prk_score_rec* d_scores, int64_t B, uint32_t which,
+                        unsigned long long* d_hist, void* stream);
+
+/* ---- verification hooks (used by tests only; not on the product path) ---- */
+/* blend-shape stage alone: v_posed [B][prk_vposed_pitch()] float32 into d_vposed, either
+ * through the tcgen05 GEMM (use_simt = 0) or a plain FFMA loop over the same bf16
+ * operands (use_simt = 1). */
+int prk_debug_blend(prk_model* model, const float* d_pose, const float* d_betas, int64_t B,
+                    float* d_vposed, int use_simt, void* d_workspace, size_t workspace_bytes,
+                    void* stream);
+int64_t prk_vposed_pitch(void);
+/* Per-stage device timing for bench.py's roofline: between begin and end every stage launch
+ * of prk_smpl_forward / prk_pipeline is bracketed by CUDA events on the launch stream.
+ * ms_out[4] / launches_out[4]: 0 pose chain, 1 blend GEMM, 2 skinning, 3 scoring.
+ * Single-threaded use only. */
+int prk_profile_begin(void);
+int prk_profile_end(double* ms_out, int64_t* launches_out);
+/* number of kernels launched by this library since load (all threads) */
+uint64_t prk_launch_count(void);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* POSERISK_B200_H */

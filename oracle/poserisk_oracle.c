@@ -85,9 +85,11 @@ static void cv_rodrigues(const double r_in[3], double R[9]) {
     }
     double c = cos(theta), s = sin(theta), c1 = 1.0 - c, it = 1.0 / theta;
     x *= it; y *= it; z *= it;
-    R[0] = c + c1 * x * x;     R[1] = c1 * x * y - s * z; R[2] = c1 * x * z + s * y;
-    R[3] = c1 * x * y + s * z; R[4] = c + c1 * y * y;     R[5] = c1 * y * z - s * x;
-    R[6] = c1 * x * z - s * y; R[7] = c1 * y * z + s * x; R[8] = c + c1 * z * z;
+    /* Matx33d R = c*eye + c1*rrt + s*r_x : products rrt_ij = r_i*r_j are formed first */
+    double xx = x * x, xy = x * y, xz = x * z, yy = y * y, yz = y * z, zz = z * z;
+    R[0] = c + c1 * xx;       R[1] = c1 * xy - s * z;   R[2] = c1 * xz + s * y;
+    R[3] = c1 * xy + s * z;   R[4] = c + c1 * yy;       R[5] = c1 * yz - s * x;
+    R[6] = c1 * xz - s * y;   R[7] = c1 * yz + s * x;   R[8] = c + c1 * zz;
 }
 
 /* One joint: axis-angle -> Euler XYZ degrees (coord_utils.py:83-95 body).

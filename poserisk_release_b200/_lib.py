@@ -1,0 +1,132 @@
+"""ctypes binding of csrc/libposerisk_b200.so (C ABI: include/poserisk_b200.h).
+
+There is no CPU or PyTorch fallback: if the library is missing the import fails
+loudly (build it with ``python -m poserisk_release_b200.build`` or
+``__graft_entry__.build()``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .build import LIB
+
+PRK_OK = 0
+PRK_SCORE_REBA = 1
+PRK_SCORE_RULA = 2
+PRK_DTYPE_F32 = 0
+PRK_DTYPE_F64 = 1
+PRK_FLAG_JOINTS_ONLY = 1
+
+REBA_KEYS = ("Legs_bilateral_weight_bearing/walking", "Sitting", "Load/Force Score",
+             "Arm_supported_leaning_L", "Arm_supported_leaning_R", "Coupling", "Activity_Score")
+RULA_KEYS = ("Arm_supported_leaning_L", "Arm_supported_leaning_R", "A_Muscle_use_L",
+             "A_Muscle_use_R", "A_Load/Force_L", "A_Load/Force_R",
+             "Legs_bilateral_weight_bearing", "B_Muscle_use", "B_Load/Force")
+
+# struct prk_score_rec (32 bytes)
+REC_DTYPE = np.dtype([('reba_score', '<i2'), ('rula_score', '<i2'), ('reba_parts', 'u1', (9,)),
+                      ('rula_parts', 'u1', (11,)), ('flags', 'u1'), ('pad', 'u1', (7,))])
+assert REC_DTYPE.itemsize == 32
+
+EXPORTS = (
+    'prk_abi_version', 'prk_strerror', 'prk_last_error_detail', 'prk_model_create',
+    'prk_model_destroy', 'prk_model_device', 'prk_model_max_weights', 'prk_workspace_bytes',
+    'prk_smpl_forward', 'prk_score_pose', 'prk_score_euler', 'prk_euler', 'prk_pipeline',
+    'prk_host_workspace_bytes', 'prk_pipeline_host', 'prk_score_histogram', 'prk_debug_blend',
+    'prk_vposed_pitch', 'prk_launch_count', 'prk_profile_begin', 'prk_profile_end')
+
+
+class PoseRiskError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB):
+        raise ImportError(
+            f'{LIB} not found: the CUDA extension is required (no CPU fallback). '
+            'Build it with `python -m poserisk_release_b200.build`.')
+    L = C.CDLL(LIB)
+    vp, i32, i64, u32, sz = C.c_void_p, C.c_int, C.c_int64, C.c_uint32, C.c_size_t
+    L.prk_abi_version.restype = i32
+    L.prk_strerror.restype = C.c_char_p
+    L.prk_strerror.argtypes = [i32]
+    L.prk_last_error_detail.restype = C.c_char_p
+    L.prk_model_create.restype = i32
+    L.prk_model_create.argtypes = [C.POINTER(vp), i32, vp, vp, vp, vp, vp, vp, vp]
+    L.prk_model_destroy.restype = None
+    L.prk_model_destroy.argtypes = [vp]
+    L.prk_model_device.restype = i32
+    L.prk_model_device.argtypes = [vp]
+    L.prk_model_max_weights.restype = i32
+    L.prk_model_max_weights.argtypes = [vp]
+    L.prk_workspace_bytes.restype = sz
+    L.prk_workspace_bytes.argtypes = [vp, i64, u32]
+    L.prk_smpl_forward.restype = i32
+    L.prk_smpl_forward.argtypes = [vp, vp, vp, vp, i32, i64, vp, vp, vp, sz, vp]
+    L.prk_score_pose.restype = i32
+    L.prk_score_pose.argtypes = [vp, i32, vp, vp, i64, u32, vp, vp, vp, i32, vp]
+    L.prk_score_euler.restype = i32
+    L.prk_score_euler.argtypes = [vp, vp, vp, i64, u32, vp, vp]
+    L.prk_euler.restype = i32
+    L.prk_euler.argtypes = [vp, i32, i64, vp, vp, vp]
+    L.prk_pipeline.restype = i32
+    L.prk_pipeline.argtypes = [vp, vp, vp, vp, i32, vp, vp, i64, vp, vp, vp, vp, sz, vp]
+    L.prk_host_workspace_bytes.restype = sz
+    L.prk_host_workspace_bytes.argtypes = [vp, i64, u32]
+    L.prk_pipeline_host.restype = i32
+    L.prk_pipeline_host.argtypes = [vp, vp, vp, vp, i32, vp, i32, vp, i64, vp, vp, vp, vp, sz, vp]
+    L.prk_score_histogram.restype = i32
+    L.prk_score_histogram.argtypes = [vp, i64, u32, vp, vp]
+    L.prk_debug_blend.restype = i32
+    L.prk_debug_blend.argtypes = [vp, vp, vp, i64, vp, i32, vp, sz, vp]
+    L.prk_vposed_pitch.restype = i64
+    L.prk_launch_count.restype = C.c_uint64
+    L.prk_profile_begin.restype = i32
+    L.prk_profile_end.restype = i32
+    L.prk_profile_end.argtypes = [vp, vp]
+    if L.prk_abi_version() != 1:
+        raise ImportError('libposerisk_b200.so ABI version mismatch')
+    _lib = L
+    return L
+
+
+def check(rc: int):
+    if rc != PRK_OK:
+        L = lib()
+        raise PoseRiskError(f'{L.prk_strerror(rc).decode()} ({L.prk_last_error_detail().decode()})')
+
+
+def launch_count() -> int:
+    return int(lib().prk_launch_count())
+
+
+def addinfo_array(add_infos) -> np.ndarray:
+    """dict, or sequence of dicts, in additional_information.json layout -> int32 (T, 16).
+
+    Missing keys raise KeyError exactly where the reference would (reba.py:59 etc.)."""
+    if isinstance(add_infos, dict):
+        add_infos = [add_infos]
+    out = np.zeros((len(add_infos), 16), np.int32)
+    for t, ai in enumerate(add_infos):
+        for k, key in enumerate(REBA_KEYS):
+            out[t, k] = _as_int(ai["REBA"][key], key)
+        for k, key in enumerate(RULA_KEYS):
+            out[t, 7 + k] = _as_int(ai["RULA"][key], key)
+    return out
+
+
+def _as_int(v, key):
+    # the reference accumulates these into int64 numpy arrays (reba.py:123-129): a float
+    # modifier raises a casting error there, so refuse it here too
+    if isinstance(v, (bool, int, np.integer)):
+        return int(v)
+    raise TypeError(f'additional information "{key}" must be an integer, got {type(v).__name__}')

@@ -1,0 +1,573 @@
+// C ABI of libposerisk_b200.so (include/poserisk_b200.h): model packing, workspace
+// layout, chunking and stream ordering of the three kernel stages.
+#include "prk_internal.h"
+
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+namespace prk {
+
+static std::atomic<uint64_t> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+// ---- optional per-stage CUDA-event timing (prk_profile_begin / prk_profile_end) --------
+struct StageTimer {
+    bool on = false;
+    std::vector<cudaEvent_t> pool;      // start/stop pairs
+    std::vector<int> stage;             // stage id of pair i
+    size_t used = 0;                    // pairs in use
+};
+static StageTimer g_timer;
+struct StageScope {
+    cudaStream_t s;
+    long idx = -1;
+    StageScope(int stage_id, cudaStream_t stream) : s(stream) {
+        if (!g_timer.on || g_timer.used >= 65536) return;
+        if (g_timer.used * 2 + 2 > g_timer.pool.size()) {
+            cudaEvent_t a, b;
+            if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+            g_timer.pool.push_back(a); g_timer.pool.push_back(b);
+            g_timer.stage.push_back(stage_id);
+        } else {
+            g_timer.stage[g_timer.used] = stage_id;
+        }
+        idx = (long)g_timer.used++;
+        cudaEventRecord(g_timer.pool[idx * 2], s);
+    }
+    ~StageScope() { if (idx >= 0) cudaEventRecord(g_timer.pool[idx * 2 + 1], s); }
+};
+
+static thread_local char t_detail[256] = "";
+static void set_detail(const char* what, const char* msg) { snprintf(t_detail, sizeof t_detail, "%s: %s", what, msg); }
+
+static int cuda_fail(cudaError_t e, const char* what) {
+    set_detail(what, cudaGetErrorString(e));
+    return PRK_ERR_CUDA;
+}
+#define PRK_CUDA(expr)                                          \
+    do {                                                        \
+        cudaError_t _e = (expr);                                \
+        if (_e != cudaSuccess) return cuda_fail(_e, #expr);     \
+    } while (0)
+
+// ---- TMA descriptor ---------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// [rows][cols] bf16 row-major, box = box_rows x box_cols (box_cols*2 bytes == 128: SWIZZLE_128B)
+int encode_tmap_2d_bf16(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                        uint32_t box_cols) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) { set_detail("cuTensorMapEncodeTiled", "driver entry point not found"); return PRK_ERR_DRIVER; }
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {cols * 2};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(gptr), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char msg[64];
+        snprintf(msg, sizeof msg, "CUresult %d", (int)r);
+        set_detail("cuTensorMapEncodeTiled", msg);
+        return PRK_ERR_DRIVER;
+    }
+    return PRK_OK;
+}
+
+// ---- host-side bf16 helpers --------------------------------------------------
+static uint16_t f2bf(float x) {   // round to nearest even
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    if ((u & 0x7F800000u) == 0x7F800000u) return (uint16_t)(u >> 16);   // inf / nan: truncate
+    u += 0x7FFFu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+static float bf2f(uint16_t b) {
+    uint32_t u = (uint32_t)b << 16;
+    float x;
+    memcpy(&x, &u, 4);
+    return x;
+}
+static void split3(float v, uint16_t& h, uint16_t& m, uint16_t& l) {
+    h = f2bf(v);
+    const float r1 = v - bf2f(h);
+    m = f2bf(r1);
+    l = f2bf(r1 - bf2f(m));
+}
+
+static const int kSmplParents[NJ] = {-1, 0, 0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 9, 9, 12, 13, 14, 16, 17, 18, 19, 20, 21};
+static const int kSmplDfs[NJ] = {0, 1, 4, 7, 10, 2, 5, 8, 11, 3, 6, 9, 12, 15, 13, 16, 18, 20, 22, 14, 17, 19, 21, 23};
+
+static int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+// ---- workspace layout ---------------------------------------------------------
+constexpr int64_t kMaxSuper = 16384;   // frames per pose-chain launch (A' + Askin scratch)
+static int64_t chunk_frames() {        // frames per GEMM+skin step: keeps v_posed L2-resident
+    static int64_t v = 0;
+    if (v == 0) {
+        v = 640;
+        if (const char* e = getenv("PRK_CHUNK_FRAMES")) { long t = atol(e); if (t >= 128) v = t; }
+        v = round_up(v, GEMM_BM);
+    }
+    return v;
+}
+
+struct Layout {
+    int64_t S = 0, C = 0;   // super-chunk and chunk frames (multiples of 128)
+    size_t off_flags = 0, off_arows = 0, off_askin = 0, off_off = 0, off_vposed = 0, total = 0;
+};
+static size_t align_up(size_t x) { return (x + 1023) & ~(size_t)1023; }
+
+static Layout make_layout(int64_t S, int64_t C, bool mesh) {
+    Layout L;
+    L.S = S; L.C = C;
+    size_t o = 0;
+    L.off_flags = o; o += 1024;
+    if (mesh) {
+        L.off_arows = o;  o += align_up((size_t)S * GEMM_K * 2);
+        L.off_askin = o;  o += align_up((size_t)S * NJ * 12 * 4);
+        L.off_off = o;    o += align_up((size_t)S * 3 * 4);
+        L.off_vposed = o; o += align_up((size_t)C * VPOSED_PITCH * 4);
+    }
+    L.total = o;
+    return L;
+}
+static Layout want_layout(int64_t B, bool mesh) {
+    int64_t S = round_up(B < 1 ? 1 : B, GEMM_BM);
+    if (S > kMaxSuper) S = kMaxSuper;
+    int64_t C = chunk_frames();
+    if (C > S) C = S;
+    return make_layout(S, C, mesh);
+}
+// largest layout that fits in `bytes`: shrink the super-chunk first, then the chunk
+static bool fit_layout(int64_t B, bool mesh, size_t bytes, Layout& L) {
+    L = want_layout(B, mesh);
+    int64_t S = L.S, C = L.C;
+    while (make_layout(S, C, mesh).total > bytes) {
+        if (S > C) { S = round_up(S / 2, GEMM_BM); if (S < C) S = C; }
+        else if (C > GEMM_BM) { C = round_up(C / 2, GEMM_BM); S = C; }
+        else return false;
+    }
+    L = make_layout(S, C, mesh);
+    return true;
+}
+
+static int forward_impl(Model* m, const float* d_pose, const float* d_betas, const float* d_trans, int center_idx,
+                        int64_t B, float* d_verts, float* d_joints, void* ws, size_t ws_bytes, cudaStream_t s) {
+    if (!m || B < 0 || (B > 0 && (!d_pose || !d_joints)) || center_idx >= NJ) {
+        set_detail("prk_smpl_forward", "invalid argument");
+        return PRK_ERR_INVALID_ARG;
+    }
+    if (B == 0) return PRK_OK;
+    const bool mesh = d_verts != nullptr;
+    if (!ws || (reinterpret_cast<uintptr_t>(ws) & 1023)) {
+        set_detail("prk_smpl_forward", "workspace missing or not 1024-byte aligned");
+        return PRK_ERR_WORKSPACE;
+    }
+    Layout L;
+    if (!fit_layout(B, mesh, ws_bytes, L)) { set_detail("prk_smpl_forward", "workspace too small"); return PRK_ERR_WORKSPACE; }
+    uint8_t* w = static_cast<uint8_t*>(ws);
+    BatchFlags* d_flags = reinterpret_cast<BatchFlags*>(w + L.off_flags);
+    uint16_t* d_arows = reinterpret_cast<uint16_t*>(w + L.off_arows);
+    float* d_askin = reinterpret_cast<float*>(w + L.off_askin);
+    float* d_off = reinterpret_cast<float*>(w + L.off_off);
+    float* d_vposed = reinterpret_cast<float*>(w + L.off_vposed);
+
+    if (pose_chain_needs_flags(*m, d_betas, d_trans, center_idx)) PRK_CUDA(launch_batch_flags(d_betas, d_trans, B, d_flags, s));
+
+    const int64_t S = mesh ? L.S : B;   // the joints-only path needs no scratch: one launch
+    for (int64_t s0 = 0; s0 < B; s0 += S) {
+        const int64_t ns = (B - s0) < S ? (B - s0) : S;
+        {
+            StageScope sc(0, s);
+            PRK_CUDA(launch_pose_chain(*m, d_pose + s0 * 72, d_betas ? d_betas + s0 * NBETA : nullptr,
+                                       d_trans ? d_trans + s0 * 3 : nullptr, d_flags, center_idx, ns, mesh, d_arows,
+                                       d_askin, d_off, d_joints + s0 * 72, s));
+        }
+        if (!mesh) continue;
+        for (int64_t c0 = 0; c0 < ns; c0 += L.C) {
+            const int64_t nc = (ns - c0) < L.C ? (ns - c0) : L.C;
+            const int64_t rows_pad = round_up(nc, GEMM_BM);
+            CUtensorMap tmA;
+            int rc = encode_tmap_2d_bf16(&tmA, d_arows + c0 * GEMM_K, (uint64_t)rows_pad, GEMM_K, GEMM_BM, GEMM_BK);
+            if (rc != PRK_OK) return rc;
+            {
+                StageScope sc(1, s);
+                PRK_CUDA(launch_blend_gemm(*m, tmA, rows_pad, d_vposed, s));
+            }
+            {
+                StageScope sc(2, s);
+                PRK_CUDA(launch_skin(*m, d_vposed, d_askin + c0 * NJ * 12, d_off + c0 * 3, nc,
+                                     d_verts + (size_t)(s0 + c0) * NVC, s));
+            }
+        }
+    }
+    return PRK_OK;
+}
+
+}  // namespace prk
+
+using namespace prk;
+
+extern "C" {
+
+int prk_abi_version(void) { return PRK_ABI_VERSION; }
+
+const char* prk_strerror(int status) {
+    switch (status) {
+        case PRK_OK: return "ok";
+        case PRK_ERR_INVALID_ARG: return "invalid argument";
+        case PRK_ERR_CUDA: return "CUDA error";
+        case PRK_ERR_WORKSPACE: return "workspace too small or misaligned";
+        case PRK_ERR_UNSUPPORTED: return "unsupported configuration";
+        case PRK_ERR_DRIVER: return "CUDA driver entry point unavailable or failed";
+        default: return "unknown status";
+    }
+}
+const char* prk_last_error_detail(void) { return t_detail; }
+uint64_t prk_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+int64_t prk_vposed_pitch(void) { return VPOSED_PITCH; }
+
+int prk_model_create(prk_model** out, int device, const float* vt, const float* sd, const float* pd, const float* jr,
+                     const float* wt, const int32_t* parents, const float* betas) {
+    if (!out || !vt || !sd || !pd || !jr || !wt || !parents) { set_detail("prk_model_create", "null argument"); return PRK_ERR_INVALID_ARG; }
+    *out = nullptr;
+    PRK_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    PRK_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_detail("prk_model_create", "this library is built for sm_100a (B200) only");
+        return PRK_ERR_UNSUPPORTED;
+    }
+    Model* m = new (std::nothrow) Model();
+    if (!m) return PRK_ERR_INVALID_ARG;
+    m->device = device;
+    m->sm_count = prop.multiProcessorCount;
+
+    // kinematic tree
+    bool std_tree = true;
+    m->pc.parents[0] = -1;
+    for (int j = 1; j < NJ; ++j) {
+        if (parents[j] < 0 || parents[j] >= j) {   // parents must precede children (smpl_layer.py:109-119)
+            delete m;
+            set_detail("prk_model_create", "kintree parent must have a smaller index than its child");
+            return PRK_ERR_INVALID_ARG;
+        }
+        m->pc.parents[j] = parents[j];
+        std_tree &= (parents[j] == kSmplParents[j]);
+    }
+    m->pc.standard_tree = std_tree ? 1 : 0;
+    for (int k = 0; k < NBETA; ++k) m->pc.model_betas[k] = betas ? betas[k] : 0.0f;
+
+    // folded joint regressor (double accumulation)
+    for (int j = 0; j < NJ; ++j)
+        for (int c = 0; c < 3; ++c) {
+            double a = 0.0, d[NBETA] = {0};
+            for (int v = 0; v < NV; ++v) {
+                const double r = jr[(size_t)j * NV + v];
+                if (r == 0.0) continue;
+                a += r * vt[v * 3 + c];
+                for (int k = 0; k < NBETA; ++k) d[k] += r * sd[((size_t)v * 3 + c) * NBETA + k];
+            }
+            m->pc.J_template[j * 3 + c] = (float)a;
+            for (int k = 0; k < NBETA; ++k) m->pc.Jdirs[(j * 3 + c) * NBETA + k] = (float)d[k];
+        }
+
+    // split-precision blend operand B' [GEMM_N][GEMM_K]
+    std::vector<uint16_t> Bm((size_t)GEMM_N * GEMM_K, 0);
+    for (int n = 0; n < NVC; ++n) {
+        uint16_t* row = &Bm[(size_t)n * GEMM_K];
+        for (int pos = 1; pos < NJ; ++pos) {
+            const int j = std_tree ? kSmplDfs[pos] : pos;
+            const int base = 27 * (pos - 1);
+            for (int e = 0; e < 9; ++e) {
+                const float v = pd[(size_t)n * NPOSE + (j - 1) * 9 + e];
+                const uint16_t hi = f2bf(v), lo = f2bf(v - bf2f(hi));
+                row[base + e] = hi; row[base + 9 + e] = lo; row[base + 18 + e] = hi;
+            }
+        }
+        for (int b = 0; b < NBETA; ++b) {
+            uint16_t h, mm, l;
+            split3(sd[(size_t)n * NBETA + b], h, mm, l);
+            uint16_t* c = row + COL_BETA0 + 6 * b;
+            c[0] = h; c[1] = mm; c[2] = h; c[3] = l; c[4] = mm; c[5] = h;
+        }
+        uint16_t h, mm, l;
+        split3(vt[n], h, mm, l);
+        row[COL_ONES] = h; row[COL_ONES + 1] = mm; row[COL_ONES + 2] = l;
+    }
+
+    // compacted skinning weights
+    int mx = 0;
+    for (int v = 0; v < NV; ++v) {
+        int c = 0;
+        for (int j = 0; j < NJ; ++j) c += wt[(size_t)v * NJ + j] != 0.0f;
+        if (c > mx) mx = c;
+    }
+    m->max_weights = mx;
+    m->nnz_groups = mx <= 4 ? 1 : (mx + 3) / 4;
+    std::vector<float4> wv((size_t)m->nnz_groups * NV, make_float4(0, 0, 0, 0));
+    std::vector<uint32_t> wi((size_t)m->nnz_groups * NV, 0);
+    for (int v = 0; v < NV; ++v) {
+        int c = 0;
+        for (int j = 0; j < NJ; ++j) {
+            const float x = wt[(size_t)v * NJ + j];
+            if (x == 0.0f) continue;
+            const int g = c >> 2, k = c & 3;
+            float* f = reinterpret_cast<float*>(&wv[(size_t)g * NV + v]);
+            f[k] = x;
+            wi[(size_t)g * NV + v] |= (uint32_t)j << (8 * k);
+            ++c;
+        }
+    }
+
+    cudaError_t e;
+#define PRK_M(expr) do { e = (expr); if (e != cudaSuccess) { prk_model_destroy(m); return cuda_fail(e, #expr); } } while (0)
+    PRK_M(cudaMalloc(&m->d_Bmat, Bm.size() * 2));
+    PRK_M(cudaMemcpy(m->d_Bmat, Bm.data(), Bm.size() * 2, cudaMemcpyHostToDevice));
+    PRK_M(cudaMalloc(&m->d_wval, wv.size() * sizeof(float4)));
+    PRK_M(cudaMemcpy(m->d_wval, wv.data(), wv.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    PRK_M(cudaMalloc(&m->d_widx, wi.size() * 4));
+    PRK_M(cudaMemcpy(m->d_widx, wi.data(), wi.size() * 4, cudaMemcpyHostToDevice));
+#undef PRK_M
+    int rc = encode_tmap_2d_bf16(&m->tmap_B, m->d_Bmat, GEMM_N, GEMM_K, GEMM_BN, GEMM_BK);
+    if (rc != PRK_OK) { prk_model_destroy(m); return rc; }
+    *out = m;
+    return PRK_OK;
+}
+
+void prk_model_destroy(prk_model* model) {
+    Model* m = model;
+    if (!m) return;
+    if (m->device >= 0) cudaSetDevice(m->device);
+    cudaFree(m->d_Bmat); cudaFree(m->d_wval); cudaFree(m->d_widx);
+    delete m;
+}
+int prk_model_device(const prk_model* model) { return model ? model->device : -1; }
+int prk_model_max_weights(const prk_model* model) { return model ? model->max_weights : 0; }
+
+size_t prk_workspace_bytes(const prk_model*, int64_t B, uint32_t flags) {
+    return want_layout(B, !(flags & PRK_FLAG_JOINTS_ONLY)).total;
+}
+
+int prk_smpl_forward(prk_model* model, const float* d_pose, const float* d_betas, const float* d_trans,
+                     int center_idx, int64_t B, float* d_verts, float* d_joints, void* ws, size_t ws_bytes,
+                     void* stream) {
+    Model* m = model;
+    if (!m) { set_detail("prk_smpl_forward", "null model"); return PRK_ERR_INVALID_ARG; }
+    PRK_CUDA(cudaSetDevice(m->device));
+    return forward_impl(m, d_pose, d_betas, d_trans, center_idx, B, d_verts, d_joints, ws, ws_bytes,
+                        static_cast<cudaStream_t>(stream));
+}
+
+int prk_score_pose(const void* d_pose, int pose_dtype, const prk_addinfo* d_info, const int32_t* d_track, int64_t B,
+                   uint32_t which, prk_score_rec* d_out, double* d_euler_out, const int32_t* h_debug_joint_ids,
+                   int n_debug, void* stream) {
+    if (B < 0 || (B > 0 && (!d_pose || !d_info || !d_out)) || (pose_dtype != PRK_DTYPE_F32 && pose_dtype != PRK_DTYPE_F64) ||
+        !(which & 3u) || n_debug < 0 || n_debug > NJ || (n_debug > 0 && (!d_euler_out || !h_debug_joint_ids))) {
+        set_detail("prk_score_pose", "invalid argument");
+        return PRK_ERR_INVALID_ARG;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    uint32_t mask = 0;
+    int8_t slot[NJ];
+    for (int j = 0; j < NJ; ++j) slot[j] = -1;
+    for (int k = 0; k < n_debug; ++k) {
+        const int j = h_debug_joint_ids[k];
+        if (j < 0 || j >= NJ || (mask & (1u << j))) { set_detail("prk_score_pose", "bad or duplicate debug joint id"); return PRK_ERR_INVALID_ARG; }
+        mask |= 1u << j;
+        slot[j] = (int8_t)k;
+    }
+    int8_t* d_slot = nullptr;
+    if (n_debug > 0) {   // 24-byte table, stream-ordered allocation (debug path only)
+        PRK_CUDA(cudaMallocAsync(&d_slot, NJ, s));
+        PRK_CUDA(cudaMemcpyAsync(d_slot, slot, NJ, cudaMemcpyHostToDevice, s));
+        PRK_CUDA(cudaStreamSynchronize(s));   // `slot` is a stack buffer
+    }
+    cudaError_t e = launch_score_pose(d_pose, pose_dtype, d_info, d_track, B, which, d_out,
+                                      n_debug > 0 ? d_euler_out : nullptr, mask, d_slot, n_debug, s);
+    if (d_slot) cudaFreeAsync(d_slot, s);
+    if (e != cudaSuccess) return cuda_fail(e, "score_pose_kernel");
+    return PRK_OK;
+}
+
+int prk_score_euler(const double* d_euler, const prk_addinfo* d_info, const int32_t* d_track, int64_t B,
+                    uint32_t which, prk_score_rec* d_out, void* stream) {
+    if (B < 0 || (B > 0 && (!d_euler || !d_info || !d_out)) || !(which & 3u)) {
+        set_detail("prk_score_euler", "invalid argument");
+        return PRK_ERR_INVALID_ARG;
+    }
+    PRK_CUDA(launch_score_euler(d_euler, d_info, d_track, B, which, d_out, static_cast<cudaStream_t>(stream)));
+    return PRK_OK;
+}
+
+int prk_euler(const void* d_pose, int pose_dtype, int64_t n_rot, double* d_euler, uint8_t* d_bad, void* stream) {
+    if (n_rot < 0 || (n_rot > 0 && (!d_pose || !d_euler)) || (pose_dtype != PRK_DTYPE_F32 && pose_dtype != PRK_DTYPE_F64)) {
+        set_detail("prk_euler", "invalid argument");
+        return PRK_ERR_INVALID_ARG;
+    }
+    PRK_CUDA(launch_euler(d_pose, pose_dtype, n_rot, d_euler, d_bad, static_cast<cudaStream_t>(stream)));
+    return PRK_OK;
+}
+
+int prk_pipeline(prk_model* model, const float* d_pose, const float* d_betas, const float* d_trans, int center_idx,
+                 const prk_addinfo* d_info, const int32_t* d_track, int64_t B, float* d_verts, float* d_joints,
+                 prk_score_rec* d_scores, void* ws, size_t ws_bytes, void* stream) {
+    Model* m = model;
+    if (!m || !d_info || (B > 0 && !d_scores)) { set_detail("prk_pipeline", "invalid argument"); return PRK_ERR_INVALID_ARG; }
+    PRK_CUDA(cudaSetDevice(m->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int rc = forward_impl(m, d_pose, d_betas, d_trans, center_idx, B, d_verts, d_joints, ws, ws_bytes, s);
+    if (rc != PRK_OK) return rc;
+    {
+        StageScope sc(3, s);
+        PRK_CUDA(launch_score_pose(d_pose, PRK_DTYPE_F32, d_info, d_track, B, PRK_SCORE_REBA | PRK_SCORE_RULA, d_scores,
+                                   nullptr, 0, nullptr, 0, s));
+    }
+    return PRK_OK;
+}
+
+// host-staging layout in front of the device workspace
+struct HostStage { size_t pose, betas, trans, info, track, joints, scores, inner, total; };
+static HostStage host_stage(int64_t B, int32_t n_tracks, size_t inner_bytes) {
+    HostStage h;
+    size_t o = 0;
+    h.pose = o;   o += align_up((size_t)B * 72 * 4);
+    h.betas = o;  o += align_up((size_t)B * NBETA * 4);
+    h.trans = o;  o += align_up((size_t)B * 3 * 4);
+    h.info = o;   o += align_up((size_t)(n_tracks < 1 ? 1 : n_tracks) * sizeof(prk_addinfo));
+    h.track = o;  o += align_up((size_t)B * 4);
+    h.joints = o; o += align_up((size_t)B * 72 * 4);
+    h.scores = o; o += align_up((size_t)B * sizeof(prk_score_rec));
+    h.inner = o;  o += inner_bytes;
+    h.total = o;
+    return h;
+}
+
+size_t prk_host_workspace_bytes(const prk_model* model, int64_t B, uint32_t flags) {
+    // room for up to 4096 tracks of add_info
+    return host_stage(B, 4096, prk_workspace_bytes(model, B, flags)).total;
+}
+
+int prk_pipeline_host(prk_model* model, const float* h_pose, const float* h_betas, const float* h_trans,
+                      int center_idx, const prk_addinfo* h_info, int32_t n_tracks, const int32_t* h_track, int64_t B,
+                      float* d_verts, float* h_joints, prk_score_rec* h_scores, void* ws, size_t ws_bytes,
+                      void* stream) {
+    Model* m = model;
+    if (!m || B < 0 || !h_info || n_tracks < 1 || n_tracks > 4096 || (B > 0 && (!h_pose || !h_scores))) {
+        set_detail("prk_pipeline_host", "invalid argument");
+        return PRK_ERR_INVALID_ARG;
+    }
+    if (B == 0) return PRK_OK;
+    if (!ws || (reinterpret_cast<uintptr_t>(ws) & 1023)) { set_detail("prk_pipeline_host", "workspace missing or misaligned"); return PRK_ERR_WORKSPACE; }
+    PRK_CUDA(cudaSetDevice(m->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const HostStage h = host_stage(B, 4096, 0);
+    if (ws_bytes <= h.inner) { set_detail("prk_pipeline_host", "workspace too small"); return PRK_ERR_WORKSPACE; }
+    uint8_t* w = static_cast<uint8_t*>(ws);
+    float* d_pose = reinterpret_cast<float*>(w + h.pose);
+    float* d_betas = h_betas ? reinterpret_cast<float*>(w + h.betas) : nullptr;
+    float* d_trans = h_trans ? reinterpret_cast<float*>(w + h.trans) : nullptr;
+    prk_addinfo* d_info = reinterpret_cast<prk_addinfo*>(w + h.info);
+    int32_t* d_track = h_track ? reinterpret_cast<int32_t*>(w + h.track) : nullptr;
+    float* d_joints = reinterpret_cast<float*>(w + h.joints);
+    prk_score_rec* d_scores = reinterpret_cast<prk_score_rec*>(w + h.scores);
+    PRK_CUDA(cudaMemcpyAsync(d_pose, h_pose, (size_t)B * 72 * 4, cudaMemcpyHostToDevice, s));
+    if (h_betas) PRK_CUDA(cudaMemcpyAsync(d_betas, h_betas, (size_t)B * NBETA * 4, cudaMemcpyHostToDevice, s));
+    if (h_trans) PRK_CUDA(cudaMemcpyAsync(d_trans, h_trans, (size_t)B * 3 * 4, cudaMemcpyHostToDevice, s));
+    PRK_CUDA(cudaMemcpyAsync(d_info, h_info, (size_t)n_tracks * sizeof(prk_addinfo), cudaMemcpyHostToDevice, s));
+    if (h_track) PRK_CUDA(cudaMemcpyAsync(d_track, h_track, (size_t)B * 4, cudaMemcpyHostToDevice, s));
+    int rc = prk_pipeline(model, d_pose, d_betas, d_trans, center_idx, d_info, d_track, B, d_verts, d_joints, d_scores,
+                          w + h.inner, ws_bytes - h.inner, stream);
+    if (rc != PRK_OK) return rc;
+    if (h_joints) PRK_CUDA(cudaMemcpyAsync(h_joints, d_joints, (size_t)B * 72 * 4, cudaMemcpyDeviceToHost, s));
+    PRK_CUDA(cudaMemcpyAsync(h_scores, d_scores, (size_t)B * sizeof(prk_score_rec), cudaMemcpyDeviceToHost, s));
+    return PRK_OK;
+}
+
+int prk_score_histogram(const prk_score_rec* d_scores, int64_t B, uint32_t which, unsigned long long* d_hist,
+                        void* stream) {
+    if (B < 0 || !d_hist || (B > 0 && !d_scores) || (which != PRK_SCORE_REBA && which != PRK_SCORE_RULA)) {
+        set_detail("prk_score_histogram", "invalid argument");
+        return PRK_ERR_INVALID_ARG;
+    }
+    PRK_CUDA(launch_score_hist(d_scores, B, which, d_hist, static_cast<cudaStream_t>(stream)));
+    return PRK_OK;
+}
+
+int prk_profile_begin(void) {
+    g_timer.on = true;
+    g_timer.used = 0;
+    return PRK_OK;
+}
+
+int prk_profile_end(double* ms_out, int64_t* launches_out) {
+    g_timer.on = false;
+    for (int k = 0; k < 4; ++k) { if (ms_out) ms_out[k] = 0.0; if (launches_out) launches_out[k] = 0; }
+    for (size_t i = 0; i < g_timer.used; ++i) {
+        PRK_CUDA(cudaEventSynchronize(g_timer.pool[i * 2 + 1]));
+        float ms = 0.f;
+        PRK_CUDA(cudaEventElapsedTime(&ms, g_timer.pool[i * 2], g_timer.pool[i * 2 + 1]));
+        const int st = g_timer.stage[i];
+        if (st >= 0 && st < 4) { if (ms_out) ms_out[st] += ms; if (launches_out) launches_out[st] += 1; }
+    }
+    g_timer.used = 0;
+    return PRK_OK;
+}
+
+int prk_debug_blend(prk_model* model, const float* d_pose, const float* d_betas, int64_t B, float* d_vposed,
+                    int use_simt, void* ws, size_t ws_bytes, void* stream) {
+    Model* m = model;
+    if (!m || B <= 0 || !d_pose || !d_vposed || !ws) { set_detail("prk_debug_blend", "invalid argument"); return PRK_ERR_INVALID_ARG; }
+    PRK_CUDA(cudaSetDevice(m->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int64_t rows_pad = round_up(B, GEMM_BM);
+    // scratch: A' rows, Askin, off, joints (the caller's d_vposed must hold rows_pad rows)
+    size_t o = 0;
+    const size_t o_arows = o; o += align_up((size_t)rows_pad * GEMM_K * 2);
+    const size_t o_askin = o; o += align_up((size_t)rows_pad * NJ * 12 * 4);
+    const size_t o_off = o;   o += align_up((size_t)rows_pad * 3 * 4);
+    const size_t o_j = o;     o += align_up((size_t)rows_pad * 72 * 4);
+    const size_t o_flags = o; o += 1024;
+    if (o > ws_bytes || (reinterpret_cast<uintptr_t>(ws) & 1023)) { set_detail("prk_debug_blend", "workspace too small or misaligned"); return PRK_ERR_WORKSPACE; }
+    uint8_t* w = static_cast<uint8_t*>(ws);
+    uint16_t* d_arows = reinterpret_cast<uint16_t*>(w + o_arows);
+    BatchFlags* d_flags = reinterpret_cast<BatchFlags*>(w + o_flags);
+    PRK_CUDA(cudaMemsetAsync(d_arows, 0, (size_t)rows_pad * GEMM_K * 2, s));
+    if (pose_chain_needs_flags(*m, d_betas, nullptr, -1)) PRK_CUDA(launch_batch_flags(d_betas, nullptr, B, d_flags, s));
+    PRK_CUDA(launch_pose_chain(*m, d_pose, d_betas, nullptr, d_flags, -1, B, true, d_arows,
+                               reinterpret_cast<float*>(w + o_askin), reinterpret_cast<float*>(w + o_off),
+                               reinterpret_cast<float*>(w + o_j), s));
+    if (use_simt) {
+        PRK_CUDA(launch_blend_simt(*m, d_arows, rows_pad, d_vposed, s));
+    } else {
+        CUtensorMap tmA;
+        int rc = encode_tmap_2d_bf16(&tmA, d_arows, (uint64_t)rows_pad, GEMM_K, GEMM_BM, GEMM_BK);
+        if (rc != PRK_OK) return rc;
+        PRK_CUDA(launch_blend_gemm(*m, tmA, rows_pad, d_vposed, s));
+    }
+    return PRK_OK;
+}
+
+}  // extern "C"

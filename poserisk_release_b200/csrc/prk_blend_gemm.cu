@@ -1,0 +1,284 @@
+// K1: shape + pose blend shapes as one tcgen05 / TMA GEMM.
+//
+// Reference behaviour (lib/smplpytorch/smplpytorch/pytorch/smpl_layer.py:93-99):
+//   v_shaped = v_template + shapedirs @ betas
+//   v_posed  = v_shaped  + posedirs  @ (R_1..23 - I)
+// restated as  v_posed[frame][vc] = sum_k A'[frame][k] * B'[vc][k]  with K = 704 bf16
+// columns that carry hi/lo splits of every factor (prk_internal.h), so the fp32
+// accumulator in tensor memory reproduces the fp32 reference to ~1e-7 relative.
+//
+// Kernel shape (persistent, one CTA per SM, 192 threads):
+//   warp 0      TMA producer: A' tile 128x64 and B' tile 256x64 (128B swizzle) per k-block,
+//               4-stage mbarrier ring
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (M=128, N=256, K=16 x4 per
+//               k-block), accumulators double-buffered in TMEM (2 x 256 columns)
+//   warps 2-5   epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> 16-byte global
+//               stores of fp32 v_posed rows (row pitch 20736 floats)
+// Roofline: tensor pipe.  Algorithmic work 2*217*20670 = 8.97 MFLOP/frame; executed MMA
+// work 2*704*20736 = 29.2 MFLOP/frame (split precision x padding).
+#include "prk_internal.h"
+
+#include <cuda_bf16.h>
+
+namespace prk {
+
+namespace {
+
+constexpr int kStages = 4;
+constexpr int kATileBytes = GEMM_BM * GEMM_BK * 2;   // 16 KB
+constexpr int kBTileBytes = GEMM_BN * GEMM_BK * 2;   // 32 KB
+constexpr int kStageBytes = kATileBytes + kBTileBytes;
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int kThreads = 192;
+constexpr uint32_t kTmemCols = 512;
+constexpr int kUmmaK = 16;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Bounded wait: a protocol bug must trap after ~4 s, never hang the GPU.
+__device__ __forceinline__ uint64_t global_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    uint64_t t0 = 0;
+    for (uint32_t spin = 0;; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return;
+        if ((spin & 0xFF) == 0xFF) {
+            const uint64_t now = global_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000ull) __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, kind::f16 (bf16 inputs, fp32 accumulate)
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// K-major, 128-byte swizzle, rows of 64 bf16: 8-row atoms 1024 B apart (SBO), LBO unused.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);          // start address  [0,14)
+    d |= (uint64_t)1 << 16;                             // leading byte offset (ignored for SW128 K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset [32,46)
+    d |= (uint64_t)1 << 46;                             // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
+    return d;
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=256
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__global__ void __launch_bounds__(kThreads, 1)
+blend_gemm_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid_constant__ CUtensorMap tmap_B,
+                  float* __restrict__ vposed, int num_m_blocks, int num_tiles) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+    uint64_t* full_bar = bars;                 // [kStages]
+    uint64_t* empty_bar = bars + kStages;      // [kStages]
+    uint64_t* tfull_bar = bars + 2 * kStages;  // [2]
+    uint64_t* tempty_bar = tfull_bar + 2;      // [2]
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_A)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_B)) : "memory");
+        for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {   // TMEM allocation (whole warp), 512 columns = two 128x256 fp32 accumulators
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)),
+                     "r"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m_blk = tile % num_m_blocks, n_blk = tile / num_m_blocks;
+                for (int kb = 0; kb < GEMM_KBLOCKS; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * kStageBytes;
+                    mbar_expect_tx(&full_bar[stage], kStageBytes);
+                    tma_load_2d(&tmap_A, &full_bar[stage], sa, kb * GEMM_BK, m_blk * GEMM_BM);
+                    tma_load_2d(&tmap_B, &full_bar[stage], sa + kATileBytes, kb * GEMM_BK, n_blk * GEMM_BN);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one elected lane) =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(GEMM_BM, GEMM_BN);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);     // epilogue drained this accumulator
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)acc * GEMM_BN;
+                for (int kb = 0; kb < GEMM_KBLOCKS; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);          // TMA bytes landed
+                    tcgen05_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+                    const uint64_t adesc = make_smem_desc(sa);
+                    const uint64_t bdesc = make_smem_desc(sa + kATileBytes);
+#pragma unroll
+                    for (int k = 0; k < GEMM_BK / kUmmaK; ++k) {
+                        // advance 16 bf16 = 32 bytes inside the swizzle row: +2 in the encoded address
+                        umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                                  (uint32_t)((kb | k) != 0));
+                    }
+                    tcgen05_commit(&empty_bar[stage]);           // frees the smem slot when MMAs retire
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+                tcgen05_commit(&tfull_bar[acc]);                 // accumulator complete
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===== epilogue: TMEM -> registers -> global (warps 2..5 own lane quarters 2,3,0,1) =====
+        const int quarter = warp & 3;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m_blk = tile % num_m_blocks, n_blk = tile / num_m_blocks;
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tcgen05_fence_after();
+            const int row = m_blk * GEMM_BM + quarter * 32 + lane;
+            float* dst = vposed + (size_t)row * VPOSED_PITCH + (size_t)n_blk * GEMM_BN;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * GEMM_BN;
+#pragma unroll 1
+            for (int c = 0; c < GEMM_BN / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld_32x32(taddr + (uint32_t)c * 32, r);
+                tmem_ld_wait();
+                float4* d4 = reinterpret_cast<float4*>(dst + c * 32);
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    d4[q] = make_float4(__uint_as_float(r[4 * q + 0]), __uint_as_float(r[4 * q + 1]),
+                                        __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+// Verification only: same bf16 operands, plain FFMA accumulation (prk_debug_blend use_simt=1).
+__global__ void __launch_bounds__(256)
+blend_simt_kernel(const uint16_t* __restrict__ Arows, const uint16_t* __restrict__ Bmat, int64_t rows,
+                  float* __restrict__ vposed) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;   // vertex coordinate
+    const int64_t f = blockIdx.y;
+    if (n >= GEMM_N || f >= rows) return;
+    const uint16_t* a = Arows + f * GEMM_K;
+    const uint16_t* b = Bmat + (size_t)n * GEMM_K;
+    float acc = 0.f;
+    for (int k = 0; k < GEMM_K; ++k)
+        acc = fmaf(__uint_as_float((uint32_t)a[k] << 16), __uint_as_float((uint32_t)b[k] << 16), acc);
+    vposed[f * VPOSED_PITCH + n] = acc;
+}
+
+}  // namespace
+
+cudaError_t launch_blend_gemm(const Model& m, const CUtensorMap& tmap_A, int64_t rows_pad, float* d_vposed,
+                              cudaStream_t s) {
+    if (rows_pad == 0) return cudaSuccess;
+    static bool attr_set[64] = {};
+    if (m.device >= 0 && m.device < 64 && !attr_set[m.device]) {
+        cudaError_t e = cudaFuncSetAttribute(blend_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (e != cudaSuccess) return e;
+        attr_set[m.device] = true;
+    }
+    const int num_m_blocks = (int)(rows_pad / GEMM_BM);
+    const int num_tiles = num_m_blocks * GEMM_NBLOCKS;
+    int grid = m.sm_count > 0 ? m.sm_count : 148;
+    if (grid > num_tiles) grid = num_tiles;
+    blend_gemm_kernel<<<grid, kThreads, kSmemBytes, s>>>(tmap_A, m.tmap_B, d_vposed, num_m_blocks, num_tiles);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_blend_simt(const Model& m, const uint16_t* d_Arows, int64_t rows, float* d_vposed,
+                              cudaStream_t s) {
+    if (rows == 0) return cudaSuccess;
+    dim3 grid((GEMM_N + 255) / 256, (unsigned)rows);
+    blend_simt_kernel<<<grid, 256, 0, s>>>(d_Arows, m.d_Bmat, rows, d_vposed);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace prk

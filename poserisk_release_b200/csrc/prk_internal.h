@@ -1,0 +1,112 @@
+// Internal declarations shared by the translation units of libposerisk_b200.so.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <stdint.h>
+
+#include "../../include/poserisk_b200.h"
+
+namespace prk {
+
+constexpr int NV = PRK_NUM_VERTS;       // 6890
+constexpr int NJ = PRK_NUM_JOINTS;      // 24
+constexpr int NBETA = PRK_NUM_BETAS;    // 10
+constexpr int NPOSE = PRK_NUM_POSE_FEATS;  // 207
+constexpr int NVC = NV * 3;             // 20670 vertex coordinates
+
+// ---- blend GEMM geometry (DESIGN.md "K1") ---------------------------------
+// D[frame][vc] = sum_k A'[frame][k] * B'[vc][k], bf16 x bf16 -> fp32 (tcgen05 kind::f16).
+// fp32-class accuracy comes from split precision along K:
+//   pose feature p = 9*jj+e (jj = joint-1):  cols 27*jj + {e, 9+e, 18+e} = A:{hi,hi,lo} x B:{hi,lo,hi}
+//   beta b:  cols 621+6b+{0..5} = A:{h,h,m,h,m,l} x B:{h,m,h,l,m,h}   (3-way split, 6 products)
+//   template: cols 681..683 = A:{1,1,1} x B:{h,m,l}                   (exact fp32 v_template)
+//   cols 684..703 zero.
+constexpr int GEMM_K = 704;             // 11 k-blocks of 64 bf16 (128-byte swizzle rows)
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_KBLOCKS = GEMM_K / GEMM_BK;
+constexpr int GEMM_BM = 128;            // frames per tile (TMEM lanes)
+constexpr int GEMM_BN = 256;            // vertex coordinates per tile (TMEM columns)
+constexpr int GEMM_N = 20736;           // 20670 padded to 81 * 256
+constexpr int GEMM_NBLOCKS = GEMM_N / GEMM_BN;
+constexpr int COL_BETA0 = 621;
+constexpr int COL_ONES = 681;
+constexpr int VPOSED_PITCH = GEMM_N;    // floats per frame row of the v_posed scratch
+
+// Rest joints as an affine function of betas: J = J_template + Jdirs * beta
+// (folds J_regressor @ (v_template + shapedirs beta), smpl_layer.py:91,95).
+struct PoseConsts {
+    float J_template[NJ * 3];
+    float Jdirs[NJ * 3 * NBETA];   // [joint*3+c][beta]
+    float model_betas[NBETA];
+    int32_t parents[NJ];
+    int32_t standard_tree;         // 1: parents == SMPL kintree (static unroll path)
+};
+
+}  // namespace prk
+
+// The opaque handle of the C ABI.
+struct prk_model {
+    int device = -1;
+    int sm_count = 0;
+    int nnz_groups = 1;            // ceil(max non-zero weights per vertex / 4)
+    int max_weights = 0;
+    prk::PoseConsts pc;                 // host copy, passed by value to the pose kernel
+    // device buffers
+    uint16_t* d_Bmat = nullptr;    // [GEMM_N][GEMM_K] bf16 bits, K-major
+    float4* d_wval = nullptr;      // [nnz_groups][NV] weights, 4 per group
+    uint32_t* d_widx = nullptr;    // [nnz_groups][NV] joint ids, 4 x u8 per group
+    CUtensorMap tmap_B;            // [GEMM_N][GEMM_K], box 64 x 256, 128B swizzle
+};
+
+namespace prk {
+using Model = ::prk_model;
+
+// Per-batch device flags (whole-batch tests of smpl_layer.py:87,148)
+struct BatchFlags {
+    int32_t betas_nonzero;
+    int32_t trans_nonzero;
+};
+
+// ---- launchers (each returns cudaError_t from the launch) ------------------
+cudaError_t launch_batch_flags(const float* d_betas, const float* d_trans, int64_t B,
+                               BatchFlags* d_flags, cudaStream_t s);
+
+// K2a: Rodrigues + kinematic chain (+ split-precision GEMM operand rows when full_mesh)
+cudaError_t launch_pose_chain(const Model& m, const float* d_pose, const float* d_betas,
+                              const float* d_trans, const BatchFlags* d_flags, int center_idx,
+                              int64_t B, bool full_mesh, uint16_t* d_Arows, float* d_Askin,
+                              float* d_off, float* d_joints, cudaStream_t s);
+
+bool pose_chain_needs_flags(const Model& m, const float* d_betas, const float* d_trans, int center_idx);
+
+// K1: tcgen05 blend GEMM  (rows_pad = multiple of 128)
+cudaError_t launch_blend_gemm(const Model& m, const CUtensorMap& tmap_A, int64_t rows_pad,
+                              float* d_vposed, cudaStream_t s);
+cudaError_t launch_blend_simt(const Model& m, const uint16_t* d_Arows, int64_t rows,
+                              float* d_vposed, cudaStream_t s);
+
+// K2b: linear-blend skinning
+cudaError_t launch_skin(const Model& m, const float* d_vposed, const float* d_Askin,
+                        const float* d_off, int64_t B, float* d_verts, cudaStream_t s);
+
+// K3: Euler angles + REBA/RULA
+cudaError_t launch_score_pose(const void* d_pose, int pose_dtype, const prk_addinfo* d_info,
+                              const int32_t* d_track, int64_t B, uint32_t which,
+                              prk_score_rec* d_out, double* d_euler_out, uint32_t debug_mask,
+                              const int8_t* debug_slot, int n_debug, cudaStream_t s);
+cudaError_t launch_score_euler(const double* d_euler, const prk_addinfo* d_info,
+                               const int32_t* d_track, int64_t B, uint32_t which,
+                               prk_score_rec* d_out, cudaStream_t s);
+cudaError_t launch_euler(const void* d_pose, int pose_dtype, int64_t n_rot, double* d_euler,
+                         uint8_t* d_bad, cudaStream_t s);
+cudaError_t launch_score_hist(const prk_score_rec* d_scores, int64_t B, uint32_t which,
+                              unsigned long long* d_hist, cudaStream_t s);
+
+// TMA descriptor helper (driver entry point fetched at run time; no libcuda link)
+int encode_tmap_2d_bf16(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols,
+                        uint32_t box_rows, uint32_t box_cols);
+
+void count_launch(int n = 1);
+
+}  // namespace prk

@@ -1,0 +1,266 @@
+// K2a: per-frame batch Rodrigues + 24-joint kinematic chain, one thread per frame.
+//
+// Reference behaviour (paths relative to the reference root):
+//   th_posemap_axisang / batch_rodrigues / quat2mat   lib/smplpytorch/smplpytorch/pytorch/tensutils.py:6-19,
+//                                                     rodrigues_layer.py:13-52
+//   subtract_flat_id (pose_map = R - I)               tensutils.py:41-48
+//   th_j = J_regressor @ v_shaped                     smpl_layer.py:87-95   (folded: J = J0 + Jdirs*beta)
+//   kinematic chain, rest-pose removal, joints        smpl_layer.py:103-132,145
+//   centring / translation                            smpl_layer.py:148-155
+//
+// Outputs per frame:
+//   joints [24][3]                                     (always)
+//   A' row [704] bf16: split-precision operand of the blend GEMM (K1)      (full mesh only)
+//   Askin  [24][12] fp32: rows of A_j = [R_g | t_g - R_g j_rest]            (full mesh only)
+//   off    [3]: +trans or -centre joint, applied to vertices by K2b        (full mesh only)
+//
+// The chain is walked depth-first with every index a compile-time constant, so the at
+// most three live 3x4 transforms stay in registers; HBM traffic is 288 B pose (+40 betas,
+// +12 trans) in and 288 B joints (+1408 A' +1152 Askin +12 off) out per frame.
+#include "prk_internal.h"
+
+#include <cuda_bf16.h>
+
+namespace prk {
+
+// SMPL kintree parents (smpl_layer.py:60-62) and a depth-first visiting order.
+__host__ __device__ constexpr int smpl_parent(int j) {
+    constexpr int t[24] = {-1, 0, 0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 9, 9, 12, 13, 14, 16, 17, 18, 19, 20, 21};
+    return t[j];
+}
+__host__ __device__ constexpr int smpl_dfs(int pos) {
+    constexpr int t[24] = {0, 1, 4, 7, 10, 2, 5, 8, 11, 3, 6, 9, 12, 15, 13, 16, 18, 20, 22, 14, 17, 19, 21, 23};
+    return t[pos];
+}
+
+__device__ __forceinline__ uint16_t bf16_bits(float x) { return __bfloat16_as_ushort(__float2bfloat16_rn(x)); }
+__device__ __forceinline__ float bf16_val(uint16_t b) { return __uint_as_float((uint32_t)b << 16); }
+
+// Streams bf16 values into a global row, 8 at a time (one 16-byte store).
+struct RowWriter {
+    uint4* dst;
+    uint32_t buf[4];
+    int n;
+    __device__ __forceinline__ void push(uint16_t v) {
+        const int w = (n >> 1) & 3;
+        if (n & 1) buf[w] |= (uint32_t)v << 16; else buf[w] = v;
+        ++n;
+        if ((n & 7) == 0) { *dst = make_uint4(buf[0], buf[1], buf[2], buf[3]); ++dst; }
+    }
+};
+
+// batch_rodrigues + quat2mat in fp32 (rodrigues_layer.py:41-52, 13-38), row-major R[9].
+__device__ __forceinline__ void smpl_rodrigues(float ax, float ay, float az, float* R) {
+    const float x = ax + 1e-8f, y = ay + 1e-8f, z = az + 1e-8f;
+    const float angle = sqrtf(x * x + y * y + z * z);
+    const float inv = 1.0f / angle;
+    const float nx = ax * inv, ny = ay * inv, nz = az * inv;
+    float s, c;
+    sincosf(angle * 0.5f, &s, &c);
+    float qw = c, qx = s * nx, qy = s * ny, qz = s * nz;
+    const float qinv = 1.0f / sqrtf(qw * qw + qx * qx + qy * qy + qz * qz);
+    qw *= qinv; qx *= qinv; qy *= qinv; qz *= qinv;
+    const float w2 = qw * qw, x2 = qx * qx, y2 = qy * qy, z2 = qz * qz;
+    const float wx = qw * qx, wy = qw * qy, wz = qw * qz;
+    const float xy = qx * qy, xz = qx * qz, yz = qy * qz;
+    R[0] = w2 + x2 - y2 - z2; R[1] = 2 * xy - 2 * wz;   R[2] = 2 * wy + 2 * xz;
+    R[3] = 2 * wz + 2 * xy;   R[4] = w2 - x2 + y2 - z2; R[5] = 2 * yz - 2 * wx;
+    R[6] = 2 * xz - 2 * wy;   R[7] = 2 * wx + 2 * yz;   R[8] = w2 - x2 - y2 + z2;
+}
+
+// mode bits
+constexpr uint32_t MODE_FRAME_BETAS_ALWAYS = 1u;  // betas given and model betas are zero
+constexpr uint32_t MODE_FRAME_BETAS_FLAG = 2u;    // betas given, honour flags->betas_nonzero
+constexpr uint32_t MODE_TRANS_ALWAYS = 4u;        // trans given, no centre joint configured
+constexpr uint32_t MODE_TRANS_FLAG = 8u;          // trans given and centre joint configured
+
+template <bool kStd, bool kMesh>
+__global__ void __launch_bounds__(128)
+pose_chain_kernel(const __grid_constant__ PoseConsts pc, const float* __restrict__ pose,
+                  const float* __restrict__ betas, const float* __restrict__ trans,
+                  const BatchFlags* __restrict__ flags, uint32_t mode, int center_idx, int64_t B,
+                  uint16_t* __restrict__ Arows, float* __restrict__ Askin,
+                  float* __restrict__ off, float* __restrict__ joints) {
+    const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= B) return;
+
+    bool frame_betas = (mode & MODE_FRAME_BETAS_ALWAYS) != 0;
+    bool add_trans = (mode & MODE_TRANS_ALWAYS) != 0;
+    if (mode & MODE_FRAME_BETAS_FLAG) frame_betas = flags->betas_nonzero != 0;
+    if (mode & MODE_TRANS_FLAG) add_trans = flags->trans_nonzero != 0;
+    const bool centre = (center_idx >= 0) && !add_trans;
+
+    float beta[NBETA];
+#pragma unroll
+    for (int k = 0; k < NBETA; ++k) beta[k] = frame_betas ? betas[f * NBETA + k] : pc.model_betas[k];
+
+    float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+    if (add_trans) { o0 = trans[f * 3 + 0]; o1 = trans[f * 3 + 1]; o2 = trans[f * 3 + 2]; }
+
+    RowWriter rw;
+    rw.dst = kMesh ? reinterpret_cast<uint4*>(Arows + f * GEMM_K) : nullptr;
+    rw.n = 0;
+    rw.buf[0] = rw.buf[1] = rw.buf[2] = rw.buf[3] = 0;
+
+    const float* p = pose + f * 72;
+    float* jout = joints + f * 72;
+    float G[NJ][12];     // global transforms, rows [R | t]
+    float J[NJ][3];      // rest joints
+    float c0 = 0.f, c1 = 0.f, c2 = 0.f;   // centre joint translation
+
+#pragma unroll
+    for (int pos = 0; pos < NJ; ++pos) {
+        const int j = kStd ? smpl_dfs(pos) : pos;
+        const int par = kStd ? smpl_parent(j) : (pos == 0 ? -1 : pc.parents[j]);
+
+        float R[9];
+        smpl_rodrigues(p[j * 3 + 0], p[j * 3 + 1], p[j * 3 + 2], R);
+
+        if (kMesh && pos > 0) {   // pose_map = R - I, split hi/lo (tensutils.py:41-48)
+            uint16_t hi[9], lo[9];
+#pragma unroll
+            for (int e = 0; e < 9; ++e) {
+                const float v = R[e] - ((e == 0 || e == 4 || e == 8) ? 1.0f : 0.0f);
+                hi[e] = bf16_bits(v);
+                lo[e] = bf16_bits(v - bf16_val(hi[e]));
+            }
+#pragma unroll
+            for (int e = 0; e < 9; ++e) rw.push(hi[e]);
+#pragma unroll
+            for (int e = 0; e < 9; ++e) rw.push(hi[e]);
+#pragma unroll
+            for (int e = 0; e < 9; ++e) rw.push(lo[e]);
+        }
+
+        // rest joint: J = J_template + Jdirs * beta
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float acc = pc.J_template[j * 3 + c];
+#pragma unroll
+            for (int k = 0; k < NBETA; ++k) acc = fmaf(pc.Jdirs[(j * 3 + c) * NBETA + k], beta[k], acc);
+            J[j][c] = acc;
+        }
+
+        if (pos == 0) {          // smpl_layer.py:105-106
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                G[j][r * 4 + 0] = R[r * 3 + 0]; G[j][r * 4 + 1] = R[r * 3 + 1];
+                G[j][r * 4 + 2] = R[r * 3 + 2]; G[j][r * 4 + 3] = J[j][r];
+            }
+        } else {                 // smpl_layer.py:109-119
+            const float t0 = J[j][0] - J[par][0], t1 = J[j][1] - J[par][1], t2 = J[j][2] - J[par][2];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const float g0 = G[par][r * 4 + 0], g1 = G[par][r * 4 + 1], g2 = G[par][r * 4 + 2];
+                G[j][r * 4 + 0] = g0 * R[0] + g1 * R[3] + g2 * R[6];
+                G[j][r * 4 + 1] = g0 * R[1] + g1 * R[4] + g2 * R[7];
+                G[j][r * 4 + 2] = g0 * R[2] + g1 * R[5] + g2 * R[8];
+                G[j][r * 4 + 3] = g0 * t0 + g1 * t1 + g2 * t2 + G[par][r * 4 + 3];
+            }
+        }
+        // joints (smpl_layer.py:145), translation added now, centring applied below
+        jout[j * 3 + 0] = G[j][3] + o0;
+        jout[j * 3 + 1] = G[j][7] + o1;
+        jout[j * 3 + 2] = G[j][11] + o2;
+        if (j == center_idx) { c0 = G[j][3]; c1 = G[j][7]; c2 = G[j][11]; }
+
+        if (kMesh) {             // A_j = G_j - pack(G_j @ [j_rest; 0])  (smpl_layer.py:126-132)
+            float4* dst = reinterpret_cast<float4*>(Askin + (f * NJ + j) * 12);
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const float g0 = G[j][r * 4 + 0], g1 = G[j][r * 4 + 1], g2 = G[j][r * 4 + 2];
+                const float tt = G[j][r * 4 + 3] - (g0 * J[j][0] + g1 * J[j][1] + g2 * J[j][2]);
+                dst[r] = make_float4(g0, g1, g2, tt);
+            }
+        }
+    }
+
+    if (centre) {   // smpl_layer.py:149-152
+        o0 = -c0; o1 = -c1; o2 = -c2;
+#pragma unroll
+        for (int k = 0; k < 72; k += 3) {
+            jout[k + 0] += o0; jout[k + 1] += o1; jout[k + 2] += o2;
+        }
+    }
+
+    if (kMesh) {
+        off[f * 3 + 0] = o0; off[f * 3 + 1] = o1; off[f * 3 + 2] = o2;
+        // betas: 3-way split, products {h,h,m,h,m,l} x {h,m,h,l,m,h}
+#pragma unroll
+        for (int k = 0; k < NBETA; ++k) {
+            const uint16_t h = bf16_bits(beta[k]);
+            const float r1 = beta[k] - bf16_val(h);
+            const uint16_t m = bf16_bits(r1);
+            const uint16_t l = bf16_bits(r1 - bf16_val(m));
+            rw.push(h); rw.push(h); rw.push(m); rw.push(h); rw.push(m); rw.push(l);
+        }
+        rw.push(0x3F80); rw.push(0x3F80); rw.push(0x3F80);   // 1.0 x {vt_h, vt_m, vt_l}
+#pragma unroll
+        for (int k = COL_ONES + 3; k < GEMM_K; ++k) rw.push(0);
+    }
+}
+
+// Whole-batch tests `torch.norm(x) == 0` (smpl_layer.py:87,148): true iff every x*x is 0
+// in fp32 (NaN counts as non-zero).  d_flags must be zeroed before launch.
+__global__ void __launch_bounds__(256)
+batch_flags_kernel(const float* __restrict__ betas, const float* __restrict__ trans, int64_t B,
+                   BatchFlags* __restrict__ flags) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int bnz = 0, tnz = 0;
+    if (betas)
+        for (int64_t i = t0; i < B * NBETA; i += stride) { const float v = betas[i]; bnz |= !(v * v == 0.0f); }
+    if (trans)
+        for (int64_t i = t0; i < B * 3; i += stride) { const float v = trans[i]; tnz |= !(v * v == 0.0f); }
+    bnz = __syncthreads_or(bnz);
+    tnz = __syncthreads_or(tnz);
+    if (threadIdx.x == 0) {
+        if (bnz) atomicOr(&flags->betas_nonzero, 1);
+        if (tnz) atomicOr(&flags->trans_nonzero, 1);
+    }
+}
+
+cudaError_t launch_batch_flags(const float* d_betas, const float* d_trans, int64_t B,
+                               BatchFlags* d_flags, cudaStream_t s) {
+    cudaError_t e = cudaMemsetAsync(d_flags, 0, sizeof(BatchFlags), s);
+    if (e != cudaSuccess) return e;
+    int64_t n = B * NBETA;
+    unsigned g = (unsigned)((n + 256 * 8 - 1) / (256 * 8));
+    if (g < 1) g = 1;
+    if (g > 148u * 4u) g = 148u * 4u;
+    batch_flags_kernel<<<g, 256, 0, s>>>(d_betas, d_trans, B, d_flags);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pose_chain(const Model& m, const float* d_pose, const float* d_betas,
+                              const float* d_trans, const BatchFlags* d_flags, int center_idx,
+                              int64_t B, bool full_mesh, uint16_t* d_Arows, float* d_Askin,
+                              float* d_off, float* d_joints, cudaStream_t s) {
+    if (B == 0) return cudaSuccess;
+    bool model_betas_zero = true;
+    for (int k = 0; k < NBETA; ++k) model_betas_zero &= (m.pc.model_betas[k] == 0.0f);
+    uint32_t mode = 0;
+    if (d_betas) mode |= model_betas_zero ? MODE_FRAME_BETAS_ALWAYS : MODE_FRAME_BETAS_FLAG;
+    if (d_trans) mode |= (center_idx < 0) ? MODE_TRANS_ALWAYS : MODE_TRANS_FLAG;
+    const unsigned grid = (unsigned)((B + 127) / 128);
+    const bool std_tree = m.pc.standard_tree != 0;
+#define PRK_LAUNCH(STD, MESH)                                                              \
+    pose_chain_kernel<STD, MESH><<<grid, 128, 0, s>>>(m.pc, d_pose, d_betas, d_trans, d_flags, \
+                                                      mode, center_idx, B, d_Arows, d_Askin, \
+                                                      d_off, d_joints)
+    if (std_tree) { if (full_mesh) PRK_LAUNCH(true, true); else PRK_LAUNCH(true, false); }
+    else          { if (full_mesh) PRK_LAUNCH(false, true); else PRK_LAUNCH(false, false); }
+#undef PRK_LAUNCH
+    count_launch();
+    return cudaGetLastError();
+}
+
+// true when launch_pose_chain will read d_flags for this configuration
+bool pose_chain_needs_flags(const Model& m, const float* d_betas, const float* d_trans, int center_idx) {
+    bool model_betas_zero = true;
+    for (int k = 0; k < NBETA; ++k) model_betas_zero &= (m.pc.model_betas[k] == 0.0f);
+    return (d_betas && !model_betas_zero) || (d_trans && center_idx >= 0);
+}
+
+}  // namespace prk

@@ -1,0 +1,163 @@
+"""Batched frame engine: what ``lib/core/base.py:225-239,151,168`` does per frame in
+Python (Euler angles, SMPL forward, REBA, RULA) done for whole batches on one GPU.
+
+``PoseRiskEngine.run`` takes device tensors, ``run_host`` takes (pinned) host arrays
+and goes through ``prk_pipeline_host`` (host->device copies, kernels, device->host
+copies of scores and joints on one stream).  Multi-person tracks with different
+genders / additional information are handled by grouping frames per gender
+(BASELINE.json config 4).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib, _runtime
+from .model_provider import get_model_data
+
+GENDERS = ('neutral', 'female', 'male')
+
+
+class PoseRiskEngine:
+    def __init__(self, device=None, genders=('neutral',), model_root=None):
+        self.device = _runtime.require_cuda(device)
+        self.models = {}
+        for g in genders:
+            self.models[g] = _runtime.ModelHandle(get_model_data(g, model_root), self.device)
+        self._host_ws = None
+
+    # ------------------------------------------------------------------ device path
+    def run(self, pose, betas=None, trans=None, add_info=None, track_of_frame=None, gender='neutral',
+            want_verts=True, center_idx=None, verts_out=None):
+        """pose (B,72) float32 CUDA tensor.  Returns dict(verts|None, joints, scores) where
+        scores is a (B,32) uint8 tensor of prk_score_rec."""
+        dev = self.device
+        B = pose.shape[0]
+        pose = pose.to(dev, torch.float32).reshape(B, 72).contiguous()
+        betas = None if betas is None else betas.to(dev, torch.float32).reshape(B, 10).contiguous()
+        trans = None if trans is None else trans.to(dev, torch.float32).reshape(B, 3).contiguous()
+        info = add_info if isinstance(add_info, torch.Tensor) else _runtime.addinfo_tensor(add_info, dev)
+        track = None if track_of_frame is None else torch.as_tensor(track_of_frame, dtype=torch.int32).to(dev).contiguous()
+        h = self.models[gender]
+        with torch.cuda.device(dev):
+            verts = None
+            if want_verts:
+                verts = verts_out if verts_out is not None else torch.empty((B, 6890, 3), dtype=torch.float32, device=dev)
+            joints = torch.empty((B, 24, 3), dtype=torch.float32, device=dev)
+            scores = torch.empty((B, 32), dtype=torch.uint8, device=dev)
+            if B > 0:
+                ws, ws_bytes, _keep = _runtime.workspace.get(dev, h.workspace_bytes(B, not want_verts))
+                _lib.check(_lib.lib().prk_pipeline(
+                    h.handle, _runtime.ptr(pose), _runtime.ptr(betas), _runtime.ptr(trans),
+                    -1 if center_idx is None else int(center_idx), _runtime.ptr(info), _runtime.ptr(track), B,
+                    _runtime.ptr(verts), _runtime.ptr(joints), _runtime.ptr(scores), ws, ws_bytes,
+                    _runtime.stream_ptr(dev)))
+        return {'verts': verts, 'joints': joints, 'scores': scores}
+
+    def run_tracks(self, pose, betas, trans, add_infos, track_of_frame, gender_of_track, want_verts=True):
+        """Mixed-gender multi-person batch: frames are grouped by their track's gender, each
+        group goes through its own model; outputs are scattered back to frame order."""
+        dev = self.device
+        track = torch.as_tensor(track_of_frame, dtype=torch.int64).to(dev)
+        B = pose.shape[0]
+        info = _runtime.addinfo_tensor(add_infos, dev)
+        g_of_t = torch.tensor([GENDERS.index(g) for g in gender_of_track], device=dev)
+        g_of_f = g_of_t[track]
+        joints = torch.empty((B, 24, 3), dtype=torch.float32, device=dev)
+        scores = torch.empty((B, 32), dtype=torch.uint8, device=dev)
+        verts = torch.empty((B, 6890, 3), dtype=torch.float32, device=dev) if want_verts else None
+        for gi, g in enumerate(GENDERS):
+            idx = torch.nonzero(g_of_f == gi).squeeze(1)
+            if idx.numel() == 0:
+                continue
+            r = self.run(pose[idx], None if betas is None else betas[idx], None if trans is None else trans[idx],
+                         info, track[idx].to(torch.int32), gender=g, want_verts=want_verts)
+            joints[idx] = r['joints']
+            scores[idx] = r['scores']
+            if want_verts:
+                verts[idx] = r['verts']
+        return {'verts': verts, 'joints': joints, 'scores': scores}
+
+    def euler_debug(self, pose, joint_ids, add_info, track_of_frame=None):
+        """Scores + Euler sequences of the listed joints (the --debug_joints output,
+        base.py:144-146): returns (scores (B,32) uint8, euler (B,k,3) float64)."""
+        dev = self.device
+        B = pose.shape[0]
+        is64 = pose.dtype == torch.float64
+        pose = pose.to(dev).reshape(B, 72).contiguous()
+        info = add_info if isinstance(add_info, torch.Tensor) else _runtime.addinfo_tensor(add_info, dev)
+        track = None if track_of_frame is None else torch.as_tensor(track_of_frame, dtype=torch.int32).to(dev).contiguous()
+        ids = np.asarray(joint_ids, np.int32)
+        scores = torch.empty((B, 32), dtype=torch.uint8, device=dev)
+        eul = torch.empty((B, len(ids), 3), dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().prk_score_pose(
+                _runtime.ptr(pose), _lib.PRK_DTYPE_F64 if is64 else _lib.PRK_DTYPE_F32, _runtime.ptr(info),
+                _runtime.ptr(track), B, _lib.PRK_SCORE_REBA | _lib.PRK_SCORE_RULA, _runtime.ptr(scores),
+                _runtime.ptr(eul), ids.ctypes.data_as(C.c_void_p), len(ids), _runtime.stream_ptr(dev)))
+        return scores, eul
+
+    # ------------------------------------------------------------------ host path
+    def run_host(self, pose, betas, trans, add_infos, track_of_frame, joints_out, scores_out, gender='neutral',
+                 verts_out=None, center_idx=None):
+        """Host buffers in, host buffers out (torch CPU tensors, ideally pinned):
+        pose (B,72) f32, betas (B,10)|None, trans (B,3)|None, joints_out (B,24,3) f32,
+        scores_out (B,32) uint8; verts_out is an optional CUDA tensor.  Asynchronous on the
+        current stream: synchronize before reading the outputs."""
+        dev = self.device
+        B = pose.shape[0]
+        h = self.models[gender]
+        info = _lib.addinfo_array(add_infos)
+        track = None if track_of_frame is None else np.ascontiguousarray(track_of_frame, np.int32)
+        joints_only = verts_out is None
+        with torch.cuda.device(dev):
+            ws, ws_bytes, _keep = _runtime.workspace.get(dev, h.host_workspace_bytes(B, joints_only))
+            _lib.check(_lib.lib().prk_pipeline_host(
+                h.handle, _runtime.ptr(pose), _runtime.ptr(betas), _runtime.ptr(trans),
+                -1 if center_idx is None else int(center_idx), info.ctypes.data_as(C.c_void_p), info.shape[0],
+                None if track is None else track.ctypes.data_as(C.c_void_p), B, _runtime.ptr(verts_out),
+                _runtime.ptr(joints_out), _runtime.ptr(scores_out), ws, ws_bytes, _runtime.stream_ptr(dev)))
+        self._keep = (info, track)   # pageable host arrays must outlive the async copies
+        return joints_out, scores_out
+
+    # ------------------------------------------------------------------ aggregation
+    def aggregate(self, scores, which='REBA'):
+        """Predictor.post_processing numbers (base.py:260-271) from a device histogram:
+        (mean, top-50% mean, top-10% mean, max, mode), each rounded to 3 decimals like the
+        reference (top-10% is nan when fewer than 10 frames)."""
+        dev = self.device
+        B = scores.shape[0]
+        hist = torch.empty(64, dtype=torch.int64, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().prk_score_histogram(
+                _runtime.ptr(scores), B, _lib.PRK_SCORE_REBA if which == 'REBA' else _lib.PRK_SCORE_RULA,
+                _runtime.ptr(hist), _runtime.stream_ptr(dev)))
+        return aggregate_from_histogram(hist.cpu().numpy(), B)
+
+
+def aggregate_from_histogram(hist: np.ndarray, n: int):
+    """hist[k] = number of frames with score k-16.  Mirrors base.py:260-271: scores sorted
+    descending, mean, mean of first n//2, mean of first n//10, max, scipy mode (smallest of
+    the most frequent values)."""
+    values = np.arange(64) - 16
+
+    def top_mean(k):
+        if k == 0:
+            return float('nan')
+        left, tot = k, 0.0
+        for v in range(63, -1, -1):
+            take = min(left, int(hist[v]))
+            tot += take * float(values[v])
+            left -= take
+            if left == 0:
+                break
+        return tot / k
+
+    if n == 0:
+        return (float('nan'),) * 5
+    mean = float((hist * values).sum()) / n
+    mx = int(values[np.nonzero(hist)[0].max()])
+    mode = int(values[int(np.argmax(hist))])          # argmax returns the first = smallest value
+    return (round(mean, 3), round(top_mean(n // 2), 3), round(top_mean(n // 10), 3), round(mx, 3), mode)

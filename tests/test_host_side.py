@@ -1,0 +1,224 @@
+"""CPU-only tests: C-ABI surface, host logic of the drop-ins, sharding over gloo."""
+import ctypes
+import json
+import os
+import pickle
+import re
+import subprocess
+import sys
+import types
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    """The shared library loads without a GPU and exports exactly what include/*.h declares."""
+    from poserisk_release_b200.build import build_library
+    lib = build_library()
+    L = ctypes.CDLL(lib)
+    hdr = open(os.path.join(ROOT, 'include', 'poserisk_b200.h')).read()
+    hdr = re.sub(r'/\*.*?\*/', '', hdr, flags=re.S)
+    declared = set(re.findall(r'\b(prk_[a-z0-9_]+)\s*\(', hdr))
+    assert len(declared) >= 20
+    for sym in declared:
+        assert hasattr(L, sym), sym
+    from poserisk_release_b200 import _lib
+    assert set(_lib.EXPORTS) == declared
+    L.prk_abi_version.restype = ctypes.c_int
+    assert L.prk_abi_version() == 1
+    L.prk_strerror.restype = ctypes.c_char_p
+    assert L.prk_strerror(0) == b'ok' and b'workspace' in L.prk_strerror(3)
+    # struct sizes the Python side relies on
+    assert _lib.REC_DTYPE.itemsize == 32
+
+
+def test_product_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under the package may import or load it."""
+    pkg = os.path.join(ROOT, 'poserisk_release_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.h', '.cuh')):
+                src = open(os.path.join(dirpath, f)).read()
+                assert 'oracle' not in src.lower(), os.path.join(dirpath, f)
+
+
+def test_no_gpu_means_loud_failure():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    from poserisk_release_b200 import SMPL_Layer, REBA
+    lay = SMPL_Layer(gender='neutral', model_root='unused')
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        lay(torch.zeros(1, 72))
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        REBA()(np.zeros((1, 24, 3)), np.zeros((1, 1)), {"REBA": {}, "RULA": {}})
+
+
+def test_smpl_layer_attributes_match_reference_surface():
+    import torch
+    from poserisk_release_b200 import SMPL_Layer
+    lay = SMPL_Layer(center_idx=2, gender='female', model_root='some/root')
+    assert lay.model_path == os.path.join('some/root', 'SMPL_FEMALE.pkl')
+    assert lay.center_idx == 2 and lay.gender == 'female' and lay.num_joints == 24
+    assert tuple(lay.th_betas.shape) == (1, 10) and tuple(lay.th_shapedirs.shape) == (6890, 3, 10)
+    assert tuple(lay.th_posedirs.shape) == (6890, 3, 207) and tuple(lay.th_v_template.shape) == (1, 6890, 3)
+    assert tuple(lay.th_J_regressor.shape) == (24, 6890) and tuple(lay.th_weights.shape) == (6890, 24)
+    assert lay.th_faces.dtype == torch.int64 and lay.th_faces.shape[1] == 3
+    assert lay.kintree_parents[1:] == [0, 0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 9, 9, 12, 13, 14, 16, 17, 18, 19, 20, 21]
+    assert tuple(lay.vertice_segmentation.shape) == (6890,)
+    assert lay.kintree_table.shape == (2, 24)
+
+
+def test_pkl_loader_without_chumpy(tmp_path):
+    """SMPL pickles hold chumpy objects; the loader must read them with chumpy absent."""
+    import scipy.sparse as sp
+    from poserisk_release_b200.model_provider import load_smpl_pkl, synthetic_smpl
+    m = synthetic_smpl('neutral')
+    ch_mod, ch_ch = types.ModuleType('chumpy'), types.ModuleType('chumpy.ch')
+
+    class Ch:
+        def __init__(self, x):
+            self.x = np.asarray(x)
+
+        def __getstate__(self):
+            return {'x': self.x, 'dterms': ('x',)}
+    Ch.__module__, Ch.__qualname__ = 'chumpy.ch', 'Ch'
+    ch_ch.Ch = Ch
+    ch_mod.ch = ch_ch
+    sys.modules['chumpy'], sys.modules['chumpy.ch'] = ch_mod, ch_ch
+    try:
+        dd = {'v_template': m.v_template.astype(np.float64), 'shapedirs': Ch(m.shapedirs.astype(np.float64)),
+              'posedirs': m.posedirs.astype(np.float64), 'weights': m.weights.astype(np.float64),
+              'J_regressor': sp.csc_matrix(m.J_regressor.astype(np.float64)), 'f': m.faces.astype(np.uint32),
+              'kintree_table': m.kintree_table, 'bs_type': 'lrotmin'}
+        path = tmp_path / 'SMPL_NEUTRAL.pkl'
+        with open(path, 'wb') as f:
+            pickle.dump(dd, f, protocol=2)
+    finally:
+        del sys.modules['chumpy'], sys.modules['chumpy.ch']
+    got = load_smpl_pkl(str(path))
+    assert not got.synthetic
+    for k in ('v_template', 'shapedirs', 'posedirs', 'weights', 'J_regressor'):
+        assert np.array_equal(getattr(got, k), getattr(m, k)), k
+    assert np.array_equal(got.betas, np.zeros(10, np.float32))
+    assert got.parents[1:] == m.parents[1:]
+
+
+def test_addinfo_validation():
+    from poserisk_release_b200 import _lib
+    from oracle import oracle
+    ok = {"REBA": {k: 1 for k in _lib.REBA_KEYS}, "RULA": {k: 2 for k in _lib.RULA_KEYS}}
+    a = _lib.addinfo_array([ok, ok])
+    assert a.shape == (2, 16) and a.dtype == np.int32 and (a[:, :7] == 1).all() and (a[:, 7:] == 2).all()
+    assert np.array_equal(a, oracle.addinfo_array([ok, ok]))
+    bad = json.loads(json.dumps(ok))
+    del bad["RULA"]["B_Muscle_use"]
+    with pytest.raises(KeyError):
+        _lib.addinfo_array(bad)
+    bad = json.loads(json.dumps(ok))
+    bad["REBA"]["Coupling"] = 1.5
+    with pytest.raises(TypeError):
+        _lib.addinfo_array(bad)
+
+
+def test_aggregate_from_histogram_matches_post_processing():
+    """base.py:260-271 on random score sequences, including n < 10 (top-10% mean is nan)."""
+    from scipy.stats import mode
+    from poserisk_release_b200.pipeline import aggregate_from_histogram
+    rng = np.random.default_rng(0)
+    for n in (1, 3, 9, 10, 11, 57, 1000, 4097):
+        scores = rng.integers(1, 13, n)
+        hist = np.bincount(scores + 16, minlength=64)
+        s = np.sort(scores)[::-1]
+        with np.errstate(all='ignore'):
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter('ignore')
+                expect = (round(s.mean(), 3), round(s[:n // 2].mean(), 3), round(s[:n // 10].mean(), 3),
+                          round(s.max(), 3), mode(s).mode.item())
+        got = aggregate_from_histogram(hist, n)
+        for g, e in zip(got, expect):
+            assert (np.isnan(g) and np.isnan(e)) or g == pytest.approx(e, abs=1e-12)
+
+
+def test_debug_angle_logs_match_reference():
+    """The debug `log` strings of REBA/RULA (reba.py:142-390, rula.py:198-418), including the
+    `angle4=1` leak (rula.py:183,198) and the crossed variables in the abducted logs."""
+    from ref_harness import reference_available, load_reference
+    if not reference_available():
+        pytest.skip('reference tree not present')
+    from golden.make_golden import fuzz_euler, expand_used
+    from poserisk_release_b200.reba import REBA
+    from poserisk_release_b200.rula import RULA
+    ref = load_reference()
+    info = json.load(open(os.path.join(ref.root, 'example', 'additional_information.json')))
+    e = expand_used(fuzz_euler(np.random.default_rng(1), 400))
+    dummy = np.zeros((400, 1))
+    r_reba, r_rula = ref.REBA(debug=True), ref.RULA(debug=True)
+    r_reba(e, dummy, info)
+    r_rula(e, dummy, info)
+    mine_reba, mine_rula = REBA(debug=True), RULA(debug=True)
+    for i in range(400):
+        a, b = mine_reba._angle_log(e[i]), r_reba.log[i]
+        assert a == b and list(a) == list(b)
+        a, b = mine_rula._angle_log(e[i]), r_rula.log[i]
+        assert a == b and list(a) == list(b)
+    for s in (1, 2, 3, 5, 7, 8, 10, 11, 15, 4.4, 7.5):
+        assert mine_reba.action_level(s) == r_reba.action_level(s)
+        assert mine_rula.action_level(s) == r_rula.action_level(s)
+    assert mine_reba.eval_items == r_reba.eval_items and mine_rula.eval_items == r_rula.eval_items
+    assert np.array_equal(mine_reba.table_a, r_reba.table_a) and np.array_equal(mine_reba.table_c, r_reba.table_c)
+    assert np.array_equal(mine_rula.table_a, r_rula.table_a) and np.array_equal(mine_rula.table_b, r_rula.table_b)
+
+
+def test_shard_ranges_cover_everything():
+    from poserisk_release_b200.distributed import shard_range, shard_sizes
+    for n in (0, 1, 7, 8, 1000003):
+        for w in (1, 2, 3, 8):
+            r = [shard_range(n, k, w) for k in range(w)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(r[k][1] == r[k + 1][0] for k in range(w - 1))
+            assert max(shard_sizes(n, w)) - min(shard_sizes(n, w)) <= 1
+
+
+_GLOO_WORKER = r'''
+import os, sys
+sys.path.insert(0, {root!r})
+import torch, torch.distributed as dist
+from poserisk_release_b200.distributed import shard_range, all_gather_rows
+dist.init_process_group('gloo', rank=int(os.environ['RANK']), world_size=int(os.environ['WORLD_SIZE']))
+rank, world = dist.get_rank(), dist.get_world_size()
+for n in (10, 11, 4096):
+    full = (torch.arange(n * 32, dtype=torch.int64) % 251).to(torch.uint8).reshape(n, 32)
+    lo, hi = shard_range(n, rank, world)
+    got = all_gather_rows(full[lo:hi].clone(), n)
+    assert got.shape == full.shape and torch.equal(got, full), (n, rank)
+dist.barrier()
+dist.destroy_process_group()
+print('ok', rank)
+'''
+
+
+def test_all_gather_rows_gloo_world2(tmp_path):
+    """N>1 path on CPU: two ranks, ragged and equal shards, gathered rows in frame order."""
+    script = tmp_path / 'worker.py'
+    script.write_text(_GLOO_WORKER.format(root=ROOT))
+    env = dict(os.environ, MASTER_ADDR='127.0.0.1', MASTER_PORT='29571', WORLD_SIZE='2')
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)),
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT) for r in range(2)]
+    outs = [p.communicate(timeout=120)[0].decode() for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+
+
+def test_bench_reference_arm_prints_contract_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1',
+                          '--warmup', '3'], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line['impl'] == 'reference' and line['unit'] == 'frames/s' and line['value'] > 0
+    assert line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['cores'] >= 1
+    assert line['e2e']['h2d_bytes_per_step'] == 0 and line['e2e']['value'] == line['value']

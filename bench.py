@@ -246,7 +246,7 @@ def run_gpu_arm(args):
     if sampler:
         sampler.start()
     # preload: keep the GPU busy ~1.5 s so clocks settle and the sampler sees load (not warm-up steps)
-    t_end = time.perf_counter() + 1.5
+    t_end = time.perf_counter() + float(os.environ.get('PRK_BENCH_PRELOAD_S', '1.5'))
     i = 0
     while time.perf_counter() < t_end:
         step_device(i)

@@ -74,18 +74,19 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// [rows][cols] bf16 row-major, box = box_rows x box_cols (box_cols*2 bytes == 128: SWIZZLE_128B)
-int encode_tmap_2d_bf16(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, uint32_t box_rows,
-                        uint32_t box_cols) {
+// [rows][cols] row-major tensor of bf16 (elem_bytes 2) or fp32 (elem_bytes 4), box = box_rows x box_cols with
+// box_cols * elem_bytes == 128 (SWIZZLE_128B)
+int encode_tmap_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                   uint32_t box_cols, int elem_bytes) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) { set_detail("cuTensorMapEncodeTiled", "driver entry point not found"); return PRK_ERR_DRIVER; }
     cuuint64_t gdim[2] = {cols, rows};
-    cuuint64_t gstride[1] = {cols * 2};
+    cuuint64_t gstride[1] = {cols * (uint64_t)elem_bytes};
     cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(gptr), gdim, gstride, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = fn(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                    const_cast<void*>(gptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         char msg[64];
         snprintf(msg, sizeof msg, "CUresult %d", (int)r);
@@ -93,6 +94,10 @@ int encode_tmap_2d_bf16(CUtensorMap* out, const void* gptr, uint64_t rows, uint6
         return PRK_ERR_DRIVER;
     }
     return PRK_OK;
+}
+int encode_tmap_2d_bf16(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                        uint32_t box_cols) {
+    return encode_tmap_2d(out, gptr, rows, cols, box_rows, box_cols, 2);
 }
 
 // ---- host-side bf16 helpers --------------------------------------------------
@@ -123,10 +128,10 @@ static int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
 // ---- workspace layout ---------------------------------------------------------
 constexpr int64_t kMaxSuper = 16384;   // frames per pose-chain launch (A' + Askin scratch)
-static int64_t chunk_frames() {        // frames per GEMM+skin step: keeps v_posed L2-resident
+static int64_t chunk_frames() {        // frames per GEMM+skin step (measured: larger is faster)
     static int64_t v = 0;
     if (v == 0) {
-        v = 640;
+        v = 8192;
         if (const char* e = getenv("PRK_CHUNK_FRAMES")) { long t = atol(e); if (t >= 128) v = t; }
         v = round_up(v, GEMM_BM);
     }
@@ -350,6 +355,14 @@ int prk_model_create(prk_model** out, int device, const float* vt, const float* 
     PRK_M(cudaMemcpy(m->d_wval, wv.data(), wv.size() * sizeof(float4), cudaMemcpyHostToDevice));
     PRK_M(cudaMalloc(&m->d_widx, wi.size() * 4));
     PRK_M(cudaMemcpy(m->d_widx, wi.data(), wi.size() * 4, cudaMemcpyHostToDevice));
+    {
+        std::vector<float> jc(72 + 720 + NBETA);
+        memcpy(jc.data(), m->pc.J_template, 72 * 4);
+        memcpy(jc.data() + 72, m->pc.Jdirs, 720 * 4);
+        memcpy(jc.data() + 792, m->pc.model_betas, NBETA * 4);
+        PRK_M(cudaMalloc(&m->d_Jc, jc.size() * 4));
+        PRK_M(cudaMemcpy(m->d_Jc, jc.data(), jc.size() * 4, cudaMemcpyHostToDevice));
+    }
 #undef PRK_M
     int rc = encode_tmap_2d_bf16(&m->tmap_B, m->d_Bmat, GEMM_N, GEMM_K, GEMM_BN, GEMM_BK);
     if (rc != PRK_OK) { prk_model_destroy(m); return rc; }
@@ -361,7 +374,7 @@ void prk_model_destroy(prk_model* model) {
     Model* m = model;
     if (!m) return;
     if (m->device >= 0) cudaSetDevice(m->device);
-    cudaFree(m->d_Bmat); cudaFree(m->d_wval); cudaFree(m->d_widx);
+    cudaFree(m->d_Bmat); cudaFree(m->d_wval); cudaFree(m->d_widx); cudaFree(m->d_Jc);
     delete m;
 }
 int prk_model_device(const prk_model* model) { return model ? model->device : -1; }

@@ -12,8 +12,9 @@
 //               4-stage mbarrier ring
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (M=128, N=256, K=16 x4 per
 //               k-block), accumulators double-buffered in TMEM (2 x 256 columns)
-//   warps 2-5   epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> 16-byte global
-//               stores of fp32 v_posed rows (row pitch 20736 floats)
+//   warps 2-5   epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> 128B-swizzled smem
+//               staging (per warp, double buffered) -> TMA store of 32x32 fp32 boxes, so every
+//               v_posed write is a full 128-byte line (row pitch 20736 floats)
 // Roofline: tensor pipe.  Algorithmic work 2*217*20670 = 8.97 MFLOP/frame; executed MMA
 // work 2*704*20736 = 29.2 MFLOP/frame (split precision x padding).
 #include "prk_internal.h"
@@ -28,7 +29,9 @@ constexpr int kStages = 4;
 constexpr int kATileBytes = GEMM_BM * GEMM_BK * 2;   // 16 KB
 constexpr int kBTileBytes = GEMM_BN * GEMM_BK * 2;   // 32 KB
 constexpr int kStageBytes = kATileBytes + kBTileBytes;
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int kStoreBufBytes = 32 * 32 * 4;            // 32 rows x 32 fp32 columns (128-byte rows, 128B swizzle)
+constexpr int kStoreBytes = 4 * 2 * kStoreBufBytes;    // 4 epilogue warps x 2 buffers
+constexpr int kSmemBytes = kStages * kStageBytes + kStoreBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int kThreads = 192;
 constexpr uint32_t kTmemCols = 512;
 constexpr int kUmmaK = 16;
@@ -78,6 +81,15 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
         ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
@@ -124,10 +136,11 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 __global__ void __launch_bounds__(kThreads, 1)
 blend_gemm_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid_constant__ CUtensorMap tmap_B,
-                  float* __restrict__ vposed, int num_m_blocks, int num_tiles) {
+                  const __grid_constant__ CUtensorMap tmap_D, int num_m_blocks, int num_tiles) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+    uint8_t* store_smem = smem + kStages * kStageBytes;   // [4 warps][2][32 rows x 128 B]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(store_smem + kStoreBytes);
     uint64_t* full_bar = bars;                 // [kStages]
     uint64_t* empty_bar = bars + kStages;      // [kStages]
     uint64_t* tfull_bar = bars + 2 * kStages;  // [2]
@@ -140,6 +153,7 @@ blend_gemm_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid_const
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_A)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_B)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_D)) : "memory");
         for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -201,32 +215,47 @@ blend_gemm_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid_const
             }
         }
     } else {
-        // ===== epilogue: TMEM -> registers -> global (warps 2..5 own lane quarters 2,3,0,1) =====
+        // ===== epilogue: TMEM -> registers -> swizzled smem -> TMA store (warps 2..5 own lane quarters 2,3,0,1) =====
         const int quarter = warp & 3;
+        uint8_t* my_store = store_smem + quarter * 2 * kStoreBufBytes;
         int acc = 0; uint32_t acc_phase = 0;
+        int sbuf = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int m_blk = tile % num_m_blocks, n_blk = tile / num_m_blocks;
             mbar_wait(&tfull_bar[acc], acc_phase);
             tcgen05_fence_after();
-            const int row = m_blk * GEMM_BM + quarter * 32 + lane;
-            float* dst = vposed + (size_t)row * VPOSED_PITCH + (size_t)n_blk * GEMM_BN;
+            const int row0 = m_blk * GEMM_BM + quarter * 32;
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * GEMM_BN;
 #pragma unroll 1
             for (int c = 0; c < GEMM_BN / 32; ++c) {
                 uint32_t r[32];
                 tmem_ld_32x32(taddr + (uint32_t)c * 32, r);
+                // the TMA store that last read this staging buffer (two chunks ago) must be done with it
+                if (lane == 0) tma_store_wait_read<1>();
+                __syncwarp();
                 tmem_ld_wait();
-                float4* d4 = reinterpret_cast<float4*>(dst + c * 32);
+                uint8_t* buf = my_store + sbuf * kStoreBufBytes;
+                // row = lane (128 B); 16-byte chunk q lands at q ^ (row & 7): the 128B-swizzle pattern of tmap_D
 #pragma unroll
-                for (int q = 0; q < 8; ++q)
-                    d4[q] = make_float4(__uint_as_float(r[4 * q + 0]), __uint_as_float(r[4 * q + 1]),
-                                        __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+                for (int q = 0; q < 8; ++q) {
+                    float4* d = reinterpret_cast<float4*>(buf + lane * 128 + ((q ^ (lane & 7)) << 4));
+                    *d = make_float4(__uint_as_float(r[4 * q + 0]), __uint_as_float(r[4 * q + 1]),
+                                     __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(&tmap_D, buf, n_blk * GEMM_BN + c * 32, row0);
+                    tma_store_commit();
+                }
+                sbuf ^= 1;
             }
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if (lane == 0) tma_store_wait_read<0>();   // smem must stay valid until the last store has read it
     }
 
     tcgen05_fence_before();
@@ -267,7 +296,9 @@ cudaError_t launch_blend_gemm(const Model& m, const CUtensorMap& tmap_A, int64_t
     const int num_tiles = num_m_blocks * GEMM_NBLOCKS;
     int grid = m.sm_count > 0 ? m.sm_count : 148;
     if (grid > num_tiles) grid = num_tiles;
-    blend_gemm_kernel<<<grid, kThreads, kSmemBytes, s>>>(tmap_A, m.tmap_B, d_vposed, num_m_blocks, num_tiles);
+    CUtensorMap tmap_D;   // v_posed [rows_pad][20736] fp32, box 32 rows x 32 columns, 128B swizzle
+    if (encode_tmap_2d(&tmap_D, d_vposed, (uint64_t)rows_pad, VPOSED_PITCH, 32, 32, 4) != PRK_OK) return cudaErrorInvalidValue;
+    blend_gemm_kernel<<<grid, kThreads, kSmemBytes, s>>>(tmap_A, m.tmap_B, tmap_D, num_m_blocks, num_tiles);
     count_launch();
     return cudaGetLastError();
 }

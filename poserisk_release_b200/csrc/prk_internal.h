@@ -55,7 +55,8 @@ struct prk_model {
     // device buffers
     uint16_t* d_Bmat = nullptr;    // [GEMM_N][GEMM_K] bf16 bits, K-major
     float4* d_wval = nullptr;      // [nnz_groups][NV] weights, 4 per group
-    uint32_t* d_widx = nullptr;    // [nnz_groups][NV] joint ids, 4 x u8 per group
+    uint32_t* d_widx = nullptr;
+    float* d_Jc = nullptr;         // J_template[72] | Jdirs[720] | model_betas[10] (lane-per-joint kernel)    // [nnz_groups][NV] joint ids, 4 x u8 per group
     CUtensorMap tmap_B;            // [GEMM_N][GEMM_K], box 64 x 256, 128B swizzle
 };
 
@@ -104,6 +105,8 @@ cudaError_t launch_score_hist(const prk_score_rec* d_scores, int64_t B, uint32_t
                               unsigned long long* d_hist, cudaStream_t s);
 
 // TMA descriptor helper (driver entry point fetched at run time; no libcuda link)
+int encode_tmap_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                   uint32_t box_cols, int elem_bytes);
 int encode_tmap_2d_bf16(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols,
                         uint32_t box_rows, uint32_t box_cols);
 

@@ -51,21 +51,54 @@ struct RowWriter {
 
 // batch_rodrigues + quat2mat in fp32 (rodrigues_layer.py:41-52, 13-38), row-major R[9].
 __device__ __forceinline__ void smpl_rodrigues(float ax, float ay, float az, float* R) {
-    const float x = ax + 1e-8f, y = ay + 1e-8f, z = az + 1e-8f;
-    const float angle = sqrtf(x * x + y * y + z * z);
-    const float inv = 1.0f / angle;
-    const float nx = ax * inv, ny = ay * inv, nz = az * inv;
+    // every product/sum is an explicit _rn op or fmaf: identical bits in every kernel variant
+    const float x = __fadd_rn(ax, 1e-8f), y = __fadd_rn(ay, 1e-8f), z = __fadd_rn(az, 1e-8f);
+    const float angle = sqrtf(fmaf(z, z, fmaf(y, y, __fmul_rn(x, x))));
+    const float nx = __fdiv_rn(ax, angle), ny = __fdiv_rn(ay, angle), nz = __fdiv_rn(az, angle);   // :45
     float s, c;
-    sincosf(angle * 0.5f, &s, &c);
-    float qw = c, qx = s * nx, qy = s * ny, qz = s * nz;
-    const float qinv = 1.0f / sqrtf(qw * qw + qx * qx + qy * qy + qz * qz);
-    qw *= qinv; qx *= qinv; qy *= qinv; qz *= qinv;
-    const float w2 = qw * qw, x2 = qx * qx, y2 = qy * qy, z2 = qz * qz;
-    const float wx = qw * qx, wy = qw * qy, wz = qw * qz;
-    const float xy = qx * qy, xz = qx * qz, yz = qy * qz;
-    R[0] = w2 + x2 - y2 - z2; R[1] = 2 * xy - 2 * wz;   R[2] = 2 * wy + 2 * xz;
-    R[3] = 2 * wz + 2 * xy;   R[4] = w2 - x2 + y2 - z2; R[5] = 2 * yz - 2 * wx;
-    R[6] = 2 * xz - 2 * wy;   R[7] = 2 * wx + 2 * yz;   R[8] = w2 - x2 - y2 + z2;
+    sincosf(__fmul_rn(angle, 0.5f), &s, &c);
+    float qw = c, qx = __fmul_rn(s, nx), qy = __fmul_rn(s, ny), qz = __fmul_rn(s, nz);
+    const float qn = sqrtf(fmaf(qz, qz, fmaf(qy, qy, fmaf(qx, qx, __fmul_rn(qw, qw)))));
+    qw = __fdiv_rn(qw, qn); qx = __fdiv_rn(qx, qn); qy = __fdiv_rn(qy, qn); qz = __fdiv_rn(qz, qn);           // :21
+    const float w2 = __fmul_rn(qw, qw), x2 = __fmul_rn(qx, qx), y2 = __fmul_rn(qy, qy), z2 = __fmul_rn(qz, qz);
+    const float wx = __fmul_rn(qw, qx), wy = __fmul_rn(qw, qy), wz = __fmul_rn(qw, qz);
+    const float xy = __fmul_rn(qx, qy), xz = __fmul_rn(qx, qz), yz = __fmul_rn(qy, qz);
+    R[0] = __fsub_rn(__fsub_rn(__fadd_rn(w2, x2), y2), z2);
+    R[1] = __fsub_rn(__fmul_rn(2.f, xy), __fmul_rn(2.f, wz));
+    R[2] = __fadd_rn(__fmul_rn(2.f, wy), __fmul_rn(2.f, xz));
+    R[3] = __fadd_rn(__fmul_rn(2.f, wz), __fmul_rn(2.f, xy));
+    R[4] = __fsub_rn(__fadd_rn(__fsub_rn(w2, x2), y2), z2);
+    R[5] = __fsub_rn(__fmul_rn(2.f, yz), __fmul_rn(2.f, wx));
+    R[6] = __fsub_rn(__fmul_rn(2.f, xz), __fmul_rn(2.f, wy));
+    R[7] = __fadd_rn(__fmul_rn(2.f, wx), __fmul_rn(2.f, yz));
+    R[8] = __fadd_rn(__fsub_rn(__fsub_rn(w2, x2), y2), z2);
+}
+
+// Shared arithmetic of both kernel variants (explicit fmaf / _rn ops so the thread-per-frame
+// and the lane-per-joint kernels produce bit-identical results).
+__device__ __forceinline__ float rest_joint(const float jt, const float* __restrict__ jd, const float* beta) {
+    float acc = jt;                                   // J = J_template + Jdirs * beta
+#pragma unroll
+    for (int k = 0; k < NBETA; ++k) acc = fmaf(jd[k], beta[k], acc);
+    return acc;
+}
+__device__ __forceinline__ float dot3(float a0, float a1, float a2, float b0, float b1, float b2) {
+    return fmaf(a2, b2, fmaf(a1, b1, __fmul_rn(a0, b0)));
+}
+// G = Gp * [R | t]   (smpl_layer.py:109-119), rows of 4
+__device__ __forceinline__ void compose(const float* Gp, const float* R, float t0, float t1, float t2, float* G) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const float g0 = Gp[r * 4 + 0], g1 = Gp[r * 4 + 1], g2 = Gp[r * 4 + 2];
+        G[r * 4 + 0] = dot3(g0, g1, g2, R[0], R[3], R[6]);
+        G[r * 4 + 1] = dot3(g0, g1, g2, R[1], R[4], R[7]);
+        G[r * 4 + 2] = dot3(g0, g1, g2, R[2], R[5], R[8]);
+        G[r * 4 + 3] = __fadd_rn(dot3(g0, g1, g2, t0, t1, t2), Gp[r * 4 + 3]);
+    }
+}
+// translation column of A_j = G_j - pack(G_j @ [j_rest; 0])  (smpl_layer.py:126-132)
+__device__ __forceinline__ float skin_t(const float* G, int r, float j0, float j1, float j2) {
+    return __fsub_rn(G[r * 4 + 3], dot3(G[r * 4 + 0], G[r * 4 + 1], G[r * 4 + 2], j0, j1, j2));
 }
 
 // mode bits
@@ -134,12 +167,7 @@ pose_chain_kernel(const __grid_constant__ PoseConsts pc, const float* __restrict
 
         // rest joint: J = J_template + Jdirs * beta
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            float acc = pc.J_template[j * 3 + c];
-#pragma unroll
-            for (int k = 0; k < NBETA; ++k) acc = fmaf(pc.Jdirs[(j * 3 + c) * NBETA + k], beta[k], acc);
-            J[j][c] = acc;
-        }
+        for (int c = 0; c < 3; ++c) J[j][c] = rest_joint(pc.J_template[j * 3 + c], &pc.Jdirs[(j * 3 + c) * NBETA], beta);
 
         if (pos == 0) {          // smpl_layer.py:105-106
 #pragma unroll
@@ -148,30 +176,21 @@ pose_chain_kernel(const __grid_constant__ PoseConsts pc, const float* __restrict
                 G[j][r * 4 + 2] = R[r * 3 + 2]; G[j][r * 4 + 3] = J[j][r];
             }
         } else {                 // smpl_layer.py:109-119
-            const float t0 = J[j][0] - J[par][0], t1 = J[j][1] - J[par][1], t2 = J[j][2] - J[par][2];
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                const float g0 = G[par][r * 4 + 0], g1 = G[par][r * 4 + 1], g2 = G[par][r * 4 + 2];
-                G[j][r * 4 + 0] = g0 * R[0] + g1 * R[3] + g2 * R[6];
-                G[j][r * 4 + 1] = g0 * R[1] + g1 * R[4] + g2 * R[7];
-                G[j][r * 4 + 2] = g0 * R[2] + g1 * R[5] + g2 * R[8];
-                G[j][r * 4 + 3] = g0 * t0 + g1 * t1 + g2 * t2 + G[par][r * 4 + 3];
-            }
+            compose(G[par], R, __fsub_rn(J[j][0], J[par][0]), __fsub_rn(J[j][1], J[par][1]),
+                    __fsub_rn(J[j][2], J[par][2]), G[j]);
         }
         // joints (smpl_layer.py:145), translation added now, centring applied below
-        jout[j * 3 + 0] = G[j][3] + o0;
-        jout[j * 3 + 1] = G[j][7] + o1;
-        jout[j * 3 + 2] = G[j][11] + o2;
+        jout[j * 3 + 0] = __fadd_rn(G[j][3], o0);
+        jout[j * 3 + 1] = __fadd_rn(G[j][7], o1);
+        jout[j * 3 + 2] = __fadd_rn(G[j][11], o2);
         if (j == center_idx) { c0 = G[j][3]; c1 = G[j][7]; c2 = G[j][11]; }
 
         if (kMesh) {             // A_j = G_j - pack(G_j @ [j_rest; 0])  (smpl_layer.py:126-132)
             float4* dst = reinterpret_cast<float4*>(Askin + (f * NJ + j) * 12);
 #pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                const float g0 = G[j][r * 4 + 0], g1 = G[j][r * 4 + 1], g2 = G[j][r * 4 + 2];
-                const float tt = G[j][r * 4 + 3] - (g0 * J[j][0] + g1 * J[j][1] + g2 * J[j][2]);
-                dst[r] = make_float4(g0, g1, g2, tt);
-            }
+            for (int r = 0; r < 3; ++r)
+                dst[r] = make_float4(G[j][r * 4 + 0], G[j][r * 4 + 1], G[j][r * 4 + 2],
+                                     skin_t(G[j], r, J[j][0], J[j][1], J[j][2]));
         }
     }
 
@@ -179,7 +198,8 @@ pose_chain_kernel(const __grid_constant__ PoseConsts pc, const float* __restrict
         o0 = -c0; o1 = -c1; o2 = -c2;
 #pragma unroll
         for (int k = 0; k < 72; k += 3) {
-            jout[k + 0] += o0; jout[k + 1] += o1; jout[k + 2] += o2;
+            jout[k + 0] = __fadd_rn(jout[k + 0], o0); jout[k + 1] = __fadd_rn(jout[k + 1], o1);
+            jout[k + 2] = __fadd_rn(jout[k + 2], o2);
         }
     }
 
@@ -198,6 +218,119 @@ pose_chain_kernel(const __grid_constant__ PoseConsts pc, const float* __restrict
 #pragma unroll
         for (int k = COL_ONES + 3; k < GEMM_K; ++k) rw.push(0);
     }
+}
+
+
+// ---- latency-optimised variant: one warp per frame, lane = joint ---------------------
+// For small batches the thread-per-frame kernel is bound by one thread's ~7,000 dependent
+// instructions.  Here the 24 joints' Rodrigues / rest joints run in parallel across lanes and
+// the kinematic chain is a level-synchronous scan in warp registers (__shfl_sync, tree depth
+// 8), cutting the critical path ~8x.  Same arithmetic helpers => bit-identical outputs.
+__device__ __constant__ int8_t c_parent[32] = {0, 0, 0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 9, 9, 12, 13, 14, 16, 17, 18, 19, 20, 21,
+                                               0, 0, 0, 0, 0, 0, 0, 0};
+__device__ __constant__ int8_t c_depth[32] = {0, 1, 1, 1, 2, 2, 2, 3, 3, 3, 4, 4, 4, 4, 4, 5, 5, 5, 6, 6, 7, 7, 8, 8,
+                                              99, 99, 99, 99, 99, 99, 99, 99};
+// position of joint j in the depth-first order used for the A' column blocks
+__device__ __constant__ int8_t c_dfs_pos[32] = {0, 1, 5, 9, 2, 6, 10, 3, 7, 11, 4, 8, 12, 14, 19, 13, 15, 20, 16, 21, 17, 22, 18, 23,
+                                                0, 0, 0, 0, 0, 0, 0, 0};
+constexpr int kWarpsPerBlock = 8;
+constexpr int64_t kWarpVariantMaxFrames = 65536;   // above this the thread-per-frame kernel fills the GPU
+
+template <bool kMesh>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+pose_chain_warp_kernel(const float* __restrict__ Jc /* J_template[72] | Jdirs[720] | model_betas[10] */,
+                       const float* __restrict__ pose, const float* __restrict__ betas,
+                       const float* __restrict__ trans, const BatchFlags* __restrict__ flags, uint32_t mode,
+                       int center_idx, int64_t B, uint16_t* __restrict__ Arows, float* __restrict__ Askin,
+                       float* __restrict__ off, float* __restrict__ joints) {
+    __shared__ __align__(16) uint16_t s_row[kMesh ? kWarpsPerBlock : 1][GEMM_K];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t f = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
+    if (f >= B) return;
+    const unsigned FULL = 0xffffffffu;
+
+    bool frame_betas = (mode & MODE_FRAME_BETAS_ALWAYS) != 0;
+    bool add_trans = (mode & MODE_TRANS_ALWAYS) != 0;
+    if (mode & MODE_FRAME_BETAS_FLAG) frame_betas = flags->betas_nonzero != 0;
+    if (mode & MODE_TRANS_FLAG) add_trans = flags->trans_nonzero != 0;
+    const bool centre = (center_idx >= 0) && !add_trans;
+
+    const bool active = lane < NJ;
+    const int j = active ? lane : 0;
+    float beta[NBETA];
+#pragma unroll
+    for (int k = 0; k < NBETA; ++k) beta[k] = frame_betas ? betas[f * NBETA + k] : Jc[72 + 720 + k];
+
+    float R[9];
+    smpl_rodrigues(pose[f * 72 + j * 3 + 0], pose[f * 72 + j * 3 + 1], pose[f * 72 + j * 3 + 2], R);
+    float J[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) J[c] = rest_joint(Jc[j * 3 + c], Jc + 72 + (j * 3 + c) * NBETA, beta);
+
+    const int par = c_parent[lane], depth = c_depth[lane];
+    float G[12];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {   // root transform (only lane 0's value is used)
+        G[r * 4 + 0] = R[r * 3 + 0]; G[r * 4 + 1] = R[r * 3 + 1]; G[r * 4 + 2] = R[r * 3 + 2]; G[r * 4 + 3] = J[r];
+    }
+    const float pj0 = __shfl_sync(FULL, J[0], par), pj1 = __shfl_sync(FULL, J[1], par), pj2 = __shfl_sync(FULL, J[2], par);
+    const float t0 = __fsub_rn(J[0], pj0), t1 = __fsub_rn(J[1], pj1), t2 = __fsub_rn(J[2], pj2);
+#pragma unroll 1
+    for (int d = 1; d <= 8; ++d) {
+        float Gp[12];
+#pragma unroll
+        for (int e = 0; e < 12; ++e) Gp[e] = __shfl_sync(FULL, G[e], par);
+        if (depth == d) compose(Gp, R, t0, t1, t2, G);
+    }
+
+    float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+    if (add_trans) { o0 = trans[f * 3 + 0]; o1 = trans[f * 3 + 1]; o2 = trans[f * 3 + 2]; }
+    float x0 = __fadd_rn(G[3], o0), x1 = __fadd_rn(G[7], o1), x2 = __fadd_rn(G[11], o2);
+    if (centre) {
+        o0 = -__shfl_sync(FULL, G[3], center_idx); o1 = -__shfl_sync(FULL, G[7], center_idx);
+        o2 = -__shfl_sync(FULL, G[11], center_idx);
+        x0 = __fadd_rn(x0, o0); x1 = __fadd_rn(x1, o1); x2 = __fadd_rn(x2, o2);
+    }
+    if (active) {
+        float* jo = joints + f * 72 + j * 3;
+        jo[0] = x0; jo[1] = x1; jo[2] = x2;
+    }
+    if (!kMesh) return;
+
+    if (active) {
+        float4* dst = reinterpret_cast<float4*>(Askin + (f * NJ + j) * 12);
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+            dst[r] = make_float4(G[r * 4 + 0], G[r * 4 + 1], G[r * 4 + 2], skin_t(G, r, J[0], J[1], J[2]));
+    }
+    if (lane == 0) { off[f * 3 + 0] = o0; off[f * 3 + 1] = o1; off[f * 3 + 2] = o2; }
+
+    // A' row assembled in shared memory, then written with 16-byte stores
+    uint16_t* row = s_row[warp];
+    if (active && j > 0) {
+        const int base = 27 * (c_dfs_pos[j] - 1);
+#pragma unroll
+        for (int e = 0; e < 9; ++e) {
+            const float v = R[e] - ((e == 0 || e == 4 || e == 8) ? 1.0f : 0.0f);
+            const uint16_t hi = bf16_bits(v);
+            const uint16_t lo = bf16_bits(v - bf16_val(hi));
+            row[base + e] = hi; row[base + 9 + e] = hi; row[base + 18 + e] = lo;
+        }
+    }
+    if (lane < NBETA) {
+        const uint16_t h = bf16_bits(beta[lane]);
+        const float r1 = beta[lane] - bf16_val(h);
+        const uint16_t m = bf16_bits(r1);
+        const uint16_t l = bf16_bits(r1 - bf16_val(m));
+        uint16_t* c = row + COL_BETA0 + 6 * lane;
+        c[0] = h; c[1] = h; c[2] = m; c[3] = h; c[4] = m; c[5] = l;
+    }
+    if (lane >= NJ && lane < NJ + 3) row[COL_ONES + (lane - NJ)] = 0x3F80;
+    for (int k = COL_ONES + 3 + lane; k < GEMM_K; k += 32) row[k] = 0;
+    __syncwarp();
+    const uint4* src = reinterpret_cast<const uint4*>(row);
+    uint4* dst = reinterpret_cast<uint4*>(Arows + f * GEMM_K);
+    for (int i = lane; i < GEMM_K / 8; i += 32) dst[i] = src[i];
 }
 
 // Whole-batch tests `torch.norm(x) == 0` (smpl_layer.py:87,148): true iff every x*x is 0
@@ -245,6 +378,17 @@ cudaError_t launch_pose_chain(const Model& m, const float* d_pose, const float* 
     if (d_trans) mode |= (center_idx < 0) ? MODE_TRANS_ALWAYS : MODE_TRANS_FLAG;
     const unsigned grid = (unsigned)((B + 127) / 128);
     const bool std_tree = m.pc.standard_tree != 0;
+    if (std_tree && B <= kWarpVariantMaxFrames) {   // latency-bound regime: one warp per frame
+        const unsigned g = (unsigned)((B + kWarpsPerBlock - 1) / kWarpsPerBlock);
+        if (full_mesh)
+            pose_chain_warp_kernel<true><<<g, kWarpsPerBlock * 32, 0, s>>>(m.d_Jc, d_pose, d_betas, d_trans, d_flags, mode,
+                                                                           center_idx, B, d_Arows, d_Askin, d_off, d_joints);
+        else
+            pose_chain_warp_kernel<false><<<g, kWarpsPerBlock * 32, 0, s>>>(m.d_Jc, d_pose, d_betas, d_trans, d_flags, mode,
+                                                                            center_idx, B, d_Arows, d_Askin, d_off, d_joints);
+        count_launch();
+        return cudaGetLastError();
+    }
 #define PRK_LAUNCH(STD, MESH)                                                              \
     pose_chain_kernel<STD, MESH><<<grid, 128, 0, s>>>(m.pc, d_pose, d_betas, d_trans, d_flags, \
                                                       mode, center_idx, B, d_Arows, d_Askin, \

@@ -540,6 +540,53 @@ score_hist_kernel(const prk_score_rec* __restrict__ recs, int64_t B, uint32_t wh
         atomicAdd(&hist[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
 }
 
+// ---- latency-optimised variant for small batches ----------------------------------------
+// 16 lanes per frame (two frames per warp): lanes 0..11 each turn one scored joint into
+// Euler angles (the float64 sincos/atan2 chains are the long pole), the angles meet in
+// shared memory, then lane 0 runs the REBA ladders and lane 1 the RULA ladders of the frame.
+// Same device functions as the thread-per-frame kernel => bit-identical records.
+constexpr int kFramesPerBlockLanes = 8;
+template <typename T>
+__global__ void __launch_bounds__(kFramesPerBlockLanes * 16)
+score_pose_lanes_kernel(const T* __restrict__ pose, const prk_addinfo* __restrict__ info,
+                        const int32_t* __restrict__ track, int64_t B, uint32_t which,
+                        prk_score_rec* __restrict__ out) {
+    __shared__ double s_e[kFramesPerBlockLanes][N_SLOTS][3];
+    __shared__ __align__(16) prk_score_rec s_rec[kFramesPerBlockLanes];
+    __shared__ int s_bad[kFramesPerBlockLanes];
+    const int fl = threadIdx.x >> 4, slot = threadIdx.x & 15;
+    const int64_t i = (int64_t)blockIdx.x * kFramesPerBlockLanes + fl;
+    const bool live = i < B;
+    if (slot == 0) {
+        s_bad[fl] = 0;
+        uint4* z = reinterpret_cast<uint4*>(&s_rec[fl]);
+        z[0] = make_uint4(0, 0, 0, 0); z[1] = make_uint4(0, 0, 0, 0);
+    }
+    __syncwarp();
+    if (live && slot < N_SLOTS) {
+        const int j = slot_joint(slot);
+        const T* p = pose + i * 72 + j * 3;
+        double ex, ey, ez;
+        const bool bad = euler_from_axis_angle<sizeof(T) == 4>((double)p[0], (double)p[1], (double)p[2], ex, ey, ez);
+        s_e[fl][slot][0] = ex; s_e[fl][slot][1] = ey; s_e[fl][slot][2] = ez;
+        if (bad) atomicOr(&s_bad[fl], 1);
+    }
+    __syncwarp();
+    if (live && slot < 2) {
+        Angles A;
+#pragma unroll
+        for (int s = 0; s < N_SLOTS; ++s) { A.a[s][0] = s_e[fl][s][0]; A.a[s][1] = s_e[fl][s][1]; A.a[s][2] = s_e[fl][s][2]; }
+        const prk_addinfo* ai = info + (track ? track[i] : 0);
+        if (slot == 0 && (which & PRK_SCORE_REBA)) reba_frame(A, ai->reba, s_rec[fl]);
+        if (slot == 1 && (which & PRK_SCORE_RULA)) rula_frame(A, ai->rula, s_rec[fl]);
+    }
+    __syncwarp();
+    if (live && slot == 0) {
+        s_rec[fl].flags = (uint8_t)(s_bad[fl] ? 1 : 0);
+        store_rec(out + i, s_rec[fl]);
+    }
+}
+
 static inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
 
 cudaError_t launch_score_pose(const void* d_pose, int pose_dtype, const prk_addinfo* d_info,
@@ -547,6 +594,15 @@ cudaError_t launch_score_pose(const void* d_pose, int pose_dtype, const prk_addi
                               prk_score_rec* d_out, double* d_euler_out, uint32_t debug_mask,
                               const int8_t* debug_slot, int n_debug, cudaStream_t s) {
     if (B == 0) return cudaSuccess;
+    if (n_debug == 0 && B <= 131072) {   // latency-bound regime: spread each frame over 16 lanes
+        const unsigned g = grid_for(B, kFramesPerBlockLanes);
+        if (pose_dtype == PRK_DTYPE_F32)
+            score_pose_lanes_kernel<float><<<g, kFramesPerBlockLanes * 16, 0, s>>>((const float*)d_pose, d_info, d_track, B, which, d_out);
+        else
+            score_pose_lanes_kernel<double><<<g, kFramesPerBlockLanes * 16, 0, s>>>((const double*)d_pose, d_info, d_track, B, which, d_out);
+        count_launch();
+        return cudaGetLastError();
+    }
     if (pose_dtype == PRK_DTYPE_F32)
         score_pose_kernel<float><<<grid_for(B, 128), 128, 0, s>>>(
             (const float*)d_pose, d_info, d_track, B, which, d_out, d_euler_out, debug_mask,

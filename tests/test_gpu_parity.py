@@ -428,6 +428,29 @@ def test_aggregate_matches_reference_formula(engine):
         assert got == pytest.approx(expect, abs=1e-9)
 
 
+def test_kernel_variants_bit_identical(engine, layers):
+    """Small batches use lane-per-joint kernels (pose chain: one warp per frame; scoring: 16 lanes
+    per frame), big batches thread-per-frame kernels.  Both must give identical bits."""
+    from poserisk_release_b200 import _runtime
+    g = torch.Generator().manual_seed(77)
+    n_big = 140000
+    pose = (torch.randn(n_big, 72, generator=g) * 0.5).cuda()
+    betas = torch.randn(n_big, 10, generator=g).cuda()
+    trans = torch.randn(n_big, 3, generator=g).cuda()
+    big = engine.run(pose, betas, trans, add_info=EXAMPLE_INFO, want_verts=False)
+    small = engine.run(pose[:3000], betas[:3000], trans[:3000], add_info=EXAMPLE_INFO, want_verts=False)
+    assert torch.equal(big['joints'][:3000], small['joints'])
+    assert torch.equal(big['scores'][:3000], small['scores'])
+    ref = oracle.score_pose(pose.cpu().numpy(), EXAMPLE_INFO)
+    assert same_records(_runtime.records_to_numpy(big['scores']), ref).all()
+    # full-mesh path: thread-per-frame pose kernel (B > 65536) vs warp-per-frame on a slice
+    lay = layers['neutral']
+    nb = 66000
+    v_big, j_big = lay(pose[:nb], betas[:nb], trans[:nb])
+    v_small, j_small = lay(pose[nb - 500:nb], betas[nb - 500:nb], trans[nb - 500:nb])
+    assert torch.equal(v_big[nb - 500:], v_small) and torch.equal(j_big[nb - 500:], j_small)
+
+
 def test_launch_counter_counts_our_kernels(engine):
     from poserisk_release_b200 import _lib
     before = _lib.launch_count()

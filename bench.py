@@ -98,6 +98,7 @@ def run_reference_arm(args):
         return
     from oracle import oracle
     oracle.build()
+    oracle.use_all_cores()
     # size one step so that it takes about a second on this host
     fps0, _, threads = cpu_throughput(256)
     frames = int(min(FRAMES_PER_STEP, max(256, fps0 * 1.0)))
@@ -294,10 +295,16 @@ def run_gpu_arm(args):
                      "peak_source": peaks['source']}
         dominant = roof_gemm if gemm_s >= skin_s else roof_skin
         other = roof_skin if dominant is roof_gemm else roof_gemm
-        # bounded CPU sample of the same workload
-        fps0, _, threads = cpu_throughput(256)
-        n_cpu = int(min(8 * FRAMES_PER_STEP, max(512, fps0 * 12)))
-        cpu_fps, cpu_dt, threads = cpu_throughput(n_cpu)
+        cpu_baseline = None
+        if world == 1:   # bounded CPU sample of the same workload (rank 0 at N=1 only)
+            from oracle import oracle
+            oracle.use_all_cores()
+            fps0, _, threads = cpu_throughput(256)
+            n_cpu = int(min(8 * FRAMES_PER_STEP, max(512, fps0 * 12)))
+            cpu_fps, cpu_dt, threads = cpu_throughput(n_cpu)
+            cpu_baseline = {"value": cpu_fps, "unit": UNIT, "cores": threads, "kind": "port",
+                            "sample": f"{n_cpu} frames of the same workload, {cpu_dt:.1f} s, C/OpenMP oracle "
+                                      f"port of the reference path (oracle/poserisk_oracle.c)"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": config_dict(world), "clocks": clocks,
@@ -307,9 +314,7 @@ def run_gpu_arm(args):
                         "note": "vertices stay in HBM (the reference reads them only for a debug .obj)"},
                 "gpu_launches": int(launches),
                 "roofline": dominant, "roofline_other": other, "stages": per_stage,
-                "cpu_baseline": {"value": cpu_fps, "unit": UNIT, "cores": threads, "kind": "port",
-                                 "sample": f"{n_cpu} frames of the same workload, {cpu_dt:.1f} s, C/OpenMP oracle "
-                                           f"port of the reference path (oracle/poserisk_oracle.c)"}}
+                "cpu_baseline": cpu_baseline}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -121,3 +121,13 @@ def smpl_forward(model, pose, betas=None, trans=None, center_idx=None, want_vert
 
 def num_threads() -> int:
     return int(lib().orc_num_threads())
+
+
+def use_all_cores() -> int:
+    """Use every core this process may run on (torchrun exports OMP_NUM_THREADS=1)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    lib().orc_set_num_threads(C.c_int(n))
+    return num_threads()

@@ -69,6 +69,15 @@ int orc_num_threads(void) {
 #endif
 }
 
+/* torchrun exports OMP_NUM_THREADS=1; the CPU arm of the bench asks for all cores explicitly */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 static int iclip(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 /* ===========================================================================

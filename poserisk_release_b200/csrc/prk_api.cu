@@ -128,10 +128,15 @@ static int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
 // ---- workspace layout ---------------------------------------------------------
 constexpr int64_t kMaxSuper = 16384;   // frames per pose-chain launch (A' + Askin scratch)
-static int64_t chunk_frames() {        // frames per GEMM+skin step (measured: larger is faster)
+static int overlap_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("PRK_OVERLAP"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v;
+}
+static int64_t chunk_frames() {        // frames per GEMM+skin step (pipeline granularity)
     static int64_t v = 0;
     if (v == 0) {
-        v = 8192;
+        v = 4096;
         if (const char* e = getenv("PRK_CHUNK_FRAMES")) { long t = atol(e); if (t >= 128) v = t; }
         v = round_up(v, GEMM_BM);
     }
@@ -140,7 +145,7 @@ static int64_t chunk_frames() {        // frames per GEMM+skin step (measured: l
 
 struct Layout {
     int64_t S = 0, C = 0;   // super-chunk and chunk frames (multiples of 128)
-    size_t off_flags = 0, off_arows = 0, off_askin = 0, off_off = 0, off_vposed = 0, total = 0;
+    size_t off_flags = 0, off_arows = 0, off_askin = 0, off_off = 0, off_vposed = 0, vposed_stride = 0, total = 0;
 };
 static size_t align_up(size_t x) { return (x + 1023) & ~(size_t)1023; }
 
@@ -153,7 +158,8 @@ static Layout make_layout(int64_t S, int64_t C, bool mesh) {
         L.off_arows = o;  o += align_up((size_t)S * GEMM_K * 2);
         L.off_askin = o;  o += align_up((size_t)S * NJ * 12 * 4);
         L.off_off = o;    o += align_up((size_t)S * 3 * 4);
-        L.off_vposed = o; o += align_up((size_t)C * VPOSED_PITCH * 4);
+        L.vposed_stride = align_up((size_t)C * VPOSED_PITCH * 4);
+        L.off_vposed = o; o += 2 * L.vposed_stride;       // double buffered: GEMM(c+1) overlaps skinning(c)
     }
     L.total = o;
     return L;
@@ -197,7 +203,6 @@ static int forward_impl(Model* m, const float* d_pose, const float* d_betas, con
     uint16_t* d_arows = reinterpret_cast<uint16_t*>(w + L.off_arows);
     float* d_askin = reinterpret_cast<float*>(w + L.off_askin);
     float* d_off = reinterpret_cast<float*>(w + L.off_off);
-    float* d_vposed = reinterpret_cast<float*>(w + L.off_vposed);
 
     if (pose_chain_needs_flags(*m, d_betas, d_trans, center_idx)) PRK_CUDA(launch_batch_flags(d_betas, d_trans, B, d_flags, s));
 
@@ -211,21 +216,39 @@ static int forward_impl(Model* m, const float* d_pose, const float* d_betas, con
                                        d_askin, d_off, d_joints + s0 * 72, s));
         }
         if (!mesh) continue;
-        for (int64_t c0 = 0; c0 < ns; c0 += L.C) {
+        // Two-stream pipeline: the tensor-bound blend GEMM of chunk c+1 (on the model's own
+        // stream) runs under the LSU/HBM-bound skinning of chunk c (on the caller's stream);
+        // v_posed is double buffered.  PRK_OVERLAP=0 keeps everything on the caller's stream.
+        const bool overlap = overlap_enabled() && m->s_gemm != nullptr;
+        cudaStream_t sg = overlap ? m->s_gemm : s;
+        if (overlap) {
+            PRK_CUDA(cudaEventRecord(m->ev_pose, s));
+            PRK_CUDA(cudaStreamWaitEvent(sg, m->ev_pose, 0));
+        }
+        int64_t ci = 0;
+        for (int64_t c0 = 0; c0 < ns; c0 += L.C, ++ci) {
             const int64_t nc = (ns - c0) < L.C ? (ns - c0) : L.C;
             const int64_t rows_pad = round_up(nc, GEMM_BM);
+            const int buf = (int)(ci & 1);
+            float* vp = reinterpret_cast<float*>(w + L.off_vposed + (size_t)buf * L.vposed_stride);
             CUtensorMap tmA;
             int rc = encode_tmap_2d_bf16(&tmA, d_arows + c0 * GEMM_K, (uint64_t)rows_pad, GEMM_K, GEMM_BM, GEMM_BK);
             if (rc != PRK_OK) return rc;
+            if (overlap && ci >= 2) PRK_CUDA(cudaStreamWaitEvent(sg, m->ev_skin[buf], 0));   // buffer free again
             {
-                StageScope sc(1, s);
-                PRK_CUDA(launch_blend_gemm(*m, tmA, rows_pad, d_vposed, s));
+                StageScope sc(1, sg);
+                PRK_CUDA(launch_blend_gemm(*m, tmA, rows_pad, vp, sg));
+            }
+            if (overlap) {
+                PRK_CUDA(cudaEventRecord(m->ev_gemm[buf], sg));
+                PRK_CUDA(cudaStreamWaitEvent(s, m->ev_gemm[buf], 0));
             }
             {
                 StageScope sc(2, s);
-                PRK_CUDA(launch_skin(*m, d_vposed, d_askin + c0 * NJ * 12, d_off + c0 * 3, nc,
+                PRK_CUDA(launch_skin(*m, vp, d_askin + c0 * NJ * 12, d_off + c0 * 3, nc,
                                      d_verts + (size_t)(s0 + c0) * NVC, s));
             }
+            if (overlap) PRK_CUDA(cudaEventRecord(m->ev_skin[buf], s));
         }
     }
     return PRK_OK;
@@ -363,6 +386,15 @@ int prk_model_create(prk_model** out, int device, const float* vt, const float* 
         PRK_M(cudaMalloc(&m->d_Jc, jc.size() * 4));
         PRK_M(cudaMemcpy(m->d_Jc, jc.data(), jc.size() * 4, cudaMemcpyHostToDevice));
     }
+    PRK_M(cudaStreamCreateWithFlags(&m->s_gemm, cudaStreamNonBlocking));
+    PRK_M(cudaStreamCreateWithFlags(&m->s_score, cudaStreamNonBlocking));
+    PRK_M(cudaEventCreateWithFlags(&m->ev_pose, cudaEventDisableTiming));
+    PRK_M(cudaEventCreateWithFlags(&m->ev_in, cudaEventDisableTiming));
+    PRK_M(cudaEventCreateWithFlags(&m->ev_score, cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) {
+        PRK_M(cudaEventCreateWithFlags(&m->ev_gemm[i], cudaEventDisableTiming));
+        PRK_M(cudaEventCreateWithFlags(&m->ev_skin[i], cudaEventDisableTiming));
+    }
 #undef PRK_M
     int rc = encode_tmap_2d_bf16(&m->tmap_B, m->d_Bmat, GEMM_N, GEMM_K, GEMM_BN, GEMM_BK);
     if (rc != PRK_OK) { prk_model_destroy(m); return rc; }
@@ -375,6 +407,12 @@ void prk_model_destroy(prk_model* model) {
     if (!m) return;
     if (m->device >= 0) cudaSetDevice(m->device);
     cudaFree(m->d_Bmat); cudaFree(m->d_wval); cudaFree(m->d_widx); cudaFree(m->d_Jc);
+    if (m->s_gemm) { cudaStreamSynchronize(m->s_gemm); cudaStreamDestroy(m->s_gemm); }
+    if (m->s_score) { cudaStreamSynchronize(m->s_score); cudaStreamDestroy(m->s_score); }
+    if (m->ev_pose) cudaEventDestroy(m->ev_pose);
+    if (m->ev_in) cudaEventDestroy(m->ev_in);
+    if (m->ev_score) cudaEventDestroy(m->ev_score);
+    for (int i = 0; i < 2; ++i) { if (m->ev_gemm[i]) cudaEventDestroy(m->ev_gemm[i]); if (m->ev_skin[i]) cudaEventDestroy(m->ev_skin[i]); }
     delete m;
 }
 int prk_model_device(const prk_model* model) { return model ? model->device : -1; }
@@ -451,9 +489,22 @@ int prk_pipeline(prk_model* model, const float* d_pose, const float* d_betas, co
     if (!m || !d_info || (B > 0 && !d_scores)) { set_detail("prk_pipeline", "invalid argument"); return PRK_ERR_INVALID_ARG; }
     PRK_CUDA(cudaSetDevice(m->device));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    // scoring only reads the pose: it runs on the model's scoring stream, beside the mesh path
+    const bool overlap = overlap_enabled() && m->s_score != nullptr && B > 0;
+    cudaStream_t ss = overlap ? m->s_score : s;
+    if (overlap) {
+        PRK_CUDA(cudaEventRecord(m->ev_in, s));
+        PRK_CUDA(cudaStreamWaitEvent(ss, m->ev_in, 0));
+        StageScope sc(3, ss);
+        PRK_CUDA(launch_score_pose(d_pose, PRK_DTYPE_F32, d_info, d_track, B, PRK_SCORE_REBA | PRK_SCORE_RULA, d_scores,
+                                   nullptr, 0, nullptr, 0, ss));
+    }
+    if (overlap) PRK_CUDA(cudaEventRecord(m->ev_score, ss));
     int rc = forward_impl(m, d_pose, d_betas, d_trans, center_idx, B, d_verts, d_joints, ws, ws_bytes, s);
     if (rc != PRK_OK) return rc;
-    {
+    if (overlap) {
+        PRK_CUDA(cudaStreamWaitEvent(s, m->ev_score, 0));
+    } else {
         StageScope sc(3, s);
         PRK_CUDA(launch_score_pose(d_pose, PRK_DTYPE_F32, d_info, d_track, B, PRK_SCORE_REBA | PRK_SCORE_RULA, d_scores,
                                    nullptr, 0, nullptr, 0, s));

@@ -25,7 +25,7 @@ namespace prk {
 
 namespace {
 
-constexpr int kStages = 4;
+constexpr int kStages = 3;   // 3 x 48 KB + 32 KB store staging = 177 KB: leaves room for 4 skinning blocks per SM
 constexpr int kATileBytes = GEMM_BM * GEMM_BK * 2;   // 16 KB
 constexpr int kBTileBytes = GEMM_BN * GEMM_BK * 2;   // 32 KB
 constexpr int kStageBytes = kATileBytes + kBTileBytes;

@@ -58,6 +58,10 @@ struct prk_model {
     uint32_t* d_widx = nullptr;
     float* d_Jc = nullptr;         // J_template[72] | Jdirs[720] | model_betas[10] (lane-per-joint kernel)    // [nnz_groups][NV] joint ids, 4 x u8 per group
     CUtensorMap tmap_B;            // [GEMM_N][GEMM_K], box 64 x 256, 128B swizzle
+    // internal streams/events of the two-stream pipeline (GEMM under skinning, scoring aside)
+    cudaStream_t s_gemm = nullptr, s_score = nullptr;
+    cudaEvent_t ev_pose = nullptr, ev_in = nullptr, ev_score = nullptr;
+    cudaEvent_t ev_gemm[2] = {nullptr, nullptr}, ev_skin[2] = {nullptr, nullptr};
 };
 
 namespace prk {

@@ -76,8 +76,8 @@ static EncodeTiledFn get_encode_fn() {
 
 // [rows][cols] row-major tensor of bf16 (elem_bytes 2) or fp32 (elem_bytes 4), box = box_rows x box_cols with
 // box_cols * elem_bytes == 128 (SWIZZLE_128B)
-int encode_tmap_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, uint32_t box_rows,
-                   uint32_t box_cols, int elem_bytes) {
+int encode_tmap_2d_ex(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                      uint32_t box_cols, int elem_bytes, int swizzle128) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) { set_detail("cuTensorMapEncodeTiled", "driver entry point not found"); return PRK_ERR_DRIVER; }
     cuuint64_t gdim[2] = {cols, rows};
@@ -86,7 +86,8 @@ int encode_tmap_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t c
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                     const_cast<void*>(gptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         char msg[64];
         snprintf(msg, sizeof msg, "CUresult %d", (int)r);
@@ -94,6 +95,10 @@ int encode_tmap_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t c
         return PRK_ERR_DRIVER;
     }
     return PRK_OK;
+}
+int encode_tmap_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                   uint32_t box_cols, int elem_bytes) {
+    return encode_tmap_2d_ex(out, gptr, rows, cols, box_rows, box_cols, elem_bytes, 1);
 }
 int encode_tmap_2d_bf16(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, uint32_t box_rows,
                         uint32_t box_cols) {
@@ -131,6 +136,11 @@ constexpr int64_t kMaxSuper = 16384;   // frames per pose-chain launch (A' + Ask
 static int overlap_enabled() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("PRK_OVERLAP"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v;
+}
+static int skin_mma_enabled() {      // PRK_SKIN=simt selects the shared-memory SIMT skinning kernel
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("PRK_SKIN"); v = (e && e[0] == 's') ? 0 : 1; }
     return v;
 }
 static int64_t chunk_frames() {        // frames per GEMM+skin step (pipeline granularity)
@@ -245,8 +255,12 @@ static int forward_impl(Model* m, const float* d_pose, const float* d_betas, con
             }
             {
                 StageScope sc(2, s);
-                PRK_CUDA(launch_skin(*m, vp, d_askin + c0 * NJ * 12, d_off + c0 * 3, nc,
-                                     d_verts + (size_t)(s0 + c0) * NVC, s));
+                if (skin_mma_enabled())
+                    PRK_CUDA(launch_skin_mma(*m, vp, rows_pad, d_askin + c0 * NJ * 12, d_off + c0 * 3, nc,
+                                             d_verts + (size_t)(s0 + c0) * NVC, s));
+                else
+                    PRK_CUDA(launch_skin(*m, vp, d_askin + c0 * NJ * 12, d_off + c0 * 3, nc,
+                                         d_verts + (size_t)(s0 + c0) * NVC, s));
             }
             if (overlap) PRK_CUDA(cudaEventRecord(m->ev_skin[buf], s));
         }

@@ -95,6 +95,10 @@ cudaError_t launch_blend_simt(const Model& m, const uint16_t* d_Arows, int64_t r
 cudaError_t launch_skin(const Model& m, const float* d_vposed, const float* d_Askin,
                         const float* d_off, int64_t B, float* d_verts, cudaStream_t s);
 
+// K2b on tensor cores (prk_skin_mma.cu); d_vposed must hold rows_pad >= round_up(B,128) rows
+cudaError_t launch_skin_mma(const Model& m, const float* d_vposed, int64_t rows_pad, const float* d_Askin,
+                            const float* d_off, int64_t B, float* d_verts, cudaStream_t s);
+
 // K3: Euler angles + REBA/RULA
 cudaError_t launch_score_pose(const void* d_pose, int pose_dtype, const prk_addinfo* d_info,
                               const int32_t* d_track, int64_t B, uint32_t which,
@@ -109,6 +113,8 @@ cudaError_t launch_score_hist(const prk_score_rec* d_scores, int64_t B, uint32_t
                               unsigned long long* d_hist, cudaStream_t s);
 
 // TMA descriptor helper (driver entry point fetched at run time; no libcuda link)
+int encode_tmap_2d_ex(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                      uint32_t box_cols, int elem_bytes, int swizzle128);
 int encode_tmap_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, uint32_t box_rows,
                    uint32_t box_cols, int elem_bytes);
 int encode_tmap_2d_bf16(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols,

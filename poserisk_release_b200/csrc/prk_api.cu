@@ -143,6 +143,11 @@ static int skin_mma_enabled() {      // PRK_SKIN=simt selects the shared-memory 
     if (v < 0) { const char* e = getenv("PRK_SKIN"); v = (e && e[0] == 's') ? 0 : 1; }
     return v;
 }
+static int fused_enabled() {         // PRK_PATH=split selects the separate GEMM -> v_posed -> skinning kernels
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("PRK_PATH"); v = (e && e[0] == 's') ? 0 : 1; }
+    return v;
+}
 static int64_t chunk_frames() {        // frames per GEMM+skin step (pipeline granularity)
     static int64_t v = 0;
     if (v == 0) {
@@ -164,7 +169,11 @@ static Layout make_layout(int64_t S, int64_t C, bool mesh) {
     L.S = S; L.C = C;
     size_t o = 0;
     L.off_flags = o; o += 1024;
-    if (mesh) {
+    if (mesh && fused_enabled()) {                        // K12: no v_posed scratch at all
+        L.off_arows = o;  o += align_up((size_t)S * FUSED_K * 2);
+        L.off_askin = o;  o += align_up((size_t)S * NJ * 12 * 4);
+        L.off_off = o;    o += align_up((size_t)S * 3 * 4);
+    } else if (mesh) {
         L.off_arows = o;  o += align_up((size_t)S * GEMM_K * 2);
         L.off_askin = o;  o += align_up((size_t)S * NJ * 12 * 4);
         L.off_off = o;    o += align_up((size_t)S * 3 * 4);
@@ -222,10 +231,19 @@ static int forward_impl(Model* m, const float* d_pose, const float* d_betas, con
         {
             StageScope sc(0, s);
             PRK_CUDA(launch_pose_chain(*m, d_pose + s0 * 72, d_betas ? d_betas + s0 * NBETA : nullptr,
-                                       d_trans ? d_trans + s0 * 3 : nullptr, d_flags, center_idx, ns, mesh, d_arows,
-                                       d_askin, d_off, d_joints + s0 * 72, s));
+                                       d_trans ? d_trans + s0 * 3 : nullptr, d_flags, center_idx, ns, mesh,
+                                       mesh && fused_enabled(), d_arows, d_askin, d_off, d_joints + s0 * 72, s));
         }
         if (!mesh) continue;
+        if (fused_enabled()) {
+            const int64_t rows_pad = round_up(ns, FUSED_BM);
+            CUtensorMap tmA;
+            int rc = encode_tmap_2d_bf16(&tmA, d_arows, (uint64_t)rows_pad, FUSED_K, FUSED_BM, 64);
+            if (rc != PRK_OK) return rc;
+            StageScope sc(1, s);
+            PRK_CUDA(launch_fused(*m, tmA, rows_pad, d_askin, d_off, ns, d_verts + (size_t)s0 * NVC, s));
+            continue;
+        }
         // Two-stream pipeline: the tensor-bound blend GEMM of chunk c+1 (on the model's own
         // stream) runs under the LSU/HBM-bound skinning of chunk c (on the caller's stream);
         // v_posed is double buffered.  PRK_OVERLAP=0 keeps everything on the caller's stream.
@@ -360,6 +378,28 @@ int prk_model_create(prk_model** out, int device, const float* vt, const float* 
         row[COL_ONES] = h; row[COL_ONES + 1] = mm; row[COL_ONES + 2] = l;
     }
 
+    // K12 operand (prk_internal.h "K12 operand layout"): every hi/lo part stored once
+    std::vector<uint16_t> B2((size_t)GEMM_N * FUSED_K, 0);
+    for (int n = 0; n < NVC; ++n) {
+        uint16_t* row = &B2[(size_t)n * FUSED_K];
+        for (int pos = 1; pos < NJ; ++pos) {
+            const int j = std_tree ? kSmplDfs[pos] : pos;
+            for (int e = 0; e < 9; ++e) {
+                const float v = pd[(size_t)n * NPOSE + (j - 1) * 9 + e];
+                const uint16_t hi = f2bf(v);
+                row[9 * (pos - 1) + e] = hi;
+                row[FUSED_COL_LO + 9 * (pos - 1) + e] = f2bf(v - bf2f(hi));
+            }
+        }
+        uint16_t sp[3];
+        for (int b = 0; b < NBETA; ++b) {
+            split3(sd[(size_t)n * NBETA + b], sp[0], sp[1], sp[2]);
+            for (int q = 0; q < 3; ++q) row[FUSED_COL_BETA + 16 * q + b] = sp[q];
+        }
+        split3(vt[n], sp[0], sp[1], sp[2]);
+        for (int q = 0; q < 3; ++q) row[FUSED_COL_BETA + 16 * q + NBETA] = sp[q];
+    }
+
     // compacted skinning weights
     int mx = 0;
     for (int v = 0; v < NV; ++v) {
@@ -384,10 +424,28 @@ int prk_model_create(prk_model** out, int device, const float* vt, const float* 
         }
     }
 
+    // the same pairs per 32-vertex tile for K12: [tile][group][32 float4 weights | 32 x 4 u8 (3 * joint)]
+    std::vector<uint8_t> wp((size_t)FUSED_NT * m->nnz_groups * FUSED_WGROUP_BYTES, 0);
+    for (int v = 0; v < NV; ++v) {
+        const int tile = v / FUSED_VT, vl = v % FUSED_VT;
+        for (int g = 0; g < m->nnz_groups; ++g) {
+            uint8_t* base = &wp[((size_t)tile * m->nnz_groups + g) * FUSED_WGROUP_BYTES];
+            memcpy(base + vl * 16, &wv[(size_t)g * NV + v], 16);
+            const uint32_t id = wi[(size_t)g * NV + v];
+            uint32_t id3 = 0;
+            for (int k = 0; k < 4; ++k) id3 |= (((id >> (8 * k)) & 0xFFu) * 3u) << (8 * k);
+            memcpy(base + FUSED_VT * 16 + vl * 4, &id3, 4);
+        }
+    }
+
     cudaError_t e;
 #define PRK_M(expr) do { e = (expr); if (e != cudaSuccess) { prk_model_destroy(m); return cuda_fail(e, #expr); } } while (0)
     PRK_M(cudaMalloc(&m->d_Bmat, Bm.size() * 2));
     PRK_M(cudaMemcpy(m->d_Bmat, Bm.data(), Bm.size() * 2, cudaMemcpyHostToDevice));
+    PRK_M(cudaMalloc(&m->d_B2, B2.size() * 2));
+    PRK_M(cudaMemcpy(m->d_B2, B2.data(), B2.size() * 2, cudaMemcpyHostToDevice));
+    PRK_M(cudaMalloc(&m->d_wpack, wp.size()));
+    PRK_M(cudaMemcpy(m->d_wpack, wp.data(), wp.size(), cudaMemcpyHostToDevice));
     PRK_M(cudaMalloc(&m->d_wval, wv.size() * sizeof(float4)));
     PRK_M(cudaMemcpy(m->d_wval, wv.data(), wv.size() * sizeof(float4), cudaMemcpyHostToDevice));
     PRK_M(cudaMalloc(&m->d_widx, wi.size() * 4));
@@ -412,6 +470,8 @@ int prk_model_create(prk_model** out, int device, const float* vt, const float* 
 #undef PRK_M
     int rc = encode_tmap_2d_bf16(&m->tmap_B, m->d_Bmat, GEMM_N, GEMM_K, GEMM_BN, GEMM_BK);
     if (rc != PRK_OK) { prk_model_destroy(m); return rc; }
+    rc = encode_tmap_2d_bf16(&m->tmap_B2, m->d_B2, GEMM_N, FUSED_K, FUSED_BN, 64);
+    if (rc != PRK_OK) { prk_model_destroy(m); return rc; }
     *out = m;
     return PRK_OK;
 }
@@ -420,6 +480,7 @@ void prk_model_destroy(prk_model* model) {
     Model* m = model;
     if (!m) return;
     if (m->device >= 0) cudaSetDevice(m->device);
+    cudaFree(m->d_B2); cudaFree(m->d_wpack);
     cudaFree(m->d_Bmat); cudaFree(m->d_wval); cudaFree(m->d_widx); cudaFree(m->d_Jc);
     if (m->s_gemm) { cudaStreamSynchronize(m->s_gemm); cudaStreamDestroy(m->s_gemm); }
     if (m->s_score) { cudaStreamSynchronize(m->s_score); cudaStreamDestroy(m->s_score); }
@@ -634,7 +695,7 @@ int prk_debug_blend(prk_model* model, const float* d_pose, const float* d_betas,
     BatchFlags* d_flags = reinterpret_cast<BatchFlags*>(w + o_flags);
     PRK_CUDA(cudaMemsetAsync(d_arows, 0, (size_t)rows_pad * GEMM_K * 2, s));
     if (pose_chain_needs_flags(*m, d_betas, nullptr, -1)) PRK_CUDA(launch_batch_flags(d_betas, nullptr, B, d_flags, s));
-    PRK_CUDA(launch_pose_chain(*m, d_pose, d_betas, nullptr, d_flags, -1, B, true, d_arows,
+    PRK_CUDA(launch_pose_chain(*m, d_pose, d_betas, nullptr, d_flags, -1, B, true, false, d_arows,
                                reinterpret_cast<float*>(w + o_askin), reinterpret_cast<float*>(w + o_off),
                                reinterpret_cast<float*>(w + o_j), s));
     if (use_simt) {

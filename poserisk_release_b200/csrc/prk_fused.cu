@@ -1,0 +1,400 @@
+// K12: blend-shape GEMM and linear-blend skinning in ONE kernel -- v_posed never leaves the SM.
+//
+// Reference behaviour (lib/smplpytorch/smplpytorch/pytorch/smpl_layer.py):
+//   :93-99    v_posed = v_template + shapedirs @ betas + posedirs @ (R_1..23 - I)
+//   :134-144  T_v = sum_j weights[v][j] * A_j ;  vert = (T_v @ [v_posed; 1])[:3]
+//   :148-155  + trans | - centre joint
+//
+// Shape of the computation (one CTA per SM, persistent over a contiguous range of work units;
+// a unit = 128 frames x 32 vertices):
+//   * frames are the TMEM lanes (M = 128), vertex coordinates the accumulator columns
+//     (N = 96 = 32 vertices x 3), so after the MMA thread `lane` of an epilogue warp owns ONE
+//     FRAME and walks over vertices: every per-vertex quantity (weights, joint ids) is
+//     warp-uniform and every per-frame quantity is thread-private.
+//   * the per-frame skinning transforms A_j (24 x 12 fp32) live in TENSOR MEMORY, columns
+//     0..287 of the frame's lane, written once per frame tile with tcgen05.st and gathered per
+//     vertex with tcgen05.ld at a warp-uniform column 12*joint.  TMEM reads run at ~260 B/clk/SM
+//     (scripts/ubench_tmem.cu), twice what shared memory gives the same gather.
+//   * the blend GEMM runs on tcgen05 (kind::f16, bf16 x bf16 -> fp32) with fp32-class accuracy
+//     from split precision, but the hi/lo parts are stored ONCE (prk_internal.h "K12 operand
+//     layout"): the A' tile of the 128 frames (29 k-steps, 128 KB) stays resident in shared
+//     memory for the whole frame tile, only the 12 KB B' chunks stream through a TMA ring, and
+//     each B' k-step is multiplied with every A' k-step it pairs with (45 MMAs per unit).
+//   * accumulators are double buffered in TMEM (columns 288..383 / 384..479), so the MMAs of
+//     unit i+1 run under the skinning of unit i.
+//   * vertices leave through a per-warp shared-memory transpose so that every global store
+//     instruction writes contiguous 48-byte runs of a frame's row.
+// HBM traffic per frame: 82,680 B of vertices out, ~2.2 KB of operands in (B' is L2 resident)
+// -> HBM roofline; executed MMA work 2*45*16*96*... = 29.9 MFLOP/frame.
+//
+// Warp roles (576 threads): warps 0-15 epilogue (TMEM lane quarter = warp & 3, vertex octet =
+// warp >> 2), warp 16 TMA producer, warp 17 TMEM allocator + MMA issuer.  All mbarrier waits
+// are time-bounded (prk_tc.cuh).
+#include "prk_internal.h"
+#include "prk_tc.cuh"
+
+namespace prk {
+
+namespace {
+
+using namespace tc;
+
+constexpr int kAChunkBytes = FUSED_BM * 128;                     // 128 frames x 64 bf16
+constexpr int kABytes = FUSED_KCHUNKS * kAChunkBytes;            // 131,072: resident A' tile
+constexpr int kBChunkBytes = FUSED_BN * 128;                     // 96 vertex coords x 64 bf16 = 12,288
+constexpr int kEpiWarps = 16;
+constexpr int kOutBytesPerWarp = 32 * 48;                        // 32 frames x 4 vertices x 3 floats
+constexpr int kOutBytes = kEpiWarps * kOutBytesPerWarp;          // 24,576
+constexpr int kWSlots = 4;
+constexpr int kMaxStages = 6;
+constexpr int kNumBars = 2 * kMaxStages + 2 + 2 + kWSlots + 2;
+constexpr int kThreads = (kEpiWarps + 2) * 32;                   // 576
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kAccCol0 = 288;                               // accumulators behind the 24 x 12 A_j columns
+constexpr int kSmemLimit = 232448;                               // 227 KB opt-in maximum per CTA
+
+constexpr int fused_smem_bytes(int stages, int groups) {
+    return kABytes + stages * kBChunkBytes + kOutBytes + kWSlots * groups * FUSED_WGROUP_BYTES + kNumBars * 8 + 16 +
+           1024 /*alignment slack*/;
+}
+
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x4(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_x8(uint32_t taddr, const uint32_t* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory"); }
+
+// descriptor offset (units of 16 B) of A' k-step `a` inside the resident tile: chunk a/4, 32 B per k-step
+__host__ __device__ constexpr uint32_t a_step_off(int a) { return (uint32_t)((a >> 2) * (kAChunkBytes >> 4) + (a & 3) * 2); }
+// kind::f16 MMA with the two shared-memory descriptors given as (low word, common high word):
+// all tiles here share SBO / version / swizzle, only the 14-bit start address differs.
+__device__ __forceinline__ void umma_bf16_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc,
+                                               bool accumulate) {
+    if (accumulate)
+        asm volatile(
+            "{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\t"
+            "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+            "setp.ne.b32 p, 1, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+            ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\t"
+            "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+            "setp.ne.b32 p, 0, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+            ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc)
+            : "memory");
+}
+
+// kGroups: weight groups of 4 per vertex known at compile time (1 = SMPL), 0 = run-time `groups`
+template <int kGroups>
+__global__ void __launch_bounds__(kThreads, 1)
+fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid_constant__ CUtensorMap tmap_B,
+                        const float* __restrict__ AskinT, const float* __restrict__ off,
+                        const uint8_t* __restrict__ wpack, int groups_rt, int stages, int64_t B, int64_t n_units,
+                        float* __restrict__ verts) {
+    const int groups = kGroups > 0 ? kGroups : groups_rt;
+    extern __shared__ uint8_t smem_raw[];
+    // 1024-byte alignment by OFFSET on the __shared__ array, so every derived pointer stays in the
+    // shared address space (LDS/STS instead of generic LD/ST)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sA = smem;                                           // [8 chunks][128 rows][128 B], 128B swizzle
+    uint8_t* sB = sA + kABytes;                                   // [stages][96 rows][128 B]
+    uint8_t* sOut = sB + stages * kBChunkBytes;                   // [16 warps][32 frames][12 floats]
+    uint8_t* sW = sOut + kOutBytes;                               // [4 slots][groups][32 x float4 | 32 x u32]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sW + kWSlots * groups * FUSED_WGROUP_BYTES);
+    uint64_t* full_bar = bars;                                    // [kMaxStages]
+    uint64_t* empty_bar = bars + kMaxStages;                      // [kMaxStages]
+    uint64_t* tfull_bar = bars + 2 * kMaxStages;                  // [2]
+    uint64_t* tempty_bar = tfull_bar + 2;                         // [2]
+    uint64_t* wfull_bar = tempty_bar + 2;                         // [kWSlots]
+    uint64_t* afull_bar = wfull_bar + kWSlots;
+    uint64_t* aempty_bar = afull_bar + 1;
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(aempty_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_A)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_B)) : "memory");
+        for (int i = 0; i < kMaxStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], kEpiWarps); }
+        for (int i = 0; i < kWSlots; ++i) mbar_init(&wfull_bar[i], 1);
+        mbar_init(afull_bar, 1);
+        mbar_init(aempty_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kEpiWarps + 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)),
+                     "r"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    // contiguous unit range of this CTA; unit u = frame tile (u / 216), vertex tile (u % 216)
+    const int64_t u0 = (int64_t)blockIdx.x * n_units / gridDim.x;
+    const int64_t u1 = (int64_t)(blockIdx.x + 1) * n_units / gridDim.x;
+
+    if (warp == kEpiWarps) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            int64_t cur_ft = -1; uint32_t n_ft = 0, i = 0;
+            for (int64_t u = u0; u < u1; ++u, ++i) {
+                const int64_t ft = u / FUSED_NT;
+                const int vt = (int)(u - ft * FUSED_NT);
+                if (ft != cur_ft) {
+                    // the MMAs of the previous frame tile still read the resident A' tile
+                    if (n_ft > 0) mbar_wait(aempty_bar, (n_ft - 1) & 1);
+                    mbar_expect_tx(afull_bar, kABytes);
+                    for (int c = 0; c < FUSED_KCHUNKS; ++c)
+                        tma_load_2d(&tmap_A, afull_bar, sA + c * kAChunkBytes, c * 64, (int)(ft * FUSED_BM));
+                    ++n_ft; cur_ft = ft;
+                }
+                // skinning weights of the tile's 32 vertices.  Slot i&3 was last read by unit i-4;
+                // the ring is shorter than one unit, so the chunk loads of unit i-1 already issued
+                // imply the MMA of unit i-1 has started, i.e. every epilogue warp finished unit i-3.
+                const uint32_t wbytes = (uint32_t)groups * FUSED_WGROUP_BYTES;
+                uint64_t* wb = &wfull_bar[i & (kWSlots - 1)];
+                mbar_expect_tx(wb, wbytes);
+                bulk_load_1d(sW + (i & (kWSlots - 1)) * wbytes, wpack + (size_t)vt * wbytes, wbytes, wb);
+                for (int c = 0; c < FUSED_KCHUNKS; ++c) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_expect_tx(&full_bar[stage], kBChunkBytes);
+                    tma_load_2d(&tmap_B, &full_bar[stage], sB + stage * kBChunkBytes, c * 64, vt * FUSED_BN);
+                    if (++stage == stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == kEpiWarps + 1) {
+        // ===== MMA issuer (one elected lane) =====
+        // Everything about a k-step is a compile-time constant (both loops fully unrolled): an MMA
+        // costs a 32-bit add per descriptor plus the issue, so one thread keeps the tensor pipe fed.
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(FUSED_BM, FUSED_BN);
+            const uint64_t adesc0 = make_smem_desc(smem_u32(sA));
+            const uint32_t a_lo = (uint32_t)adesc0, d_hi = (uint32_t)(adesc0 >> 32);
+            const uint32_t b_lo0 = (uint32_t)make_smem_desc(smem_u32(sB));
+            int stage = 0; uint32_t phase = 0;
+            int64_t cur_ft = -1; uint32_t n_ft = 0, i = 0;
+            for (int64_t u = u0; u < u1; ++u, ++i) {
+                const int64_t ft = u / FUSED_NT;
+                if (ft != cur_ft) {
+                    if (n_ft > 0) tcgen05_commit(aempty_bar);     // all MMAs on the old A' tile retire first
+                    mbar_wait(afull_bar, n_ft & 1);
+                    tcgen05_fence_after();
+                    ++n_ft; cur_ft = ft;
+                }
+                const int acc = i & 1;
+                mbar_wait(&tempty_bar[acc], ((i >> 1) & 1) ^ 1);   // epilogue drained this accumulator
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + kAccCol0 + (uint32_t)acc * FUSED_BN;
+#pragma unroll
+                for (int c = 0; c < FUSED_KCHUNKS; ++c) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tcgen05_fence_after();
+                    const uint32_t b_lo = b_lo0 + (uint32_t)stage * (kBChunkBytes >> 4);
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) {
+                        const int b = c * 4 + s;                  // B' k-step (compile-time)
+                        const uint32_t bl = b_lo + 2 * s;
+                        if (b < FUSED_POSE_STEPS) {               // posedirs hi: x pose hi, x pose lo
+                            umma_bf16_lohi(d_tmem, a_lo + a_step_off(b), bl, d_hi, idesc, b != 0);
+                            umma_bf16_lohi(d_tmem, a_lo + a_step_off(FUSED_POSE_STEPS + b), bl, d_hi, idesc, true);
+                        } else if (b < 2 * FUSED_POSE_STEPS) {    // posedirs lo: x pose hi
+                            umma_bf16_lohi(d_tmem, a_lo + a_step_off(b - FUSED_POSE_STEPS), bl, d_hi, idesc, true);
+                        } else if (b < FUSED_KSTEPS) {            // shapedirs/template split q: x beta splits 0..2-q
+                            const int q = b - 2 * FUSED_POSE_STEPS;
+#pragma unroll
+                            for (int p = 0; p < 3; ++p)
+                                if (p + q < 3)
+                                    umma_bf16_lohi(d_tmem, a_lo + a_step_off(2 * FUSED_POSE_STEPS + p), bl, d_hi, idesc, true);
+                        }
+                    }
+                    tcgen05_commit(&empty_bar[stage]);            // frees the ring slot when the MMAs retire
+                    if (++stage == stages) { stage = 0; phase ^= 1; }
+                }
+                tcgen05_commit(&tfull_bar[acc]);
+            }
+        }
+    } else {
+        // ===== epilogue: thread = frame (TMEM lane), loop over the warp's 8 vertices of each unit =====
+        const int quarter = warp & 3, oct = warp >> 2;
+        const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        float* my_out = reinterpret_cast<float*>(sOut + warp * kOutBytesPerWarp);
+        // transpose read-back: float2 index q = it*32 + lane over [32 frames][6 float2]
+        int rb_row[3], rb_col[3];
+#pragma unroll
+        for (int it = 0; it < 3; ++it) { const int q = it * 32 + lane; rb_row[it] = q / 6; rb_col[it] = q - rb_row[it] * 6; }
+
+        int64_t cur_ft = -1; uint32_t i = 0;
+        int64_t f = 0;
+        float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+        for (int64_t u = u0; u < u1; ++u, ++i) {
+            const int64_t ft = u / FUSED_NT;
+            const int vt = (int)(u - ft * FUSED_NT);
+            if (ft != cur_ft) {
+                // ---- new frame tile: A_j of my 32 frames -> TMEM columns [72*oct, 72*oct+72) ----
+                epi_barrier();                                    // nobody still gathers the old A_j
+                f = ft * FUSED_BM + quarter * 32 + lane;
+                const float* src = AskinT + ((size_t)(ft * 4 + quarter) * FUSED_ASKIN_COLS + oct * 72) * 32 + lane;
+#pragma unroll 1
+                for (int c = 0; c < 9; ++c) {
+                    uint32_t v[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) v[k] = __float_as_uint(src[(c * 8 + k) * 32]);
+                    tmem_st_x8(t_lane + (uint32_t)(oct * 72 + c * 8), v);
+                }
+                tmem_st_wait();
+                if (f < B) { o0 = off[f * 3 + 0]; o1 = off[f * 3 + 1]; o2 = off[f * 3 + 2]; }
+                tcgen05_fence_before();
+                epi_barrier();
+                tcgen05_fence_after();
+                cur_ft = ft;
+            }
+            const int acc = i & 1;
+            const uint32_t wbytes = (uint32_t)groups * FUSED_WGROUP_BYTES;
+            const uint8_t* wslot = sW + (i & (kWSlots - 1)) * wbytes;
+            mbar_wait(&wfull_bar[i & (kWSlots - 1)], (i >> 2) & 1);
+            mbar_wait(&tfull_bar[acc], (i >> 1) & 1);
+            tcgen05_fence_after();
+            const uint32_t t_acc = t_lane + kAccCol0 + (uint32_t)acc * FUSED_BN + (uint32_t)(oct * 24);
+            const int v_first = vt * FUSED_VT + oct * 8;          // first of this warp's 8 vertices
+            float* vrow = verts + (size_t)(ft * FUSED_BM + quarter * 32) * NVC + (size_t)v_first * 3;
+
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                float res[12];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int vl = oct * 8 + half * 4 + k;        // vertex within the tile
+                    uint32_t p[4];
+                    tmem_ld_x4(t_acc + (uint32_t)((half * 4 + k) * 3), p);
+                    float ax = o0, ay = o1, az = o2;
+                    float px = 0.f, py = 0.f, pz = 0.f;
+#pragma unroll
+                    for (int g = 0; g < (kGroups > 0 ? kGroups : groups); ++g) {
+                        const uint8_t* wg = wslot + g * FUSED_WGROUP_BYTES;
+                        const float4 w = reinterpret_cast<const float4*>(wg)[vl];
+                        const uint32_t id = reinterpret_cast<const uint32_t*>(wg + 512)[vl];   // 4 x (3 * joint)
+                        uint32_t r[48];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const uint32_t col = ((id >> (8 * q)) & 0xFFu) << 2;              // 12 * joint
+                            tmem_ld_x8(t_lane + col, r + q * 12);
+                            tmem_ld_x4(t_lane + col + 8, r + q * 12 + 8);
+                        }
+                        tmem_ld_wait();
+                        if (g == 0) { px = __uint_as_float(p[0]); py = __uint_as_float(p[1]); pz = __uint_as_float(p[2]); }
+                        const float ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const uint32_t* a = r + q * 12;
+                            const float tx = fmaf(__uint_as_float(a[0]), px, fmaf(__uint_as_float(a[1]), py,
+                                             fmaf(__uint_as_float(a[2]), pz, __uint_as_float(a[3]))));
+                            const float ty = fmaf(__uint_as_float(a[4]), px, fmaf(__uint_as_float(a[5]), py,
+                                             fmaf(__uint_as_float(a[6]), pz, __uint_as_float(a[7]))));
+                            const float tz = fmaf(__uint_as_float(a[8]), px, fmaf(__uint_as_float(a[9]), py,
+                                             fmaf(__uint_as_float(a[10]), pz, __uint_as_float(a[11]))));
+                            ax = fmaf(ws[q], tx, ax); ay = fmaf(ws[q], ty, ay); az = fmaf(ws[q], tz, az);
+                        }
+                    }
+                    res[k * 3 + 0] = ax; res[k * 3 + 1] = ay; res[k * 3 + 2] = az;
+                }
+                if (half == 1) {
+                    // both halves' accumulator columns are in registers: hand the buffer back to the MMA warp
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                }
+                // transpose through shared memory: [frame = lane][12 floats], pitch 48 B (conflict-free float4)
+                float4* dst = reinterpret_cast<float4*>(my_out + lane * 12);
+                dst[0] = make_float4(res[0], res[1], res[2], res[3]);
+                dst[1] = make_float4(res[4], res[5], res[6], res[7]);
+                dst[2] = make_float4(res[8], res[9], res[10], res[11]);
+                __syncwarp();
+                const int c_first = (v_first + half * 4) * 3;       // first vertex coordinate of this half
+#pragma unroll
+                for (int it = 0; it < 6; ++it) {
+                    const int row = rb_row[it % 3] + (it / 3) * 16, c2 = rb_col[it % 3];
+                    const float2 val = *reinterpret_cast<const float2*>(my_out + row * 12 + c2 * 2);
+                    const int64_t fr = ft * FUSED_BM + quarter * 32 + row;
+                    if (fr < B && c_first + c2 * 2 < NVC)
+                        *reinterpret_cast<float2*>(vrow + (size_t)row * NVC + half * 12 + c2 * 2) = val;
+                }
+                __syncwarp();
+            }
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == kEpiWarps + 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+}  // namespace
+
+int fused_stages(int groups) {
+    int stages = kMaxStages;
+    while (stages > 2 && fused_smem_bytes(stages, groups) > kSmemLimit) --stages;
+    return stages;
+}
+
+cudaError_t launch_fused(const Model& m, const CUtensorMap& tmap_A, int64_t rows_pad, const float* d_AskinT,
+                         const float* d_off, int64_t B, float* d_verts, cudaStream_t s) {
+    if (B == 0) return cudaSuccess;
+    const int groups = m.nnz_groups;
+    const int stages = fused_stages(groups);
+    const int smem = fused_smem_bytes(stages, groups);
+    if (smem > kSmemLimit) return cudaErrorInvalidConfiguration;
+    static int attr_set[64] = {};
+    if (m.device >= 0 && m.device < 64 && attr_set[m.device] < smem) {
+        cudaError_t e = cudaFuncSetAttribute(fused_blend_skin_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(fused_blend_skin_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        attr_set[m.device] = smem;
+    }
+    const int64_t n_units = (rows_pad / FUSED_BM) * FUSED_NT;
+    int grid = m.sm_count > 0 ? m.sm_count : 148;
+    if (grid > n_units) grid = (int)n_units;
+    if (groups == 1)
+        fused_blend_skin_kernel<1><<<grid, kThreads, smem, s>>>(tmap_A, m.tmap_B2, d_AskinT, d_off, m.d_wpack, groups, stages,
+                                                                B, n_units, d_verts);
+    else
+        fused_blend_skin_kernel<0><<<grid, kThreads, smem, s>>>(tmap_A, m.tmap_B2, d_AskinT, d_off, m.d_wpack, groups, stages,
+                                                                B, n_units, d_verts);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace prk

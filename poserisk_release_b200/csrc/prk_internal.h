@@ -33,6 +33,28 @@ constexpr int COL_BETA0 = 621;
 constexpr int COL_ONES = 681;
 constexpr int VPOSED_PITCH = GEMM_N;    // floats per frame row of the v_posed scratch
 
+// ---- fused blend + skinning geometry (DESIGN.md "K12", prk_fused.cu) ---------
+// K12 operand layout: the hi/lo parts of every factor are stored ONCE, in k-steps of 16 bf16:
+//   steps  0..12  pose features hi   (207 + 1 zero column; feature p = 9*(pos-1)+e, pos = DFS position)
+//   steps 13..25  pose features lo
+//   steps 26..28  A': beta split q (10 columns) [+ 1.0 in column 10 of step 26]
+//                 B': shapedirs split q (10 columns) + v_template split q in column 10
+//   columns 464..511 pad the row to 8 chunks of 64 (never multiplied).
+// The MMA issuer pairs  A'hi x B'hi,  A'lo x B'hi,  A'hi x B'lo  and  beta_p x shape_q for p+q <= 2
+// (45 MMAs of K=16 per tile) -- the same products as the 704-column layout of K1.
+constexpr int FUSED_K = 512;
+constexpr int FUSED_KCHUNKS = FUSED_K / 64;
+constexpr int FUSED_POSE_STEPS = 13;
+constexpr int FUSED_KSTEPS = 2 * FUSED_POSE_STEPS + 3;   // 29
+constexpr int FUSED_COL_LO = 16 * FUSED_POSE_STEPS;      // 208
+constexpr int FUSED_COL_BETA = 2 * FUSED_COL_LO;         // 416
+constexpr int FUSED_BM = 128;            // frames per tile (TMEM lanes)
+constexpr int FUSED_VT = 32;             // vertices per tile
+constexpr int FUSED_BN = FUSED_VT * 3;   // 96 accumulator columns
+constexpr int FUSED_NT = GEMM_N / FUSED_BN;   // 216 vertex tiles (6912 vertex slots)
+constexpr int FUSED_ASKIN_COLS = NJ * 12;     // 288 TMEM columns of A_j per frame
+constexpr int FUSED_WGROUP_BYTES = FUSED_VT * 16 + FUSED_VT * 4;   // per tile and group: 32 float4 weights | 32 x (4 x u8 = 3*joint)
+
 // Rest joints as an affine function of betas: J = J_template + Jdirs * beta
 // (folds J_regressor @ (v_template + shapedirs beta), smpl_layer.py:91,95).
 struct PoseConsts {
@@ -58,6 +80,9 @@ struct prk_model {
     uint32_t* d_widx = nullptr;
     float* d_Jc = nullptr;         // J_template[72] | Jdirs[720] | model_betas[10] (lane-per-joint kernel)    // [nnz_groups][NV] joint ids, 4 x u8 per group
     CUtensorMap tmap_B;            // [GEMM_N][GEMM_K], box 64 x 256, 128B swizzle
+    uint16_t* d_B2 = nullptr;      // [GEMM_N][FUSED_K] bf16 bits, K12 operand layout
+    uint8_t* d_wpack = nullptr;    // [FUSED_NT][nnz_groups][FUSED_WGROUP_BYTES] per-tile skinning weights
+    CUtensorMap tmap_B2;           // [GEMM_N][FUSED_K], box 64 x 96, 128B swizzle
     // internal streams/events of the two-stream pipeline (GEMM under skinning, scoring aside)
     cudaStream_t s_gemm = nullptr, s_score = nullptr;
     cudaEvent_t ev_pose = nullptr, ev_in = nullptr, ev_score = nullptr;
@@ -80,7 +105,7 @@ cudaError_t launch_batch_flags(const float* d_betas, const float* d_trans, int64
 // K2a: Rodrigues + kinematic chain (+ split-precision GEMM operand rows when full_mesh)
 cudaError_t launch_pose_chain(const Model& m, const float* d_pose, const float* d_betas,
                               const float* d_trans, const BatchFlags* d_flags, int center_idx,
-                              int64_t B, bool full_mesh, uint16_t* d_Arows, float* d_Askin,
+                              int64_t B, bool full_mesh, bool fused_layout, uint16_t* d_Arows, float* d_Askin,
                               float* d_off, float* d_joints, cudaStream_t s);
 
 bool pose_chain_needs_flags(const Model& m, const float* d_betas, const float* d_trans, int center_idx);
@@ -90,6 +115,10 @@ cudaError_t launch_blend_gemm(const Model& m, const CUtensorMap& tmap_A, int64_t
                               float* d_vposed, cudaStream_t s);
 cudaError_t launch_blend_simt(const Model& m, const uint16_t* d_Arows, int64_t rows,
                               float* d_vposed, cudaStream_t s);
+
+// K12: fused blend GEMM + skinning (prk_fused.cu); A' rows / AskinT in the K12 layouts, rows_pad = multiple of 128
+cudaError_t launch_fused(const Model& m, const CUtensorMap& tmap_A, int64_t rows_pad, const float* d_AskinT,
+                         const float* d_off, int64_t B, float* d_verts, cudaStream_t s);
 
 // K2b: linear-blend skinning
 cudaError_t launch_skin(const Model& m, const float* d_vposed, const float* d_Askin,

@@ -33,6 +33,8 @@
 #include "prk_internal.h"
 #include "prk_tc.cuh"
 
+#include <cstdlib>
+
 namespace prk {
 
 namespace {
@@ -107,13 +109,50 @@ __device__ __forceinline__ void umma_bf16_lohi(uint32_t d_tmem, uint32_t a_lo, u
             : "memory");
 }
 
+// Build with -DPRK_FUSED_DEBUG to get run-time switches (env PRK_FUSED_DBG) that knock out one side
+// of the pipeline at a time: 1 = no MMAs issued, 2 = epilogue skips gather+math, 4 = no global stores,
+// 8 = no TMEM gather of A_j (math on stale registers), 16 = no B' loads (producer only signals).
+#ifdef PRK_FUSED_DEBUG
+#define DBG(bit) (dbg & (bit))
+#else
+#define DBG(bit) 0
+#endif
+
+// Packed fp32 pairs (Blackwell FFMA2): one issue slot per two FMAs -- the epilogue is issue-bound.
+__device__ __forceinline__ uint64_t pack2(uint32_t lo, uint32_t hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
+}
+__device__ __forceinline__ uint64_t pack2f(float lo, float hi) { return pack2(__float_as_uint(lo), __float_as_uint(hi)); }
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+    uint32_t a, b;
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(a), "=r"(b) : "l"(v));
+    lo = __uint_as_float(a); hi = __uint_as_float(b);
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // kGroups: weight groups of 4 per vertex known at compile time (1 = SMPL), 0 = run-time `groups`
 template <int kGroups>
 __global__ void __launch_bounds__(kThreads, 1)
 fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid_constant__ CUtensorMap tmap_B,
                         const float* __restrict__ AskinT, const float* __restrict__ off,
                         const uint8_t* __restrict__ wpack, int groups_rt, int stages, int64_t B, int64_t n_units,
-                        float* __restrict__ verts) {
+                        float* __restrict__ verts, int dbg) {
     const int groups = kGroups > 0 ? kGroups : groups_rt;
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment by OFFSET on the __shared__ array, so every derived pointer stays in the
@@ -122,7 +161,7 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
     uint8_t* sA = smem;                                           // [8 chunks][128 rows][128 B], 128B swizzle
     uint8_t* sB = sA + kABytes;                                   // [stages][96 rows][128 B]
     uint8_t* sOut = sB + stages * kBChunkBytes;                   // [16 warps][32 frames][12 floats]
-    uint8_t* sW = sOut + kOutBytes;                               // [4 slots][groups][32 x float4 | 32 x u32]
+    uint8_t* sW = sOut + kOutBytes;                               // [4 slots][groups][FUSED_WGROUP_BYTES]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sW + kWSlots * groups * FUSED_WGROUP_BYTES);
     uint64_t* full_bar = bars;                                    // [kMaxStages]
     uint64_t* empty_bar = bars + kMaxStages;                      // [kMaxStages]
@@ -133,8 +172,12 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
     uint64_t* aempty_bar = afull_bar + 1;
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(aempty_bar + 1);
 
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
+    // The warp index is broadcast from lane 0 so the compiler knows it is warp-uniform: role
+    // branches stay convergent and the MMA / TMA warps compute their operands in uniform registers.
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    uint32_t lane_opaque = threadIdx.x & 31;
+    asm volatile("" : "+r"(lane_opaque));                         // never re-derived from S2R inside the loops
+    const int lane = (int)lane_opaque;
 
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_A)) : "memory");
@@ -155,73 +198,84 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
-    const uint32_t tmem_base = *tmem_holder;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_holder, 0);
 
     // contiguous unit range of this CTA; unit u = frame tile (u / 216), vertex tile (u % 216)
     const int64_t u0 = (int64_t)blockIdx.x * n_units / gridDim.x;
     const int64_t u1 = (int64_t)(blockIdx.x + 1) * n_units / gridDim.x;
+    const int n_my = (int)(u1 - u0);
+    const int64_t ft0 = u0 / FUSED_NT;
+    const int vt0 = (int)(u0 - ft0 * FUSED_NT);
 
     if (warp == kEpiWarps) {
-        // ===== TMA producer =====
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
-            int64_t cur_ft = -1; uint32_t n_ft = 0, i = 0;
-            for (int64_t u = u0; u < u1; ++u, ++i) {
-                const int64_t ft = u / FUSED_NT;
-                const int vt = (int)(u - ft * FUSED_NT);
-                if (ft != cur_ft) {
-                    // the MMAs of the previous frame tile still read the resident A' tile
-                    if (n_ft > 0) mbar_wait(aempty_bar, (n_ft - 1) & 1);
+        // ===== TMA producer (whole warp converged, one elected lane issues) =====
+        int stage = 0; uint32_t phase = 0;
+        int64_t ft = ft0; int vt = vt0;
+        uint32_t n_ft = 0;
+        for (int i = 0; i < n_my; ++i) {
+            if (i == 0 || vt == 0) {
+                // the MMAs of the previous frame tile still read the resident A' tile
+                if (n_ft > 0) mbar_wait(aempty_bar, (n_ft - 1) & 1);
+                if (elect_one()) {
                     mbar_expect_tx(afull_bar, kABytes);
                     for (int c = 0; c < FUSED_KCHUNKS; ++c)
                         tma_load_2d(&tmap_A, afull_bar, sA + c * kAChunkBytes, c * 64, (int)(ft * FUSED_BM));
-                    ++n_ft; cur_ft = ft;
                 }
-                // skinning weights of the tile's 32 vertices.  Slot i&3 was last read by unit i-4;
-                // the ring is shorter than one unit, so the chunk loads of unit i-1 already issued
-                // imply the MMA of unit i-1 has started, i.e. every epilogue warp finished unit i-3.
-                const uint32_t wbytes = (uint32_t)groups * FUSED_WGROUP_BYTES;
+                ++n_ft;
+            }
+            // skinning weights of the tile's 32 vertices.  Slot i&3 was last read by unit i-4;
+            // the ring is shorter than one unit, so the chunk loads of unit i-1 already issued
+            // imply the MMA of unit i-1 has started, i.e. every epilogue warp finished unit i-3.
+            const uint32_t wbytes = (uint32_t)groups * FUSED_WGROUP_BYTES;
+            if (elect_one()) {
                 uint64_t* wb = &wfull_bar[i & (kWSlots - 1)];
                 mbar_expect_tx(wb, wbytes);
                 bulk_load_1d(sW + (i & (kWSlots - 1)) * wbytes, wpack + (size_t)vt * wbytes, wbytes, wb);
-                for (int c = 0; c < FUSED_KCHUNKS; ++c) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_expect_tx(&full_bar[stage], kBChunkBytes);
-                    tma_load_2d(&tmap_B, &full_bar[stage], sB + stage * kBChunkBytes, c * 64, vt * FUSED_BN);
-                    if (++stage == stages) { stage = 0; phase ^= 1; }
-                }
             }
+#pragma unroll 1
+            for (int c = 0; c < FUSED_KCHUNKS; ++c) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                if (elect_one()) {
+                    if (DBG(16)) { mbar_arrive(&full_bar[stage]); }
+                    else {
+                        mbar_expect_tx(&full_bar[stage], kBChunkBytes);
+                        tma_load_2d(&tmap_B, &full_bar[stage], sB + stage * kBChunkBytes, c * 64, vt * FUSED_BN);
+                    }
+                }
+                if (++stage == stages) { stage = 0; phase ^= 1; }
+            }
+            if (++vt == FUSED_NT) { vt = 0; ++ft; }
         }
     } else if (warp == kEpiWarps + 1) {
-        // ===== MMA issuer (one elected lane) =====
-        // Everything about a k-step is a compile-time constant (both loops fully unrolled): an MMA
-        // costs a 32-bit add per descriptor plus the issue, so one thread keeps the tensor pipe fed.
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(FUSED_BM, FUSED_BN);
-            const uint64_t adesc0 = make_smem_desc(smem_u32(sA));
-            const uint32_t a_lo = (uint32_t)adesc0, d_hi = (uint32_t)(adesc0 >> 32);
-            const uint32_t b_lo0 = (uint32_t)make_smem_desc(smem_u32(sB));
-            int stage = 0; uint32_t phase = 0;
-            int64_t cur_ft = -1; uint32_t n_ft = 0, i = 0;
-            for (int64_t u = u0; u < u1; ++u, ++i) {
-                const int64_t ft = u / FUSED_NT;
-                if (ft != cur_ft) {
-                    if (n_ft > 0) tcgen05_commit(aempty_bar);     // all MMAs on the old A' tile retire first
-                    mbar_wait(afull_bar, n_ft & 1);
-                    tcgen05_fence_after();
-                    ++n_ft; cur_ft = ft;
-                }
-                const int acc = i & 1;
-                mbar_wait(&tempty_bar[acc], ((i >> 1) & 1) ^ 1);   // epilogue drained this accumulator
+        // ===== MMA issuer (whole warp converged, one elected lane issues) =====
+        // Everything about a k-step is a compile-time constant (both loops fully unrolled) and every
+        // run-time operand is warp-uniform, so an MMA costs a couple of uniform adds plus the issue.
+        constexpr uint32_t idesc = make_idesc(FUSED_BM, FUSED_BN);
+        const uint64_t adesc0 = make_smem_desc(smem_u32(sA));
+        const uint32_t a_lo = (uint32_t)adesc0, d_hi = (uint32_t)(adesc0 >> 32);
+        const uint32_t b_lo0 = (uint32_t)make_smem_desc(smem_u32(sB));
+        int stage = 0; uint32_t phase = 0;
+        int vt = vt0;
+        uint32_t n_ft = 0;
+        for (int i = 0; i < n_my; ++i) {
+            if (i == 0 || vt == 0) {
+                if (n_ft > 0 && elect_one()) tcgen05_commit(aempty_bar);   // all MMAs on the old A' tile retire first
+                mbar_wait(afull_bar, n_ft & 1);
                 tcgen05_fence_after();
-                const uint32_t d_tmem = tmem_base + kAccCol0 + (uint32_t)acc * FUSED_BN;
+                ++n_ft;
+            }
+            const int acc = i & 1;
+            mbar_wait(&tempty_bar[acc], ((i >> 1) & 1) ^ 1);       // epilogue drained this accumulator
+            tcgen05_fence_after();
+            const uint32_t d_tmem = tmem_base + kAccCol0 + (uint32_t)acc * FUSED_BN;
 #pragma unroll
-                for (int c = 0; c < FUSED_KCHUNKS; ++c) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tcgen05_fence_after();
-                    const uint32_t b_lo = b_lo0 + (uint32_t)stage * (kBChunkBytes >> 4);
+            for (int c = 0; c < FUSED_KCHUNKS; ++c) {
+                mbar_wait(&full_bar[stage], phase);
+                tcgen05_fence_after();
+                const uint32_t b_lo = b_lo0 + (uint32_t)stage * (kBChunkBytes >> 4);
+                if (elect_one()) {
 #pragma unroll
-                    for (int s = 0; s < 4; ++s) {
+                    for (int s = 0; s < (DBG(1) ? 0 : 4); ++s) {
                         const int b = c * 4 + s;                  // B' k-step (compile-time)
                         const uint32_t bl = b_lo + 2 * s;
                         if (b < FUSED_POSE_STEPS) {               // posedirs hi: x pose hi, x pose lo
@@ -238,31 +292,35 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
                         }
                     }
                     tcgen05_commit(&empty_bar[stage]);            // frees the ring slot when the MMAs retire
-                    if (++stage == stages) { stage = 0; phase ^= 1; }
+                    if (c == FUSED_KCHUNKS - 1) tcgen05_commit(&tfull_bar[acc]);
                 }
-                tcgen05_commit(&tfull_bar[acc]);
+                if (++stage == stages) { stage = 0; phase ^= 1; }
             }
+            if (++vt == FUSED_NT) vt = 0;
         }
     } else {
         // ===== epilogue: thread = frame (TMEM lane), loop over the warp's 8 vertices of each unit =====
         const int quarter = warp & 3, oct = warp >> 2;
         const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
         float* my_out = reinterpret_cast<float*>(sOut + warp * kOutBytesPerWarp);
-        // transpose read-back: float2 index q = it*32 + lane over [32 frames][6 float2]
-        int rb_row[3], rb_col[3];
+        // transpose read-back: float2 index q = it*32 + lane over [32 frames][6 float2]; iterations
+        // it+3 hit the same column 16 rows further down
+        int rb_smem[3], rb_glob[3], rb_row[3], rb_c2[3];
 #pragma unroll
-        for (int it = 0; it < 3; ++it) { const int q = it * 32 + lane; rb_row[it] = q / 6; rb_col[it] = q - rb_row[it] * 6; }
+        for (int it = 0; it < 3; ++it) {
+            const int q = it * 32 + lane;
+            rb_row[it] = q / 6; rb_c2[it] = (q - rb_row[it] * 6) * 2;
+            rb_smem[it] = rb_row[it] * 12 + rb_c2[it];            // float index in the staging tile
+            rb_glob[it] = rb_row[it] * NVC + rb_c2[it];           // float offset from the tile's first frame row
+        }
 
-        int64_t cur_ft = -1; uint32_t i = 0;
-        int64_t f = 0;
+        int64_t ft = ft0; int vt = vt0;
         float o0 = 0.f, o1 = 0.f, o2 = 0.f;
-        for (int64_t u = u0; u < u1; ++u, ++i) {
-            const int64_t ft = u / FUSED_NT;
-            const int vt = (int)(u - ft * FUSED_NT);
-            if (ft != cur_ft) {
+        for (int i = 0; i < n_my; ++i) {
+            if (i == 0 || vt == 0) {
                 // ---- new frame tile: A_j of my 32 frames -> TMEM columns [72*oct, 72*oct+72) ----
                 epi_barrier();                                    // nobody still gathers the old A_j
-                f = ft * FUSED_BM + quarter * 32 + lane;
+                const int64_t f = ft * FUSED_BM + quarter * 32 + lane;
                 const float* src = AskinT + ((size_t)(ft * 4 + quarter) * FUSED_ASKIN_COLS + oct * 72) * 32 + lane;
 #pragma unroll 1
                 for (int c = 0; c < 9; ++c) {
@@ -276,7 +334,6 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
                 tcgen05_fence_before();
                 epi_barrier();
                 tcgen05_fence_after();
-                cur_ft = ft;
             }
             const int acc = i & 1;
             const uint32_t wbytes = (uint32_t)groups * FUSED_WGROUP_BYTES;
@@ -284,9 +341,17 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
             mbar_wait(&wfull_bar[i & (kWSlots - 1)], (i >> 2) & 1);
             mbar_wait(&tfull_bar[acc], (i >> 1) & 1);
             tcgen05_fence_after();
+            if (DBG(2)) {
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                if (++vt == FUSED_NT) { vt = 0; ++ft; }
+                continue;
+            }
             const uint32_t t_acc = t_lane + kAccCol0 + (uint32_t)acc * FUSED_BN + (uint32_t)(oct * 24);
-            const int v_first = vt * FUSED_VT + oct * 8;          // first of this warp's 8 vertices
-            float* vrow = verts + (size_t)(ft * FUSED_BM + quarter * 32) * NVC + (size_t)v_first * 3;
+            const int c_unit = (vt * FUSED_VT + oct * 8) * 3;       // first vertex coordinate of this warp's 8 vertices
+            float* vrow = verts + (size_t)(ft * FUSED_BM + quarter * 32) * NVC + c_unit;
+            const int rows_valid = (int)((B - (ft * FUSED_BM + quarter * 32)) < 32 ? (B - (ft * FUSED_BM + quarter * 32)) : 32);
 
 #pragma unroll 1
             for (int half = 0; half < 2; ++half) {
@@ -296,36 +361,46 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
                     const int vl = oct * 8 + half * 4 + k;        // vertex within the tile
                     uint32_t p[4];
                     tmem_ld_x4(t_acc + (uint32_t)((half * 4 + k) * 3), p);
-                    float ax = o0, ay = o1, az = o2;
-                    float px = 0.f, py = 0.f, pz = 0.f;
+                    uint64_t accxy = pack2f(o0, o1), accz = pack2f(o2, 0.f);
+                    uint64_t pxx = 0, pyy = 0, pzz = 0, pxy = 0, pz1 = 0;
 #pragma unroll
                     for (int g = 0; g < (kGroups > 0 ? kGroups : groups); ++g) {
                         const uint8_t* wg = wslot + g * FUSED_WGROUP_BYTES;
-                        const float4 w = reinterpret_cast<const float4*>(wg)[vl];
-                        const uint32_t id = reinterpret_cast<const uint32_t*>(wg + 512)[vl];   // 4 x (3 * joint)
+                        const uint4 cj = reinterpret_cast<const uint4*>(wg + 1024)[vl];     // 12 * joint, 4 joints
                         uint32_t r[48];
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const uint32_t col = ((id >> (8 * q)) & 0xFFu) << 2;              // 12 * joint
-                            tmem_ld_x8(t_lane + col, r + q * 12);
-                            tmem_ld_x4(t_lane + col + 8, r + q * 12 + 8);
+                        for (int q = 0; q < 48; ++q) r[q] = 0x3f000000u + q;
+                        if (!DBG(8)) {
+                            tmem_ld_x8(t_lane + cj.x, r +  0); tmem_ld_x4(t_lane + cj.x + 8, r +  8);
+                            tmem_ld_x8(t_lane + cj.y, r + 12); tmem_ld_x4(t_lane + cj.y + 8, r + 20);
+                            tmem_ld_x8(t_lane + cj.z, r + 24); tmem_ld_x4(t_lane + cj.z + 8, r + 32);
+                            tmem_ld_x8(t_lane + cj.w, r + 36); tmem_ld_x4(t_lane + cj.w + 8, r + 44);
                         }
+                        const float4 wA = reinterpret_cast<const float4*>(wg)[vl];          // w0 w0 w1 w1
+                        const float4 wB = reinterpret_cast<const float4*>(wg + 512)[vl];    // w2 w2 w3 w3
                         tmem_ld_wait();
-                        if (g == 0) { px = __uint_as_float(p[0]); py = __uint_as_float(p[1]); pz = __uint_as_float(p[2]); }
-                        const float ws[4] = {w.x, w.y, w.z, w.w};
+                        if (g == 0) {
+                            pxx = pack2(p[0], p[0]); pyy = pack2(p[1], p[1]); pzz = pack2(p[2], p[2]);
+                            pxy = pack2(p[0], p[1]); pz1 = pack2(p[2], 0x3f800000u);
+                        }
+                        const uint64_t ww[4] = {pack2f(wA.x, wA.y), pack2f(wA.z, wA.w), pack2f(wB.x, wB.y), pack2f(wB.z, wB.w)};
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
+                            // TMEM columns of a joint: R00 R10 R01 R11 R02 R12 t0 t1 | R20 R21 R22 t2
                             const uint32_t* a = r + q * 12;
-                            const float tx = fmaf(__uint_as_float(a[0]), px, fmaf(__uint_as_float(a[1]), py,
-                                             fmaf(__uint_as_float(a[2]), pz, __uint_as_float(a[3]))));
-                            const float ty = fmaf(__uint_as_float(a[4]), px, fmaf(__uint_as_float(a[5]), py,
-                                             fmaf(__uint_as_float(a[6]), pz, __uint_as_float(a[7]))));
-                            const float tz = fmaf(__uint_as_float(a[8]), px, fmaf(__uint_as_float(a[9]), py,
-                                             fmaf(__uint_as_float(a[10]), pz, __uint_as_float(a[11]))));
-                            ax = fmaf(ws[q], tx, ax); ay = fmaf(ws[q], ty, ay); az = fmaf(ws[q], tz, az);
+                            uint64_t xy = fma2(pack2(a[0], a[1]), pxx, pack2(a[6], a[7]));
+                            xy = fma2(pack2(a[2], a[3]), pyy, xy);
+                            xy = fma2(pack2(a[4], a[5]), pzz, xy);
+                            uint64_t zz = mul2(pack2(a[8], a[9]), pxy);     // (R20 px, R21 py)
+                            zz = fma2(pack2(a[10], a[11]), pz1, zz);        // (+ R22 pz, + t2): z = lo + hi
+                            accxy = fma2(ww[q], xy, accxy);
+                            accz = fma2(ww[q], zz, accz);
                         }
                     }
-                    res[k * 3 + 0] = ax; res[k * 3 + 1] = ay; res[k * 3 + 2] = az;
+                    float zl, zh;
+                    unpack2(accxy, res[k * 3 + 0], res[k * 3 + 1]);
+                    unpack2(accz, zl, zh);
+                    res[k * 3 + 2] = zl + zh;
                 }
                 if (half == 1) {
                     // both halves' accumulator columns are in registers: hand the buffer back to the MMA warp
@@ -339,17 +414,18 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
                 dst[1] = make_float4(res[4], res[5], res[6], res[7]);
                 dst[2] = make_float4(res[8], res[9], res[10], res[11]);
                 __syncwarp();
-                const int c_first = (v_first + half * 4) * 3;       // first vertex coordinate of this half
+                const int c_first = c_unit + half * 12;             // first vertex coordinate of this half
+                float* vhalf = vrow + half * 12;
 #pragma unroll
                 for (int it = 0; it < 6; ++it) {
-                    const int row = rb_row[it % 3] + (it / 3) * 16, c2 = rb_col[it % 3];
-                    const float2 val = *reinterpret_cast<const float2*>(my_out + row * 12 + c2 * 2);
-                    const int64_t fr = ft * FUSED_BM + quarter * 32 + row;
-                    if (fr < B && c_first + c2 * 2 < NVC)
-                        *reinterpret_cast<float2*>(vrow + (size_t)row * NVC + half * 12 + c2 * 2) = val;
+                    const int j = it % 3, up = (it / 3) * 16;
+                    const float2 val = *reinterpret_cast<const float2*>(my_out + rb_smem[j] + up * 12);
+                    if (rb_row[j] + up < rows_valid && c_first + rb_c2[j] < NVC && !DBG(4))
+                        *reinterpret_cast<float2*>(vhalf + rb_glob[j] + up * NVC) = val;
                 }
                 __syncwarp();
             }
+            if (++vt == FUSED_NT) { vt = 0; ++ft; }
         }
     }
 
@@ -384,15 +460,19 @@ cudaError_t launch_fused(const Model& m, const CUtensorMap& tmap_A, int64_t rows
         if (e != cudaSuccess) return e;
         attr_set[m.device] = smem;
     }
+    int dbg = 0;
+#ifdef PRK_FUSED_DEBUG
+    if (const char* e = getenv("PRK_FUSED_DBG")) dbg = atoi(e);
+#endif
     const int64_t n_units = (rows_pad / FUSED_BM) * FUSED_NT;
     int grid = m.sm_count > 0 ? m.sm_count : 148;
     if (grid > n_units) grid = (int)n_units;
     if (groups == 1)
         fused_blend_skin_kernel<1><<<grid, kThreads, smem, s>>>(tmap_A, m.tmap_B2, d_AskinT, d_off, m.d_wpack, groups, stages,
-                                                                B, n_units, d_verts);
+                                                                B, n_units, d_verts, dbg);
     else
         fused_blend_skin_kernel<0><<<grid, kThreads, smem, s>>>(tmap_A, m.tmap_B2, d_AskinT, d_off, m.d_wpack, groups, stages,
-                                                                B, n_units, d_verts);
+                                                                B, n_units, d_verts, dbg);
     count_launch();
     return cudaGetLastError();
 }

@@ -101,6 +101,10 @@ __device__ __forceinline__ float skin_t(const float* G, int r, float j0, float j
     return __fsub_rn(G[r * 4 + 3], dot3(G[r * 4 + 0], G[r * 4 + 1], G[r * 4 + 2], j0, j1, j2));
 }
 
+// K12 TMEM column of entry (row r, column c) of a 3x4 skinning transform: rows 0 and 1 are interleaved
+// so the fused kernel's packed FFMA2 sees (R0c, R1c) register pairs:  R00 R10 R01 R11 R02 R12 t0 t1 | R20 R21 R22 t2
+__host__ __device__ constexpr int askin_col(int r, int c) { return r == 2 ? 8 + c : 2 * c + r; }
+
 // mode bits
 constexpr uint32_t MODE_FRAME_BETAS_ALWAYS = 1u;  // betas given and model betas are zero
 constexpr uint32_t MODE_FRAME_BETAS_FLAG = 2u;    // betas given, honour flags->betas_nonzero
@@ -197,8 +201,8 @@ pose_chain_kernel(const __grid_constant__ PoseConsts pc, const float* __restrict
             float* dst = Askin + ((f >> 5) * FUSED_ASKIN_COLS + j * 12) * 32 + (f & 31);
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
-                dst[(r * 4 + 0) * 32] = G[j][r * 4 + 0]; dst[(r * 4 + 1) * 32] = G[j][r * 4 + 1];
-                dst[(r * 4 + 2) * 32] = G[j][r * 4 + 2]; dst[(r * 4 + 3) * 32] = skin_t(G[j], r, J[j][0], J[j][1], J[j][2]);
+                dst[askin_col(r, 0) * 32] = G[j][r * 4 + 0]; dst[askin_col(r, 1) * 32] = G[j][r * 4 + 1];
+                dst[askin_col(r, 2) * 32] = G[j][r * 4 + 2]; dst[askin_col(r, 3) * 32] = skin_t(G[j], r, J[j][0], J[j][1], J[j][2]);
             }
         } else if (kMesh) {
             float4* dst = reinterpret_cast<float4*>(Askin + (f * NJ + j) * 12);
@@ -336,8 +340,8 @@ pose_chain_warp_kernel(const float* __restrict__ Jc /* J_template[72] | Jdirs[72
         float* dst = Askin + ((f >> 5) * FUSED_ASKIN_COLS + j * 12) * 32 + (f & 31);
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
-            dst[(r * 4 + 0) * 32] = G[r * 4 + 0]; dst[(r * 4 + 1) * 32] = G[r * 4 + 1];
-            dst[(r * 4 + 2) * 32] = G[r * 4 + 2]; dst[(r * 4 + 3) * 32] = skin_t(G, r, J[0], J[1], J[2]);
+            dst[askin_col(r, 0) * 32] = G[r * 4 + 0]; dst[askin_col(r, 1) * 32] = G[r * 4 + 1];
+            dst[askin_col(r, 2) * 32] = G[r * 4 + 2]; dst[askin_col(r, 3) * 32] = skin_t(G, r, J[0], J[1], J[2]);
         }
     } else if (active) {
         float4* dst = reinterpret_cast<float4*>(Askin + (f * NJ + j) * 12);

@@ -41,15 +41,22 @@ namespace {
 
 using namespace tc;
 
+#ifdef PRK_FUSED_SPIN
+#define MBAR_WAIT mbar_wait_spin
+#else
+#define MBAR_WAIT mbar_wait
+#endif
+
 constexpr int kAChunkBytes = FUSED_BM * 128;                     // 128 frames x 64 bf16
 constexpr int kABytes = FUSED_KCHUNKS * kAChunkBytes;            // 131,072: resident A' tile
 constexpr int kBChunkBytes = FUSED_BN * 128;                     // 96 vertex coords x 64 bf16 = 12,288
 constexpr int kEpiWarps = 16;
-constexpr int kOutBytesPerWarp = 32 * 48;                        // 32 frames x 4 vertices x 3 floats
-constexpr int kOutBytes = kEpiWarps * kOutBytesPerWarp;          // 24,576
+constexpr int kOutPitch = 52;                                    // floats per staged frame row: 16 vertices x 3 (+4: conflict-free float4)
+constexpr int kOutBytesPerQuarter = 32 * kOutPitch * 4;          // 32 frames of one TMEM lane quarter
+constexpr int kOutBytes = 4 * kOutBytesPerQuarter;               // 26,624
 constexpr int kWSlots = 4;
 constexpr int kMaxStages = 6;
-constexpr int kNumBars = 2 * kMaxStages + 2 + 2 + kWSlots + 2;
+constexpr int kNumBars = 2 * kMaxStages + 2 * kEpiWarps + 2 + kWSlots + 2;
 constexpr int kThreads = (kEpiWarps + 2) * 32;                   // 576
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kAccCol0 = 288;                               // accumulators behind the 24 x 12 A_j columns
@@ -83,6 +90,9 @@ __device__ __forceinline__ void tmem_st_x8(uint32_t taddr, const uint32_t* r) {
                  : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void quarter_barrier(int quarter) {   // the 4 epilogue warps of one TMEM lane quarter
+    asm volatile("bar.sync %0, 128;" ::"r"(2 + quarter) : "memory");
+}
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory"); }
 
 // descriptor offset (units of 16 B) of A' k-step `a` inside the resident tile: chunk a/4, 32 B per k-step
@@ -114,8 +124,13 @@ __device__ __forceinline__ void umma_bf16_lohi(uint32_t d_tmem, uint32_t a_lo, u
 // 8 = no TMEM gather of A_j (math on stale registers), 16 = no B' loads (producer only signals).
 #ifdef PRK_FUSED_DEBUG
 #define DBG(bit) (dbg & (bit))
+__device__ unsigned long long g_fdbg[8];
+#define TCLK(var) const long long var = clock64()
+#define TACC(k, a, b) t_sum[k] += (b) - (a)
 #else
 #define DBG(bit) 0
+#define TCLK(var)
+#define TACC(k, a, b)
 #endif
 
 // Packed fp32 pairs (Blackwell FFMA2): one issue slot per two FMAs -- the epilogue is issue-bound.
@@ -165,8 +180,10 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
     uint64_t* bars = reinterpret_cast<uint64_t*>(sW + kWSlots * groups * FUSED_WGROUP_BYTES);
     uint64_t* full_bar = bars;                                    // [kMaxStages]
     uint64_t* empty_bar = bars + kMaxStages;                      // [kMaxStages]
-    uint64_t* tfull_bar = bars + 2 * kMaxStages;                  // [2]
-    uint64_t* tempty_bar = tfull_bar + 2;                         // [2]
+    // one "accumulator full" barrier PER EPILOGUE WARP: warps parked on a common mbarrier are woken
+    // one after the other (~2.5 us per unit for 16 waiters), a private barrier wakes at once
+    uint64_t* tfull_bar = bars + 2 * kMaxStages;                  // [2 accumulators][kEpiWarps]
+    uint64_t* tempty_bar = tfull_bar + 2 * kEpiWarps;             // [2]
     uint64_t* wfull_bar = tempty_bar + 2;                         // [kWSlots]
     uint64_t* afull_bar = wfull_bar + kWSlots;
     uint64_t* aempty_bar = afull_bar + 1;
@@ -183,7 +200,8 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_A)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_B)) : "memory");
         for (int i = 0; i < kMaxStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], kEpiWarps); }
+        for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&tfull_bar[i], 1);
+        for (int i = 0; i < 2; ++i) mbar_init(&tempty_bar[i], kEpiWarps);
         for (int i = 0; i < kWSlots; ++i) mbar_init(&wfull_bar[i], 1);
         mbar_init(afull_bar, 1);
         mbar_init(aempty_bar, 1);
@@ -215,7 +233,7 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
         for (int i = 0; i < n_my; ++i) {
             if (i == 0 || vt == 0) {
                 // the MMAs of the previous frame tile still read the resident A' tile
-                if (n_ft > 0) mbar_wait(aempty_bar, (n_ft - 1) & 1);
+                if (n_ft > 0) MBAR_WAIT(aempty_bar, (n_ft - 1) & 1);
                 if (elect_one()) {
                     mbar_expect_tx(afull_bar, kABytes);
                     for (int c = 0; c < FUSED_KCHUNKS; ++c)
@@ -234,7 +252,7 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
             }
 #pragma unroll 1
             for (int c = 0; c < FUSED_KCHUNKS; ++c) {
-                mbar_wait(&empty_bar[stage], phase ^ 1);
+                MBAR_WAIT(&empty_bar[stage], phase ^ 1);
                 if (elect_one()) {
                     if (DBG(16)) { mbar_arrive(&full_bar[stage]); }
                     else {
@@ -260,17 +278,20 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
         for (int i = 0; i < n_my; ++i) {
             if (i == 0 || vt == 0) {
                 if (n_ft > 0 && elect_one()) tcgen05_commit(aempty_bar);   // all MMAs on the old A' tile retire first
-                mbar_wait(afull_bar, n_ft & 1);
+                MBAR_WAIT(afull_bar, n_ft & 1);
                 tcgen05_fence_after();
                 ++n_ft;
             }
             const int acc = i & 1;
-            mbar_wait(&tempty_bar[acc], ((i >> 1) & 1) ^ 1);       // epilogue drained this accumulator
+            // the tile's skinning weights: waited for here (single waiter) so the epilogue warps,
+            // which see them through their tfull barrier, never park on the TMA barrier
+            MBAR_WAIT(&wfull_bar[i & (kWSlots - 1)], (i >> 2) & 1);
+            MBAR_WAIT(&tempty_bar[acc], ((i >> 1) & 1) ^ 1);       // epilogue drained this accumulator
             tcgen05_fence_after();
             const uint32_t d_tmem = tmem_base + kAccCol0 + (uint32_t)acc * FUSED_BN;
 #pragma unroll
             for (int c = 0; c < FUSED_KCHUNKS; ++c) {
-                mbar_wait(&full_bar[stage], phase);
+                MBAR_WAIT(&full_bar[stage], phase);
                 tcgen05_fence_after();
                 const uint32_t b_lo = b_lo0 + (uint32_t)stage * (kBChunkBytes >> 4);
                 if (elect_one()) {
@@ -292,7 +313,10 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
                         }
                     }
                     tcgen05_commit(&empty_bar[stage]);            // frees the ring slot when the MMAs retire
-                    if (c == FUSED_KCHUNKS - 1) tcgen05_commit(&tfull_bar[acc]);
+                    if (c == FUSED_KCHUNKS - 1) {
+#pragma unroll
+                        for (int w = 0; w < kEpiWarps; ++w) tcgen05_commit(&tfull_bar[acc * kEpiWarps + w]);
+                    }
                 }
                 if (++stage == stages) { stage = 0; phase ^= 1; }
             }
@@ -302,20 +326,28 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
         // ===== epilogue: thread = frame (TMEM lane), loop over the warp's 8 vertices of each unit =====
         const int quarter = warp & 3, oct = warp >> 2;
         const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
-        float* my_out = reinterpret_cast<float*>(sOut + warp * kOutBytesPerWarp);
-        // transpose read-back: float2 index q = it*32 + lane over [32 frames][6 float2]; iterations
-        // it+3 hit the same column 16 rows further down
+        // Vertices leave through a staging tile shared by the four warps of a lane quarter:
+        // [32 frames][16 vertices x 3 floats] per half unit, so every frame row is written to HBM as one
+        // 192-byte run (the L1->L2 store path is paid per 128-byte line touched, not per byte).
+        // In half h warp `oct` computes vertices 16h + 4oct .. +3 and stores frame rows 8oct .. 8oct+7.
+        float* q_out = reinterpret_cast<float*>(sOut + quarter * kOutBytesPerQuarter);
+        // read-back: float2 index q = it*32 + lane over [8 rows][24 float2]; iterations it+3 hit the same
+        // column 4 rows further down
         int rb_smem[3], rb_glob[3], rb_row[3], rb_c2[3];
 #pragma unroll
         for (int it = 0; it < 3; ++it) {
             const int q = it * 32 + lane;
-            rb_row[it] = q / 6; rb_c2[it] = (q - rb_row[it] * 6) * 2;
-            rb_smem[it] = rb_row[it] * 12 + rb_c2[it];            // float index in the staging tile
+            rb_row[it] = oct * 8 + q / 24; rb_c2[it] = (q % 24) * 2;
+            rb_smem[it] = rb_row[it] * kOutPitch + rb_c2[it];     // float index in the staging tile
             rb_glob[it] = rb_row[it] * NVC + rb_c2[it];           // float offset from the tile's first frame row
         }
 
         int64_t ft = ft0; int vt = vt0;
         float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+#ifdef PRK_FUSED_DEBUG
+        long long t_sum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const long long t_begin = clock64();
+#endif
         for (int i = 0; i < n_my; ++i) {
             if (i == 0 || vt == 0) {
                 // ---- new frame tile: A_j of my 32 frames -> TMEM columns [72*oct, 72*oct+72) ----
@@ -338,9 +370,13 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
             const int acc = i & 1;
             const uint32_t wbytes = (uint32_t)groups * FUSED_WGROUP_BYTES;
             const uint8_t* wslot = sW + (i & (kWSlots - 1)) * wbytes;
-            mbar_wait(&wfull_bar[i & (kWSlots - 1)], (i >> 2) & 1);
-            mbar_wait(&tfull_bar[acc], (i >> 1) & 1);
+            TCLK(tw0);
+            MBAR_WAIT(&tfull_bar[acc * kEpiWarps + warp], (i >> 1) & 1);
             tcgen05_fence_after();
+            TCLK(tw1);
+            MBAR_WAIT(&wfull_bar[i & (kWSlots - 1)], (i >> 2) & 1);   // completed before the MMAs were issued: never parks
+            TCLK(tw2);
+            TACC(0, tw0, tw1); TACC(1, tw1, tw2);
             if (DBG(2)) {
                 tcgen05_fence_before();
                 __syncwarp();
@@ -348,85 +384,163 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
                 if (++vt == FUSED_NT) { vt = 0; ++ft; }
                 continue;
             }
-            const uint32_t t_acc = t_lane + kAccCol0 + (uint32_t)acc * FUSED_BN + (uint32_t)(oct * 24);
-            const int c_unit = (vt * FUSED_VT + oct * 8) * 3;       // first vertex coordinate of this warp's 8 vertices
+            const uint32_t t_acc = t_lane + kAccCol0 + (uint32_t)acc * FUSED_BN + (uint32_t)(oct * 12);
+            const int c_unit = vt * FUSED_VT * 3;                   // first vertex coordinate of the tile
             float* vrow = verts + (size_t)(ft * FUSED_BM + quarter * 32) * NVC + c_unit;
             const int rows_valid = (int)((B - (ft * FUSED_BM + quarter * 32)) < 32 ? (B - (ft * FUSED_BM + quarter * 32)) : 32);
 
-#pragma unroll 1
-            for (int half = 0; half < 2; ++half) {
+            // transposed store of the quarter's 16 finished vertices (48 floats per frame) of half unit `half`
+            auto store_half = [&](const float* res, int half) {
+                if (DBG(128)) { if (res[0] == 123.456f) vrow[0] = res[1]; return; }
+                TCLK(ts0);
+                float4* dst = reinterpret_cast<float4*>(q_out + lane * kOutPitch + oct * 12);   // pitch 208 B: conflict-free float4
+                dst[0] = make_float4(res[0], res[1], res[2], res[3]);
+                dst[1] = make_float4(res[4], res[5], res[6], res[7]);
+                dst[2] = make_float4(res[8], res[9], res[10], res[11]);
+                quarter_barrier(quarter);                           // all four warps' columns are staged
+                const int c_first = c_unit + half * 48;             // first vertex coordinate of this half
+                float* vhalf = vrow + half * 48;
+#pragma unroll
+                for (int it = 0; it < 6; ++it) {
+                    const int j = it % 3, up = (it / 3) * 4;
+                    const float2 val = *reinterpret_cast<const float2*>(q_out + rb_smem[j] + up * kOutPitch);
+                    if (rb_row[j] + up < rows_valid && c_first + rb_c2[j] < NVC && !DBG(4))
+                        *reinterpret_cast<float2*>(vhalf + rb_glob[j] + up * NVC) = val;
+                }
+                quarter_barrier(quarter);                           // tile may be overwritten by the next half
+                TCLK(ts1);
+                TACC(3, ts0, ts1);
+            };
+            // one joint's contribution: TMEM columns R00 R10 R01 R11 R02 R12 t0 t1 | R20 R21 R22 t2
+            auto joint_math = [&](const uint32_t* a, uint64_t ww, uint64_t pxx, uint64_t pyy, uint64_t pzz, uint64_t pxy,
+                                  uint64_t pz1, uint64_t& accxy, uint64_t& accz) {
+                uint64_t xy = fma2(pack2(a[0], a[1]), pxx, pack2(a[6], a[7]));
+                xy = fma2(pack2(a[2], a[3]), pyy, xy);
+                xy = fma2(pack2(a[4], a[5]), pzz, xy);
+                uint64_t zz = mul2(pack2(a[8], a[9]), pxy);     // (R20 px, R21 py)
+                zz = fma2(pack2(a[10], a[11]), pz1, zz);        // (+ R22 pz, + t2): z = lo + hi
+                accxy = fma2(ww, xy, accxy);
+                accz = fma2(ww, zz, accz);
+            };
+
+            if (kGroups == 1) {
+                // Software pipeline over the 32 (vertex, joint) items of the unit: the gather of item
+                // n+1 is in flight while item n is multiplied, with two 12-register buffers -- TMEM
+                // read bandwidth is the bound of this kernel, so it must never sit idle.
+                // the warp's k-th vertex is tile vertex 16 (k >> 2) + 4 oct + (k & 3)
+                const uint4* cols = reinterpret_cast<const uint4*>(wslot + 1024) + oct * 4;
+                const float4* wA = reinterpret_cast<const float4*>(wslot) + oct * 4;
+                const float4* wB = reinterpret_cast<const float4*>(wslot + 512) + oct * 4;
+                constexpr int kTileV[8] = {0, 1, 2, 3, 16, 17, 18, 19};
+                uint32_t buf[2][12], p[2][4];
+                uint4 cj = DBG(64) ? make_uint4(12, 36, 120, 240) : cols[0];
+                TCLK(tg0);
+#ifdef PRK_FUSED_DEBUG
+                for (int z = 0; z < 12; ++z) { buf[0][z] = 0x3f000000u + z; buf[1][z] = 0x3f100000u + z; }
+                for (int z = 0; z < 4; ++z) { p[0][z] = 0x3e000000u + z; p[1][z] = 0x3e100000u + z; }
+#endif
+                if (!DBG(256)) tmem_ld_x4(t_acc, p[0]);
+                if (!DBG(8)) { tmem_ld_x8(t_lane + cj.x, buf[0]); tmem_ld_x4(t_lane + cj.x + 8, buf[0] + 8); }
                 float res[12];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int vl = oct * 8 + half * 4 + k;        // vertex within the tile
-                    uint32_t p[4];
-                    tmem_ld_x4(t_acc + (uint32_t)((half * 4 + k) * 3), p);
+                for (int k = 0; k < 8; ++k) {
+                    const float4 wa = DBG(64) ? make_float4(.25f, .25f, .25f, .25f) : wA[kTileV[k]], wb = DBG(64) ? wa : wB[kTileV[k]];
+                    const uint64_t ww[4] = {pack2f(wa.x, wa.y), pack2f(wa.z, wa.w), pack2f(wb.x, wb.y), pack2f(wb.z, wb.w)};
+                    const uint4 cj_next = DBG(64) ? make_uint4(24, 48, 132, 252) : cols[kTileV[k < 7 ? k + 1 : 7]];
                     uint64_t accxy = pack2f(o0, o1), accz = pack2f(o2, 0.f);
                     uint64_t pxx = 0, pyy = 0, pzz = 0, pxy = 0, pz1 = 0;
 #pragma unroll
-                    for (int g = 0; g < (kGroups > 0 ? kGroups : groups); ++g) {
-                        const uint8_t* wg = wslot + g * FUSED_WGROUP_BYTES;
-                        const uint4 cj = reinterpret_cast<const uint4*>(wg + 1024)[vl];     // 12 * joint, 4 joints
-                        uint32_t r[48];
+                    for (int q = 0; q < 4; ++q) {
+                        const int n = k * 4 + q;
+                        if (!DBG(512)) tmem_ld_wait();                // item n (and p of vertex k) have landed
+                        if (q == 0) {
+                            const uint32_t* pk = p[k & 1];
+                            pxx = pack2(pk[0], pk[0]); pyy = pack2(pk[1], pk[1]); pzz = pack2(pk[2], pk[2]);
+                            pxy = pack2(pk[0], pk[1]); pz1 = pack2(pk[2], 0x3f800000u);
+                        }
+                        uint32_t* nb = buf[(n + 1) & 1];
+                        if (q < 3) {
+                            const uint32_t col = q == 0 ? cj.y : (q == 1 ? cj.z : cj.w);
+                            if (!DBG(8)) { tmem_ld_x8(t_lane + col, nb); tmem_ld_x4(t_lane + col + 8, nb + 8); }
+                        } else if (k < 7) {
+                            if (!DBG(256)) tmem_ld_x4(t_acc + (uint32_t)(kTileV[k + 1] * 3), p[(k + 1) & 1]);
+                            if (!DBG(8)) { tmem_ld_x8(t_lane + cj_next.x, nb); tmem_ld_x4(t_lane + cj_next.x + 8, nb + 8); }
+                        }
+                        if (DBG(32)) accxy = fma2(ww[q], pack2(buf[n & 1][0], buf[n & 1][11]), accxy);
+                        else
+                        joint_math(buf[n & 1], ww[q], pxx, pyy, pzz, pxy, pz1, accxy, accz);
+                        if (k == 7 && q == 0) {
+                            // the last accumulator columns are in registers: hand the buffer back to the MMA warp
+                            tcgen05_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                        }
+                    }
+                    cj = cj_next;
+                    float zl, zh;
+                    unpack2(accxy, res[(k & 3) * 3 + 0], res[(k & 3) * 3 + 1]);
+                    unpack2(accz, zl, zh);
+                    res[(k & 3) * 3 + 2] = zl + zh;
+                    if ((k & 3) == 3) {
+                        TCLK(tg1);
+                        TACC(2, tg0, tg1);
+                        store_half(res, k >> 2);
+                    }
+                }
+            } else {
+#pragma unroll 1
+                for (int half = 0; half < 2; ++half) {
+                    float res[12];
 #pragma unroll
-                        for (int q = 0; q < 48; ++q) r[q] = 0x3f000000u + q;
-                        if (!DBG(8)) {
+                    for (int k = 0; k < 4; ++k) {
+                        const int vl = half * 16 + oct * 4 + k;       // vertex within the tile
+                        uint32_t p[4];
+                        tmem_ld_x4(t_acc + (uint32_t)((half * 16 + k) * 3), p);
+                        uint64_t accxy = pack2f(o0, o1), accz = pack2f(o2, 0.f);
+                        uint64_t pxx = 0, pyy = 0, pzz = 0, pxy = 0, pz1 = 0;
+#pragma unroll 1
+                        for (int g = 0; g < groups; ++g) {
+                            const uint8_t* wg = wslot + g * FUSED_WGROUP_BYTES;
+                            const uint4 cj = reinterpret_cast<const uint4*>(wg + 1024)[vl];     // 12 * joint, 4 joints
+                            uint32_t r[48];
                             tmem_ld_x8(t_lane + cj.x, r +  0); tmem_ld_x4(t_lane + cj.x + 8, r +  8);
                             tmem_ld_x8(t_lane + cj.y, r + 12); tmem_ld_x4(t_lane + cj.y + 8, r + 20);
                             tmem_ld_x8(t_lane + cj.z, r + 24); tmem_ld_x4(t_lane + cj.z + 8, r + 32);
                             tmem_ld_x8(t_lane + cj.w, r + 36); tmem_ld_x4(t_lane + cj.w + 8, r + 44);
-                        }
-                        const float4 wA = reinterpret_cast<const float4*>(wg)[vl];          // w0 w0 w1 w1
-                        const float4 wB = reinterpret_cast<const float4*>(wg + 512)[vl];    // w2 w2 w3 w3
-                        tmem_ld_wait();
-                        if (g == 0) {
-                            pxx = pack2(p[0], p[0]); pyy = pack2(p[1], p[1]); pzz = pack2(p[2], p[2]);
-                            pxy = pack2(p[0], p[1]); pz1 = pack2(p[2], 0x3f800000u);
-                        }
-                        const uint64_t ww[4] = {pack2f(wA.x, wA.y), pack2f(wA.z, wA.w), pack2f(wB.x, wB.y), pack2f(wB.z, wB.w)};
+                            const float4 wa = reinterpret_cast<const float4*>(wg)[vl];          // w0 w0 w1 w1
+                            const float4 wb = reinterpret_cast<const float4*>(wg + 512)[vl];    // w2 w2 w3 w3
+                            tmem_ld_wait();
+                            if (g == 0) {
+                                pxx = pack2(p[0], p[0]); pyy = pack2(p[1], p[1]); pzz = pack2(p[2], p[2]);
+                                pxy = pack2(p[0], p[1]); pz1 = pack2(p[2], 0x3f800000u);
+                            }
+                            const uint64_t ww[4] = {pack2f(wa.x, wa.y), pack2f(wa.z, wa.w), pack2f(wb.x, wb.y), pack2f(wb.z, wb.w)};
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            // TMEM columns of a joint: R00 R10 R01 R11 R02 R12 t0 t1 | R20 R21 R22 t2
-                            const uint32_t* a = r + q * 12;
-                            uint64_t xy = fma2(pack2(a[0], a[1]), pxx, pack2(a[6], a[7]));
-                            xy = fma2(pack2(a[2], a[3]), pyy, xy);
-                            xy = fma2(pack2(a[4], a[5]), pzz, xy);
-                            uint64_t zz = mul2(pack2(a[8], a[9]), pxy);     // (R20 px, R21 py)
-                            zz = fma2(pack2(a[10], a[11]), pz1, zz);        // (+ R22 pz, + t2): z = lo + hi
-                            accxy = fma2(ww[q], xy, accxy);
-                            accz = fma2(ww[q], zz, accz);
+                            for (int q = 0; q < 4; ++q) joint_math(r + q * 12, ww[q], pxx, pyy, pzz, pxy, pz1, accxy, accz);
                         }
+                        float zl, zh;
+                        unpack2(accxy, res[k * 3 + 0], res[k * 3 + 1]);
+                        unpack2(accz, zl, zh);
+                        res[k * 3 + 2] = zl + zh;
                     }
-                    float zl, zh;
-                    unpack2(accxy, res[k * 3 + 0], res[k * 3 + 1]);
-                    unpack2(accz, zl, zh);
-                    res[k * 3 + 2] = zl + zh;
+                    if (half == 1) {
+                        // both halves' accumulator columns are in registers: hand the buffer back to the MMA warp
+                        tcgen05_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                    }
+                    store_half(res, half);
                 }
-                if (half == 1) {
-                    // both halves' accumulator columns are in registers: hand the buffer back to the MMA warp
-                    tcgen05_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-                }
-                // transpose through shared memory: [frame = lane][12 floats], pitch 48 B (conflict-free float4)
-                float4* dst = reinterpret_cast<float4*>(my_out + lane * 12);
-                dst[0] = make_float4(res[0], res[1], res[2], res[3]);
-                dst[1] = make_float4(res[4], res[5], res[6], res[7]);
-                dst[2] = make_float4(res[8], res[9], res[10], res[11]);
-                __syncwarp();
-                const int c_first = c_unit + half * 12;             // first vertex coordinate of this half
-                float* vhalf = vrow + half * 12;
-#pragma unroll
-                for (int it = 0; it < 6; ++it) {
-                    const int j = it % 3, up = (it / 3) * 16;
-                    const float2 val = *reinterpret_cast<const float2*>(my_out + rb_smem[j] + up * 12);
-                    if (rb_row[j] + up < rows_valid && c_first + rb_c2[j] < NVC && !DBG(4))
-                        *reinterpret_cast<float2*>(vhalf + rb_glob[j] + up * NVC) = val;
-                }
-                __syncwarp();
             }
             if (++vt == FUSED_NT) { vt = 0; ++ft; }
         }
+#ifdef PRK_FUSED_DEBUG
+        if (lane == 0) {
+            t_sum[4] = clock64() - t_begin;
+            for (int k = 0; k < 5; ++k) atomicAdd(&g_fdbg[k], (unsigned long long)t_sum[k]);
+            atomicAdd(&g_fdbg[7], 1ull);
+        }
+#endif
     }
 
     tcgen05_fence_before();
@@ -438,6 +552,14 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
 }
 
 }  // namespace
+
+#ifdef PRK_FUSED_DEBUG
+extern "C" __attribute__((visibility("default"))) int prk_fused_debug_read(unsigned long long* out, int reset) {
+    cudaMemcpyFromSymbol(out, g_fdbg, sizeof(unsigned long long) * 8);
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_fdbg, z, sizeof z); }
+    return 0;
+}
+#endif
 
 int fused_stages(int groups) {
     int stages = kMaxStages;

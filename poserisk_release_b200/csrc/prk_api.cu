@@ -424,20 +424,17 @@ int prk_model_create(prk_model** out, int device, const float* vt, const float* 
         }
     }
 
-    // the same pairs per 32-vertex tile for K12: [tile][group][32 x {w0,w0,w1,w1} | 32 x {w2,w2,w3,w3} | 32 x uint4 columns]
+    // the same pairs per 32-vertex tile for K12: [tile][group][32 x float4 weights | 32 x uint4 TMEM columns]
     std::vector<uint8_t> wp((size_t)FUSED_NT * m->nnz_groups * FUSED_WGROUP_BYTES, 0);
     for (int v = 0; v < NV; ++v) {
         const int tile = v / FUSED_VT, vl = v % FUSED_VT;
         for (int g = 0; g < m->nnz_groups; ++g) {
             uint8_t* base = &wp[((size_t)tile * m->nnz_groups + g) * FUSED_WGROUP_BYTES];
-            const float* w4 = reinterpret_cast<const float*>(&wv[(size_t)g * NV + v]);
-            const float wa[4] = {w4[0], w4[0], w4[1], w4[1]}, wb[4] = {w4[2], w4[2], w4[3], w4[3]};
-            memcpy(base + vl * 16, wa, 16);
-            memcpy(base + FUSED_VT * 16 + vl * 16, wb, 16);
+            memcpy(base + vl * 16, &wv[(size_t)g * NV + v], 16);
             const uint32_t id = wi[(size_t)g * NV + v];
             uint32_t cols[4];
             for (int k = 0; k < 4; ++k) cols[k] = ((id >> (8 * k)) & 0xFFu) * 12u;
-            memcpy(base + FUSED_VT * 32 + vl * 16, cols, 16);
+            memcpy(base + FUSED_VT * 16 + vl * 16, cols, 16);
         }
     }
 

@@ -176,7 +176,7 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
     uint8_t* sA = smem;                                           // [8 chunks][128 rows][128 B], 128B swizzle
     uint8_t* sB = sA + kABytes;                                   // [stages][96 rows][128 B]
     uint8_t* sOut = sB + stages * kBChunkBytes;                   // [16 warps][32 frames][12 floats]
-    uint8_t* sW = sOut + kOutBytes;                               // [4 slots][groups][FUSED_WGROUP_BYTES]
+    uint8_t* sW = sOut + kOutBytes;                               // [4 slots][groups][32 x float4 weights | 32 x uint4 columns]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sW + kWSlots * groups * FUSED_WGROUP_BYTES);
     uint64_t* full_bar = bars;                                    // [kMaxStages]
     uint64_t* empty_bar = bars + kMaxStages;                      // [kMaxStages]
@@ -354,12 +354,14 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
                 epi_barrier();                                    // nobody still gathers the old A_j
                 const int64_t f = ft * FUSED_BM + quarter * 32 + lane;
                 const float* src = AskinT + ((size_t)(ft * 4 + quarter) * FUSED_ASKIN_COLS + oct * 72) * 32 + lane;
+                // 72 coalesced loads in three batches of 24: enough loads in flight to cover the L2 latency
 #pragma unroll 1
-                for (int c = 0; c < 9; ++c) {
-                    uint32_t v[8];
+                for (int b = 0; b < 3; ++b) {
+                    uint32_t v[24];
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) v[k] = __float_as_uint(src[(c * 8 + k) * 32]);
-                    tmem_st_x8(t_lane + (uint32_t)(oct * 72 + c * 8), v);
+                    for (int k = 0; k < 24; ++k) v[k] = __float_as_uint(__ldg(src + (b * 24 + k) * 32));
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) tmem_st_x8(t_lane + (uint32_t)(oct * 72 + b * 24 + c * 8), v + c * 8);
                 }
                 tmem_st_wait();
                 if (f < B) { o0 = off[f * 3 + 0]; o1 = off[f * 3 + 1]; o2 = off[f * 3 + 2]; }
@@ -428,9 +430,8 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
                 // n+1 is in flight while item n is multiplied, with two 12-register buffers -- TMEM
                 // read bandwidth is the bound of this kernel, so it must never sit idle.
                 // the warp's k-th vertex is tile vertex 16 (k >> 2) + 4 oct + (k & 3)
-                const uint4* cols = reinterpret_cast<const uint4*>(wslot + 1024) + oct * 4;
-                const float4* wA = reinterpret_cast<const float4*>(wslot) + oct * 4;
-                const float4* wB = reinterpret_cast<const float4*>(wslot + 512) + oct * 4;
+                const uint4* cols = reinterpret_cast<const uint4*>(wslot + 512) + oct * 4;
+                const float4* wgt = reinterpret_cast<const float4*>(wslot) + oct * 4;
                 constexpr int kTileV[8] = {0, 1, 2, 3, 16, 17, 18, 19};
                 uint32_t buf[2][12], p[2][4];
                 uint4 cj = DBG(64) ? make_uint4(12, 36, 120, 240) : cols[0];
@@ -444,8 +445,8 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
                 float res[12];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
-                    const float4 wa = DBG(64) ? make_float4(.25f, .25f, .25f, .25f) : wA[kTileV[k]], wb = DBG(64) ? wa : wB[kTileV[k]];
-                    const uint64_t ww[4] = {pack2f(wa.x, wa.y), pack2f(wa.z, wa.w), pack2f(wb.x, wb.y), pack2f(wb.z, wb.w)};
+                    const float4 w4 = DBG(64) ? make_float4(.25f, .25f, .25f, .25f) : wgt[kTileV[k]];
+                    const uint64_t ww[4] = {pack2f(w4.x, w4.x), pack2f(w4.y, w4.y), pack2f(w4.z, w4.z), pack2f(w4.w, w4.w)};
                     const uint4 cj_next = DBG(64) ? make_uint4(24, 48, 132, 252) : cols[kTileV[k < 7 ? k + 1 : 7]];
                     uint64_t accxy = pack2f(o0, o1), accz = pack2f(o2, 0.f);
                     uint64_t pxx = 0, pyy = 0, pzz = 0, pxy = 0, pz1 = 0;
@@ -501,20 +502,19 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
 #pragma unroll 1
                         for (int g = 0; g < groups; ++g) {
                             const uint8_t* wg = wslot + g * FUSED_WGROUP_BYTES;
-                            const uint4 cj = reinterpret_cast<const uint4*>(wg + 1024)[vl];     // 12 * joint, 4 joints
+                            const uint4 cj = reinterpret_cast<const uint4*>(wg + 512)[vl];      // 12 * joint, 4 joints
                             uint32_t r[48];
                             tmem_ld_x8(t_lane + cj.x, r +  0); tmem_ld_x4(t_lane + cj.x + 8, r +  8);
                             tmem_ld_x8(t_lane + cj.y, r + 12); tmem_ld_x4(t_lane + cj.y + 8, r + 20);
                             tmem_ld_x8(t_lane + cj.z, r + 24); tmem_ld_x4(t_lane + cj.z + 8, r + 32);
                             tmem_ld_x8(t_lane + cj.w, r + 36); tmem_ld_x4(t_lane + cj.w + 8, r + 44);
-                            const float4 wa = reinterpret_cast<const float4*>(wg)[vl];          // w0 w0 w1 w1
-                            const float4 wb = reinterpret_cast<const float4*>(wg + 512)[vl];    // w2 w2 w3 w3
+                            const float4 w4 = reinterpret_cast<const float4*>(wg)[vl];
                             tmem_ld_wait();
                             if (g == 0) {
                                 pxx = pack2(p[0], p[0]); pyy = pack2(p[1], p[1]); pzz = pack2(p[2], p[2]);
                                 pxy = pack2(p[0], p[1]); pz1 = pack2(p[2], 0x3f800000u);
                             }
-                            const uint64_t ww[4] = {pack2f(wa.x, wa.y), pack2f(wa.z, wa.w), pack2f(wb.x, wb.y), pack2f(wb.z, wb.w)};
+                            const uint64_t ww[4] = {pack2f(w4.x, w4.x), pack2f(w4.y, w4.y), pack2f(w4.z, w4.z), pack2f(w4.w, w4.w)};
 #pragma unroll
                             for (int q = 0; q < 4; ++q) joint_math(r + q * 12, ww[q], pxx, pyy, pzz, pxy, pz1, accxy, accz);
                         }

@@ -53,8 +53,8 @@ constexpr int FUSED_VT = 32;             // vertices per tile
 constexpr int FUSED_BN = FUSED_VT * 3;   // 96 accumulator columns
 constexpr int FUSED_NT = GEMM_N / FUSED_BN;   // 216 vertex tiles (6912 vertex slots)
 constexpr int FUSED_ASKIN_COLS = NJ * 12;     // 288 TMEM columns of A_j per frame
-// per tile and group of 4 weights: 32 x {w0,w0,w1,w1} | 32 x {w2,w2,w3,w3} | 32 x uint4 TMEM columns (12 * joint)
-constexpr int FUSED_WGROUP_BYTES = FUSED_VT * 48;
+// per tile and group of 4 weights: 32 x float4 weights | 32 x uint4 TMEM columns (12 * joint)
+constexpr int FUSED_WGROUP_BYTES = FUSED_VT * 32;
 
 // Rest joints as an affine function of betas: J = J_template + Jdirs * beta
 // (folds J_regressor @ (v_template + shapedirs beta), smpl_layer.py:91,95).

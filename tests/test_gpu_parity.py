@@ -457,4 +457,4 @@ def test_launch_counter_counts_our_kernels(engine):
     pose = torch.randn(256, 72).cuda() * 0.3
     engine.run(pose, add_info=EXAMPLE_INFO)
     torch.cuda.synchronize()
-    assert _lib.launch_count() - before == 4      # pose chain, blend GEMM, skinning, scoring
+    assert _lib.launch_count() - before == 3      # pose chain, fused blend GEMM + skinning, scoring

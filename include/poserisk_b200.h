@@ -166,7 +166,13 @@ int prk_pipeline(prk_model* model, const float* d_pose, const float* d_betas,
  * betas / trans host->device, runs prk_pipeline, copies scores and joints device->host.
  * Vertices stay in device memory (d_verts, may be NULL).  Staging buffers live in the
  * workspace: size it with prk_host_workspace_bytes.  Host buffers should be pinned for
- * the copies to be asynchronous. */
+ * the copies to be asynchronous.
+ * Completion is ordered on `stream` (synchronise it before reading h_joints / h_scores),
+ * but the copies run on the handle's own copy streams so that back-to-back calls overlap:
+ * the inputs of call i+1 are uploaded while the kernels of call i run (two input sets in
+ * the workspace), and joints / scores are downloaded while the vertex kernel of the same
+ * call is still running.  The host input buffers are read from the moment of the call
+ * until `stream` reaches it; they must already hold the data when the call is made. */
 size_t prk_host_workspace_bytes(const prk_model* model, int64_t B, uint32_t flags);
 int prk_pipeline_host(prk_model* model, const float* h_pose, const float* h_betas,
                       const float* h_trans, int center_idx, const prk_addinfo* h_info,

@@ -203,8 +203,11 @@ static bool fit_layout(int64_t B, bool mesh, size_t bytes, Layout& L) {
     return true;
 }
 
+// ev_joints (optional) is recorded on `s` once every frame's joints are final, i.e. after the last
+// pose-chain launch and long before the vertex kernels finish
 static int forward_impl(Model* m, const float* d_pose, const float* d_betas, const float* d_trans, int center_idx,
-                        int64_t B, float* d_verts, float* d_joints, void* ws, size_t ws_bytes, cudaStream_t s) {
+                        int64_t B, float* d_verts, float* d_joints, void* ws, size_t ws_bytes, cudaStream_t s,
+                        cudaEvent_t ev_joints = nullptr) {
     if (!m || B < 0 || (B > 0 && (!d_pose || !d_joints)) || center_idx >= NJ) {
         set_detail("prk_smpl_forward", "invalid argument");
         return PRK_ERR_INVALID_ARG;
@@ -234,6 +237,7 @@ static int forward_impl(Model* m, const float* d_pose, const float* d_betas, con
                                        d_trans ? d_trans + s0 * 3 : nullptr, d_flags, center_idx, ns, mesh,
                                        mesh && fused_enabled(), d_arows, d_askin, d_off, d_joints + s0 * 72, s));
         }
+        if (ev_joints && s0 + S >= B) PRK_CUDA(cudaEventRecord(ev_joints, s));
         if (!mesh) continue;
         if (fused_enabled()) {
             const int64_t rows_pad = round_up(ns, FUSED_BM);
@@ -466,7 +470,13 @@ int prk_model_create(prk_model** out, int device, const float* vt, const float* 
     for (int i = 0; i < 2; ++i) {
         PRK_M(cudaEventCreateWithFlags(&m->ev_gemm[i], cudaEventDisableTiming));
         PRK_M(cudaEventCreateWithFlags(&m->ev_skin[i], cudaEventDisableTiming));
+        PRK_M(cudaEventCreateWithFlags(&m->ev_set_free[i], cudaEventDisableTiming));
     }
+    PRK_M(cudaStreamCreateWithFlags(&m->s_in, cudaStreamNonBlocking));
+    PRK_M(cudaStreamCreateWithFlags(&m->s_out, cudaStreamNonBlocking));
+    PRK_M(cudaEventCreateWithFlags(&m->ev_h2d, cudaEventDisableTiming));
+    PRK_M(cudaEventCreateWithFlags(&m->ev_joints, cudaEventDisableTiming));
+    PRK_M(cudaEventCreateWithFlags(&m->ev_out, cudaEventDisableTiming));
 #undef PRK_M
     int rc = encode_tmap_2d_bf16(&m->tmap_B, m->d_Bmat, GEMM_N, GEMM_K, GEMM_BN, GEMM_BK);
     if (rc != PRK_OK) { prk_model_destroy(m); return rc; }
@@ -488,6 +498,12 @@ void prk_model_destroy(prk_model* model) {
     if (m->ev_in) cudaEventDestroy(m->ev_in);
     if (m->ev_score) cudaEventDestroy(m->ev_score);
     for (int i = 0; i < 2; ++i) { if (m->ev_gemm[i]) cudaEventDestroy(m->ev_gemm[i]); if (m->ev_skin[i]) cudaEventDestroy(m->ev_skin[i]); }
+    if (m->s_in) { cudaStreamSynchronize(m->s_in); cudaStreamDestroy(m->s_in); }
+    if (m->s_out) { cudaStreamSynchronize(m->s_out); cudaStreamDestroy(m->s_out); }
+    if (m->ev_h2d) cudaEventDestroy(m->ev_h2d);
+    if (m->ev_joints) cudaEventDestroy(m->ev_joints);
+    if (m->ev_out) cudaEventDestroy(m->ev_out);
+    for (int i = 0; i < 2; ++i) if (m->ev_set_free[i]) cudaEventDestroy(m->ev_set_free[i]);
     delete m;
 }
 int prk_model_device(const prk_model* model) { return model ? model->device : -1; }
@@ -587,8 +603,10 @@ int prk_pipeline(prk_model* model, const float* d_pose, const float* d_betas, co
     return PRK_OK;
 }
 
-// host-staging layout in front of the device workspace
-struct HostStage { size_t pose, betas, trans, info, track, joints, scores, inner, total; };
+// host-staging layout in front of the device workspace: two input sets (the copy-in of call i+1
+// runs under the kernels of call i), one output set (joints and scores are copied out while the
+// vertex kernel of the same call is still running)
+struct HostStage { size_t in_set, pose, betas, trans, info, track, joints, scores, inner, total; };
 static HostStage host_stage(int64_t B, int32_t n_tracks, size_t inner_bytes) {
     HostStage h;
     size_t o = 0;
@@ -597,6 +615,8 @@ static HostStage host_stage(int64_t B, int32_t n_tracks, size_t inner_bytes) {
     h.trans = o;  o += align_up((size_t)B * 3 * 4);
     h.info = o;   o += align_up((size_t)(n_tracks < 1 ? 1 : n_tracks) * sizeof(prk_addinfo));
     h.track = o;  o += align_up((size_t)B * 4);
+    h.in_set = o;                      // bytes of one input set; the second set follows
+    o *= 2;
     h.joints = o; o += align_up((size_t)B * 72 * 4);
     h.scores = o; o += align_up((size_t)B * sizeof(prk_score_rec));
     h.inner = o;  o += inner_bytes;
@@ -624,24 +644,53 @@ int prk_pipeline_host(prk_model* model, const float* h_pose, const float* h_beta
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const HostStage h = host_stage(B, 4096, 0);
     if (ws_bytes <= h.inner) { set_detail("prk_pipeline_host", "workspace too small"); return PRK_ERR_WORKSPACE; }
+    const int set = (int)(m->host_calls++ & 1);
     uint8_t* w = static_cast<uint8_t*>(ws);
-    float* d_pose = reinterpret_cast<float*>(w + h.pose);
-    float* d_betas = h_betas ? reinterpret_cast<float*>(w + h.betas) : nullptr;
-    float* d_trans = h_trans ? reinterpret_cast<float*>(w + h.trans) : nullptr;
-    prk_addinfo* d_info = reinterpret_cast<prk_addinfo*>(w + h.info);
-    int32_t* d_track = h_track ? reinterpret_cast<int32_t*>(w + h.track) : nullptr;
+    uint8_t* wi = w + (size_t)set * h.in_set;
+    float* d_pose = reinterpret_cast<float*>(wi + h.pose);
+    float* d_betas = h_betas ? reinterpret_cast<float*>(wi + h.betas) : nullptr;
+    float* d_trans = h_trans ? reinterpret_cast<float*>(wi + h.trans) : nullptr;
+    prk_addinfo* d_info = reinterpret_cast<prk_addinfo*>(wi + h.info);
+    int32_t* d_track = h_track ? reinterpret_cast<int32_t*>(wi + h.track) : nullptr;
     float* d_joints = reinterpret_cast<float*>(w + h.joints);
     prk_score_rec* d_scores = reinterpret_cast<prk_score_rec*>(w + h.scores);
-    PRK_CUDA(cudaMemcpyAsync(d_pose, h_pose, (size_t)B * 72 * 4, cudaMemcpyHostToDevice, s));
-    if (h_betas) PRK_CUDA(cudaMemcpyAsync(d_betas, h_betas, (size_t)B * NBETA * 4, cudaMemcpyHostToDevice, s));
-    if (h_trans) PRK_CUDA(cudaMemcpyAsync(d_trans, h_trans, (size_t)B * 3 * 4, cudaMemcpyHostToDevice, s));
-    PRK_CUDA(cudaMemcpyAsync(d_info, h_info, (size_t)n_tracks * sizeof(prk_addinfo), cudaMemcpyHostToDevice, s));
-    if (h_track) PRK_CUDA(cudaMemcpyAsync(d_track, h_track, (size_t)B * 4, cudaMemcpyHostToDevice, s));
-    int rc = prk_pipeline(model, d_pose, d_betas, d_trans, center_idx, d_info, d_track, B, d_verts, d_joints, d_scores,
-                          w + h.inner, ws_bytes - h.inner, stream);
+
+    // ---- copy-in stream: inputs of this call land while the kernels of the previous call run (the
+    // host buffers must be ready when the call is made, as for any host argument).  The set was
+    // last read by the call before the previous one (ev_set_free).
+    PRK_CUDA(cudaStreamWaitEvent(m->s_in, m->ev_set_free[set], 0));
+    PRK_CUDA(cudaMemcpyAsync(d_pose, h_pose, (size_t)B * 72 * 4, cudaMemcpyHostToDevice, m->s_in));
+    if (h_betas) PRK_CUDA(cudaMemcpyAsync(d_betas, h_betas, (size_t)B * NBETA * 4, cudaMemcpyHostToDevice, m->s_in));
+    if (h_trans) PRK_CUDA(cudaMemcpyAsync(d_trans, h_trans, (size_t)B * 3 * 4, cudaMemcpyHostToDevice, m->s_in));
+    PRK_CUDA(cudaMemcpyAsync(d_info, h_info, (size_t)n_tracks * sizeof(prk_addinfo), cudaMemcpyHostToDevice, m->s_in));
+    if (h_track) PRK_CUDA(cudaMemcpyAsync(d_track, h_track, (size_t)B * 4, cudaMemcpyHostToDevice, m->s_in));
+    PRK_CUDA(cudaEventRecord(m->ev_h2d, m->s_in));
+
+    // ---- scoring on its own stream, pose chain + vertex kernels on the caller's stream
+    cudaStream_t ss = m->s_score;
+    PRK_CUDA(cudaStreamWaitEvent(ss, m->ev_h2d, 0));
+    PRK_CUDA(cudaStreamWaitEvent(ss, m->ev_out, 0));        // d_scores of the previous call has been copied out
+    {
+        StageScope sc(3, ss);
+        PRK_CUDA(launch_score_pose(d_pose, PRK_DTYPE_F32, d_info, d_track, B, PRK_SCORE_REBA | PRK_SCORE_RULA, d_scores,
+                                   nullptr, 0, nullptr, 0, ss));
+    }
+    PRK_CUDA(cudaEventRecord(m->ev_score, ss));
+    PRK_CUDA(cudaStreamWaitEvent(s, m->ev_h2d, 0));
+    PRK_CUDA(cudaStreamWaitEvent(s, m->ev_out, 0));         // d_joints of the previous call has been copied out
+    int rc = forward_impl(m, d_pose, d_betas, d_trans, center_idx, B, d_verts, d_joints, w + h.inner, ws_bytes - h.inner, s,
+                          m->ev_joints);
     if (rc != PRK_OK) return rc;
-    if (h_joints) PRK_CUDA(cudaMemcpyAsync(h_joints, d_joints, (size_t)B * 72 * 4, cudaMemcpyDeviceToHost, s));
-    PRK_CUDA(cudaMemcpyAsync(h_scores, d_scores, (size_t)B * sizeof(prk_score_rec), cudaMemcpyDeviceToHost, s));
+
+    // ---- copy-out stream: joints and scores leave under the vertex kernel of this call
+    PRK_CUDA(cudaStreamWaitEvent(m->s_out, m->ev_joints, 0));
+    PRK_CUDA(cudaStreamWaitEvent(m->s_out, m->ev_score, 0));
+    if (h_joints) PRK_CUDA(cudaMemcpyAsync(h_joints, d_joints, (size_t)B * 72 * 4, cudaMemcpyDeviceToHost, m->s_out));
+    PRK_CUDA(cudaMemcpyAsync(h_scores, d_scores, (size_t)B * sizeof(prk_score_rec), cudaMemcpyDeviceToHost, m->s_out));
+    PRK_CUDA(cudaEventRecord(m->ev_out, m->s_out));
+    // completion stays ordered on the caller's stream: it joins the copy-out and the scoring stream
+    PRK_CUDA(cudaStreamWaitEvent(s, m->ev_out, 0));
+    PRK_CUDA(cudaEventRecord(m->ev_set_free[set], s));
     return PRK_OK;
 }
 

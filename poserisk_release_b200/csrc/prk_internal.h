@@ -88,6 +88,10 @@ struct prk_model {
     cudaStream_t s_gemm = nullptr, s_score = nullptr;
     cudaEvent_t ev_pose = nullptr, ev_in = nullptr, ev_score = nullptr;
     cudaEvent_t ev_gemm[2] = {nullptr, nullptr}, ev_skin[2] = {nullptr, nullptr};
+    // host-buffer pipeline (prk_pipeline_host): copy-in / copy-out streams beside the kernels, two input sets
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_h2d = nullptr, ev_joints = nullptr, ev_out = nullptr, ev_set_free[2] = {nullptr, nullptr};
+    uint64_t host_calls = 0;
 };
 
 namespace prk {

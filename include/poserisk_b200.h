@@ -188,9 +188,9 @@ int prk_score_histogram(const prk_score_rec* d_scores, int64_t B, uint32_t which
                         unsigned long long* d_hist, void* stream);
 
 /* ---- verification hooks (used by tests only; not on the product path) ---- */
-/* blend-shape stage alone: v_posed [B][prk_vposed_pitch()] float32 into d_vposed, either
- * through the tcgen05 GEMM (use_simt = 0) or a plain FFMA loop over the same bf16
- * operands (use_simt = 1). */
+/* blend-shape stage alone: v_posed [B][prk_vposed_pitch()] float32 into d_vposed (room for
+ * B rows), either through the product kernel run with identity skinning transforms
+ * (use_simt = 0) or a plain FFMA loop over the same bf16 operands (use_simt = 1). */
 int prk_debug_blend(prk_model* model, const float* d_pose, const float* d_betas, int64_t B,
                     float* d_vposed, int use_simt, void* d_workspace, size_t workspace_bytes,
                     void* stream);

@@ -10,7 +10,7 @@ CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(CSRC, 'libposerisk_b200.so')
 
 import os as _os
-NVCC_FLAGS = (['-DPRK_SKIN_DEBUG'] if _os.environ.get('PRK_SKIN_DEBUG') else []) + (['-DPRK_FUSED_DEBUG'] if _os.environ.get('PRK_FUSED_DEBUG') else []) + (['-DPRK_FUSED_SPIN'] if _os.environ.get('PRK_FUSED_SPIN') else []) + ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
+NVCC_FLAGS = (['-DPRK_FUSED_DEBUG'] if _os.environ.get('PRK_FUSED_DEBUG') else []) + (['-DPRK_FUSED_SPIN'] if _os.environ.get('PRK_FUSED_SPIN') else []) + ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-shared', '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden',
               '--expt-relaxed-constexpr']
 

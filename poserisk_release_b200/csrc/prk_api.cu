@@ -132,74 +132,41 @@ static const int kSmplDfs[NJ] = {0, 1, 4, 7, 10, 2, 5, 8, 11, 3, 6, 9, 12, 15, 1
 static int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
 // ---- workspace layout ---------------------------------------------------------
-constexpr int64_t kMaxSuper = 16384;   // frames per pose-chain launch (A' + Askin scratch)
-static int overlap_enabled() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("PRK_OVERLAP"); v = (e && e[0] == '0') ? 0 : 1; }
-    return v;
-}
-static int skin_mma_enabled() {      // PRK_SKIN=simt selects the shared-memory SIMT skinning kernel
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("PRK_SKIN"); v = (e && e[0] == 's') ? 0 : 1; }
-    return v;
-}
-static int fused_enabled() {         // PRK_PATH=split selects the separate GEMM -> v_posed -> skinning kernels
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("PRK_PATH"); v = (e && e[0] == 's') ? 0 : 1; }
-    return v;
-}
-static int64_t chunk_frames() {        // frames per GEMM+skin step (pipeline granularity)
-    static int64_t v = 0;
-    if (v == 0) {
-        v = 4096;
-        if (const char* e = getenv("PRK_CHUNK_FRAMES")) { long t = atol(e); if (t >= 128) v = t; }
-        v = round_up(v, GEMM_BM);
-    }
-    return v;
-}
+constexpr int64_t kMaxSuper = 65536;   // frames per pose-chain + fused-kernel launch pair (A' + A_j scratch: 2.2 KB per frame)
 
 struct Layout {
-    int64_t S = 0, C = 0;   // super-chunk and chunk frames (multiples of 128)
-    size_t off_flags = 0, off_arows = 0, off_askin = 0, off_off = 0, off_vposed = 0, vposed_stride = 0, total = 0;
+    int64_t S = 0;   // frames per launch pair (multiple of 128)
+    size_t off_flags = 0, off_arows = 0, off_askin = 0, off_off = 0, total = 0;
 };
 static size_t align_up(size_t x) { return (x + 1023) & ~(size_t)1023; }
 
-static Layout make_layout(int64_t S, int64_t C, bool mesh) {
+static Layout make_layout(int64_t S, bool mesh) {
     Layout L;
-    L.S = S; L.C = C;
+    L.S = S;
     size_t o = 0;
     L.off_flags = o; o += 1024;
-    if (mesh && fused_enabled()) {                        // K12: no v_posed scratch at all
+    if (mesh) {   // v_posed never exists in memory: only the per-frame operands of the fused kernel
         L.off_arows = o;  o += align_up((size_t)S * FUSED_K * 2);
         L.off_askin = o;  o += align_up((size_t)S * NJ * 12 * 4);
         L.off_off = o;    o += align_up((size_t)S * 3 * 4);
-    } else if (mesh) {
-        L.off_arows = o;  o += align_up((size_t)S * GEMM_K * 2);
-        L.off_askin = o;  o += align_up((size_t)S * NJ * 12 * 4);
-        L.off_off = o;    o += align_up((size_t)S * 3 * 4);
-        L.vposed_stride = align_up((size_t)C * VPOSED_PITCH * 4);
-        L.off_vposed = o; o += 2 * L.vposed_stride;       // double buffered: GEMM(c+1) overlaps skinning(c)
     }
     L.total = o;
     return L;
 }
 static Layout want_layout(int64_t B, bool mesh) {
-    int64_t S = round_up(B < 1 ? 1 : B, GEMM_BM);
+    int64_t S = round_up(B < 1 ? 1 : B, FUSED_BM);
     if (S > kMaxSuper) S = kMaxSuper;
-    int64_t C = chunk_frames();
-    if (C > S) C = S;
-    return make_layout(S, C, mesh);
+    return make_layout(S, mesh);
 }
-// largest layout that fits in `bytes`: shrink the super-chunk first, then the chunk
+// largest layout that fits in `bytes`
 static bool fit_layout(int64_t B, bool mesh, size_t bytes, Layout& L) {
     L = want_layout(B, mesh);
-    int64_t S = L.S, C = L.C;
-    while (make_layout(S, C, mesh).total > bytes) {
-        if (S > C) { S = round_up(S / 2, GEMM_BM); if (S < C) S = C; }
-        else if (C > GEMM_BM) { C = round_up(C / 2, GEMM_BM); S = C; }
-        else return false;
+    int64_t S = L.S;
+    while (make_layout(S, mesh).total > bytes) {
+        if (S <= FUSED_BM) return false;
+        S = round_up(S / 2, FUSED_BM);
     }
-    L = make_layout(S, C, mesh);
+    L = make_layout(S, mesh);
     return true;
 }
 
@@ -234,58 +201,17 @@ static int forward_impl(Model* m, const float* d_pose, const float* d_betas, con
         {
             StageScope sc(0, s);
             PRK_CUDA(launch_pose_chain(*m, d_pose + s0 * 72, d_betas ? d_betas + s0 * NBETA : nullptr,
-                                       d_trans ? d_trans + s0 * 3 : nullptr, d_flags, center_idx, ns, mesh,
-                                       mesh && fused_enabled(), d_arows, d_askin, d_off, d_joints + s0 * 72, s));
+                                       d_trans ? d_trans + s0 * 3 : nullptr, d_flags, center_idx, ns, mesh, d_arows,
+                                       d_askin, d_off, d_joints + s0 * 72, s));
         }
         if (ev_joints && s0 + S >= B) PRK_CUDA(cudaEventRecord(ev_joints, s));
         if (!mesh) continue;
-        if (fused_enabled()) {
-            const int64_t rows_pad = round_up(ns, FUSED_BM);
-            CUtensorMap tmA;
-            int rc = encode_tmap_2d_bf16(&tmA, d_arows, (uint64_t)rows_pad, FUSED_K, FUSED_BM, 64);
-            if (rc != PRK_OK) return rc;
-            StageScope sc(1, s);
-            PRK_CUDA(launch_fused(*m, tmA, rows_pad, d_askin, d_off, ns, d_verts + (size_t)s0 * NVC, s));
-            continue;
-        }
-        // Two-stream pipeline: the tensor-bound blend GEMM of chunk c+1 (on the model's own
-        // stream) runs under the LSU/HBM-bound skinning of chunk c (on the caller's stream);
-        // v_posed is double buffered.  PRK_OVERLAP=0 keeps everything on the caller's stream.
-        const bool overlap = overlap_enabled() && m->s_gemm != nullptr;
-        cudaStream_t sg = overlap ? m->s_gemm : s;
-        if (overlap) {
-            PRK_CUDA(cudaEventRecord(m->ev_pose, s));
-            PRK_CUDA(cudaStreamWaitEvent(sg, m->ev_pose, 0));
-        }
-        int64_t ci = 0;
-        for (int64_t c0 = 0; c0 < ns; c0 += L.C, ++ci) {
-            const int64_t nc = (ns - c0) < L.C ? (ns - c0) : L.C;
-            const int64_t rows_pad = round_up(nc, GEMM_BM);
-            const int buf = (int)(ci & 1);
-            float* vp = reinterpret_cast<float*>(w + L.off_vposed + (size_t)buf * L.vposed_stride);
-            CUtensorMap tmA;
-            int rc = encode_tmap_2d_bf16(&tmA, d_arows + c0 * GEMM_K, (uint64_t)rows_pad, GEMM_K, GEMM_BM, GEMM_BK);
-            if (rc != PRK_OK) return rc;
-            if (overlap && ci >= 2) PRK_CUDA(cudaStreamWaitEvent(sg, m->ev_skin[buf], 0));   // buffer free again
-            {
-                StageScope sc(1, sg);
-                PRK_CUDA(launch_blend_gemm(*m, tmA, rows_pad, vp, sg));
-            }
-            if (overlap) {
-                PRK_CUDA(cudaEventRecord(m->ev_gemm[buf], sg));
-                PRK_CUDA(cudaStreamWaitEvent(s, m->ev_gemm[buf], 0));
-            }
-            {
-                StageScope sc(2, s);
-                if (skin_mma_enabled())
-                    PRK_CUDA(launch_skin_mma(*m, vp, rows_pad, d_askin + c0 * NJ * 12, d_off + c0 * 3, nc,
-                                             d_verts + (size_t)(s0 + c0) * NVC, s));
-                else
-                    PRK_CUDA(launch_skin(*m, vp, d_askin + c0 * NJ * 12, d_off + c0 * 3, nc,
-                                         d_verts + (size_t)(s0 + c0) * NVC, s));
-            }
-            if (overlap) PRK_CUDA(cudaEventRecord(m->ev_skin[buf], s));
-        }
+        const int64_t rows_pad = round_up(ns, FUSED_BM);
+        CUtensorMap tmA;
+        int rc = encode_tmap_2d_bf16(&tmA, d_arows, (uint64_t)rows_pad, FUSED_K, FUSED_BM, 64);
+        if (rc != PRK_OK) return rc;
+        StageScope sc(1, s);
+        PRK_CUDA(launch_fused(*m, tmA, rows_pad, d_askin, d_off, ns, d_verts + (size_t)s0 * NVC, s));
     }
     return PRK_OK;
 }
@@ -311,7 +237,7 @@ const char* prk_strerror(int status) {
 }
 const char* prk_last_error_detail(void) { return t_detail; }
 uint64_t prk_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
-int64_t prk_vposed_pitch(void) { return VPOSED_PITCH; }
+int64_t prk_vposed_pitch(void) { return NVC; }
 
 int prk_model_create(prk_model** out, int device, const float* vt, const float* sd, const float* pd, const float* jr,
                      const float* wt, const int32_t* parents, const float* betas) {
@@ -357,30 +283,6 @@ int prk_model_create(prk_model** out, int device, const float* vt, const float* 
             m->pc.J_template[j * 3 + c] = (float)a;
             for (int k = 0; k < NBETA; ++k) m->pc.Jdirs[(j * 3 + c) * NBETA + k] = (float)d[k];
         }
-
-    // split-precision blend operand B' [GEMM_N][GEMM_K]
-    std::vector<uint16_t> Bm((size_t)GEMM_N * GEMM_K, 0);
-    for (int n = 0; n < NVC; ++n) {
-        uint16_t* row = &Bm[(size_t)n * GEMM_K];
-        for (int pos = 1; pos < NJ; ++pos) {
-            const int j = std_tree ? kSmplDfs[pos] : pos;
-            const int base = 27 * (pos - 1);
-            for (int e = 0; e < 9; ++e) {
-                const float v = pd[(size_t)n * NPOSE + (j - 1) * 9 + e];
-                const uint16_t hi = f2bf(v), lo = f2bf(v - bf2f(hi));
-                row[base + e] = hi; row[base + 9 + e] = lo; row[base + 18 + e] = hi;
-            }
-        }
-        for (int b = 0; b < NBETA; ++b) {
-            uint16_t h, mm, l;
-            split3(sd[(size_t)n * NBETA + b], h, mm, l);
-            uint16_t* c = row + COL_BETA0 + 6 * b;
-            c[0] = h; c[1] = mm; c[2] = h; c[3] = l; c[4] = mm; c[5] = h;
-        }
-        uint16_t h, mm, l;
-        split3(vt[n], h, mm, l);
-        row[COL_ONES] = h; row[COL_ONES + 1] = mm; row[COL_ONES + 2] = l;
-    }
 
     // K12 operand (prk_internal.h "K12 operand layout"): every hi/lo part stored once
     std::vector<uint16_t> B2((size_t)GEMM_N * FUSED_K, 0);
@@ -444,16 +346,10 @@ int prk_model_create(prk_model** out, int device, const float* vt, const float* 
 
     cudaError_t e;
 #define PRK_M(expr) do { e = (expr); if (e != cudaSuccess) { prk_model_destroy(m); return cuda_fail(e, #expr); } } while (0)
-    PRK_M(cudaMalloc(&m->d_Bmat, Bm.size() * 2));
-    PRK_M(cudaMemcpy(m->d_Bmat, Bm.data(), Bm.size() * 2, cudaMemcpyHostToDevice));
     PRK_M(cudaMalloc(&m->d_B2, B2.size() * 2));
     PRK_M(cudaMemcpy(m->d_B2, B2.data(), B2.size() * 2, cudaMemcpyHostToDevice));
     PRK_M(cudaMalloc(&m->d_wpack, wp.size()));
     PRK_M(cudaMemcpy(m->d_wpack, wp.data(), wp.size(), cudaMemcpyHostToDevice));
-    PRK_M(cudaMalloc(&m->d_wval, wv.size() * sizeof(float4)));
-    PRK_M(cudaMemcpy(m->d_wval, wv.data(), wv.size() * sizeof(float4), cudaMemcpyHostToDevice));
-    PRK_M(cudaMalloc(&m->d_widx, wi.size() * 4));
-    PRK_M(cudaMemcpy(m->d_widx, wi.data(), wi.size() * 4, cudaMemcpyHostToDevice));
     {
         std::vector<float> jc(72 + 720 + NBETA);
         memcpy(jc.data(), m->pc.J_template, 72 * 4);
@@ -462,25 +358,17 @@ int prk_model_create(prk_model** out, int device, const float* vt, const float* 
         PRK_M(cudaMalloc(&m->d_Jc, jc.size() * 4));
         PRK_M(cudaMemcpy(m->d_Jc, jc.data(), jc.size() * 4, cudaMemcpyHostToDevice));
     }
-    PRK_M(cudaStreamCreateWithFlags(&m->s_gemm, cudaStreamNonBlocking));
     PRK_M(cudaStreamCreateWithFlags(&m->s_score, cudaStreamNonBlocking));
-    PRK_M(cudaEventCreateWithFlags(&m->ev_pose, cudaEventDisableTiming));
     PRK_M(cudaEventCreateWithFlags(&m->ev_in, cudaEventDisableTiming));
     PRK_M(cudaEventCreateWithFlags(&m->ev_score, cudaEventDisableTiming));
-    for (int i = 0; i < 2; ++i) {
-        PRK_M(cudaEventCreateWithFlags(&m->ev_gemm[i], cudaEventDisableTiming));
-        PRK_M(cudaEventCreateWithFlags(&m->ev_skin[i], cudaEventDisableTiming));
-        PRK_M(cudaEventCreateWithFlags(&m->ev_set_free[i], cudaEventDisableTiming));
-    }
+    for (int i = 0; i < 2; ++i) PRK_M(cudaEventCreateWithFlags(&m->ev_set_free[i], cudaEventDisableTiming));
     PRK_M(cudaStreamCreateWithFlags(&m->s_in, cudaStreamNonBlocking));
     PRK_M(cudaStreamCreateWithFlags(&m->s_out, cudaStreamNonBlocking));
     PRK_M(cudaEventCreateWithFlags(&m->ev_h2d, cudaEventDisableTiming));
     PRK_M(cudaEventCreateWithFlags(&m->ev_joints, cudaEventDisableTiming));
     PRK_M(cudaEventCreateWithFlags(&m->ev_out, cudaEventDisableTiming));
 #undef PRK_M
-    int rc = encode_tmap_2d_bf16(&m->tmap_B, m->d_Bmat, GEMM_N, GEMM_K, GEMM_BN, GEMM_BK);
-    if (rc != PRK_OK) { prk_model_destroy(m); return rc; }
-    rc = encode_tmap_2d_bf16(&m->tmap_B2, m->d_B2, GEMM_N, FUSED_K, FUSED_BN, 64);
+    int rc = encode_tmap_2d_bf16(&m->tmap_B2, m->d_B2, GEMM_N, FUSED_K, FUSED_BN, 64);
     if (rc != PRK_OK) { prk_model_destroy(m); return rc; }
     *out = m;
     return PRK_OK;
@@ -491,13 +379,10 @@ void prk_model_destroy(prk_model* model) {
     if (!m) return;
     if (m->device >= 0) cudaSetDevice(m->device);
     cudaFree(m->d_B2); cudaFree(m->d_wpack);
-    cudaFree(m->d_Bmat); cudaFree(m->d_wval); cudaFree(m->d_widx); cudaFree(m->d_Jc);
-    if (m->s_gemm) { cudaStreamSynchronize(m->s_gemm); cudaStreamDestroy(m->s_gemm); }
+    cudaFree(m->d_Jc);
     if (m->s_score) { cudaStreamSynchronize(m->s_score); cudaStreamDestroy(m->s_score); }
-    if (m->ev_pose) cudaEventDestroy(m->ev_pose);
     if (m->ev_in) cudaEventDestroy(m->ev_in);
     if (m->ev_score) cudaEventDestroy(m->ev_score);
-    for (int i = 0; i < 2; ++i) { if (m->ev_gemm[i]) cudaEventDestroy(m->ev_gemm[i]); if (m->ev_skin[i]) cudaEventDestroy(m->ev_skin[i]); }
     if (m->s_in) { cudaStreamSynchronize(m->s_in); cudaStreamDestroy(m->s_in); }
     if (m->s_out) { cudaStreamSynchronize(m->s_out); cudaStreamDestroy(m->s_out); }
     if (m->ev_h2d) cudaEventDestroy(m->ev_h2d);
@@ -581,7 +466,7 @@ int prk_pipeline(prk_model* model, const float* d_pose, const float* d_betas, co
     PRK_CUDA(cudaSetDevice(m->device));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     // scoring only reads the pose: it runs on the model's scoring stream, beside the mesh path
-    const bool overlap = overlap_enabled() && m->s_score != nullptr && B > 0;
+    const bool overlap = m->s_score != nullptr && B > 0;
     cudaStream_t ss = overlap ? m->s_score : s;
     if (overlap) {
         PRK_CUDA(cudaEventRecord(m->ev_in, s));
@@ -730,10 +615,10 @@ int prk_debug_blend(prk_model* model, const float* d_pose, const float* d_betas,
     if (!m || B <= 0 || !d_pose || !d_vposed || !ws) { set_detail("prk_debug_blend", "invalid argument"); return PRK_ERR_INVALID_ARG; }
     PRK_CUDA(cudaSetDevice(m->device));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const int64_t rows_pad = round_up(B, GEMM_BM);
-    // scratch: A' rows, Askin, off, joints (the caller's d_vposed must hold rows_pad rows)
+    const int64_t rows_pad = round_up(B, FUSED_BM);
+    // scratch: A' rows, A_j tiles, off, joints
     size_t o = 0;
-    const size_t o_arows = o; o += align_up((size_t)rows_pad * GEMM_K * 2);
+    const size_t o_arows = o; o += align_up((size_t)rows_pad * FUSED_K * 2);
     const size_t o_askin = o; o += align_up((size_t)rows_pad * NJ * 12 * 4);
     const size_t o_off = o;   o += align_up((size_t)rows_pad * 3 * 4);
     const size_t o_j = o;     o += align_up((size_t)rows_pad * 72 * 4);
@@ -741,19 +626,22 @@ int prk_debug_blend(prk_model* model, const float* d_pose, const float* d_betas,
     if (o > ws_bytes || (reinterpret_cast<uintptr_t>(ws) & 1023)) { set_detail("prk_debug_blend", "workspace too small or misaligned"); return PRK_ERR_WORKSPACE; }
     uint8_t* w = static_cast<uint8_t*>(ws);
     uint16_t* d_arows = reinterpret_cast<uint16_t*>(w + o_arows);
+    float* d_askin = reinterpret_cast<float*>(w + o_askin);
+    float* d_off = reinterpret_cast<float*>(w + o_off);
     BatchFlags* d_flags = reinterpret_cast<BatchFlags*>(w + o_flags);
-    PRK_CUDA(cudaMemsetAsync(d_arows, 0, (size_t)rows_pad * GEMM_K * 2, s));
+    PRK_CUDA(cudaMemsetAsync(d_arows, 0, (size_t)rows_pad * FUSED_K * 2, s));
     if (pose_chain_needs_flags(*m, d_betas, nullptr, -1)) PRK_CUDA(launch_batch_flags(d_betas, nullptr, B, d_flags, s));
-    PRK_CUDA(launch_pose_chain(*m, d_pose, d_betas, nullptr, d_flags, -1, B, true, false, d_arows,
-                               reinterpret_cast<float*>(w + o_askin), reinterpret_cast<float*>(w + o_off),
+    PRK_CUDA(launch_pose_chain(*m, d_pose, d_betas, nullptr, d_flags, -1, B, true, d_arows, d_askin, d_off,
                                reinterpret_cast<float*>(w + o_j), s));
     if (use_simt) {
-        PRK_CUDA(launch_blend_simt(*m, d_arows, rows_pad, d_vposed, s));
+        PRK_CUDA(launch_blend_simt(*m, d_arows, B, d_vposed, s));
     } else {
+        // the product kernel with identity skinning transforms and no offset: vertices = v_posed
+        PRK_CUDA(launch_identity_askin(d_askin, d_off, rows_pad, s));
         CUtensorMap tmA;
-        int rc = encode_tmap_2d_bf16(&tmA, d_arows, (uint64_t)rows_pad, GEMM_K, GEMM_BM, GEMM_BK);
+        int rc = encode_tmap_2d_bf16(&tmA, d_arows, (uint64_t)rows_pad, FUSED_K, FUSED_BM, 64);
         if (rc != PRK_OK) return rc;
-        PRK_CUDA(launch_blend_gemm(*m, tmA, rows_pad, d_vposed, s));
+        PRK_CUDA(launch_fused(*m, tmA, rows_pad, d_askin, d_off, B, d_vposed, s));
     }
     return PRK_OK;
 }

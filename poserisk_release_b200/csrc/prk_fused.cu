@@ -551,7 +551,59 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
     }
 }
 
+// ---- verification only (prk_debug_blend) ------------------------------------------------
+// The same bf16 operands and the same 45 k-step pairs as the tensor-core path, plain FFMA.
+__global__ void __launch_bounds__(256)
+blend_simt_kernel(const uint16_t* __restrict__ Arows, const uint16_t* __restrict__ B2, int64_t rows,
+                  float* __restrict__ vposed) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;   // vertex coordinate
+    const int64_t f = blockIdx.y;
+    if (n >= NVC || f >= rows) return;
+    const uint16_t* a = Arows + f * FUSED_K;
+    const uint16_t* b = B2 + (size_t)n * FUSED_K;
+    auto bf = [](uint16_t v) { return __uint_as_float((uint32_t)v << 16); };
+    auto step = [&](int sa, int sb, float acc) {
+        for (int k = 0; k < 16; ++k) acc = fmaf(bf(a[sa * 16 + k]), bf(b[sb * 16 + k]), acc);
+        return acc;
+    };
+    float acc = 0.f;
+    for (int i = 0; i < FUSED_POSE_STEPS; ++i) {
+        acc = step(i, i, acc);                                   // hi x hi
+        acc = step(FUSED_POSE_STEPS + i, i, acc);                // lo x hi
+        acc = step(i, FUSED_POSE_STEPS + i, acc);                // hi x lo
+    }
+    for (int q = 0; q < 3; ++q)
+        for (int p = 0; p + q < 3; ++p) acc = step(2 * FUSED_POSE_STEPS + p, 2 * FUSED_POSE_STEPS + q, acc);
+    vposed[f * NVC + n] = acc;
+}
+
+// A_j = identity for every joint (columns R00 = 0, R11 = 3, R22 = 10 of each group of 12), off = 0
+__global__ void __launch_bounds__(256)
+identity_askin_kernel(float* __restrict__ AskinT, float* __restrict__ off, int64_t rows_pad) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < rows_pad * FUSED_ASKIN_COLS) {
+        const int col = (int)((i >> 5) % FUSED_ASKIN_COLS) % 12;
+        AskinT[i] = (col == 0 || col == 3 || col == 10) ? 1.0f : 0.0f;
+    }
+    if (i < rows_pad * 3) off[i] = 0.0f;
+}
+
 }  // namespace
+
+cudaError_t launch_blend_simt(const Model& m, const uint16_t* d_Arows, int64_t rows, float* d_vposed, cudaStream_t s) {
+    if (rows == 0) return cudaSuccess;
+    dim3 grid((NVC + 255) / 256, (unsigned)rows);
+    blend_simt_kernel<<<grid, 256, 0, s>>>(d_Arows, m.d_B2, rows, d_vposed);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_identity_askin(float* d_AskinT, float* d_off, int64_t rows_pad, cudaStream_t s) {
+    const int64_t n = rows_pad * FUSED_ASKIN_COLS;
+    identity_askin_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_AskinT, d_off, rows_pad);
+    count_launch();
+    return cudaGetLastError();
+}
 
 #ifdef PRK_FUSED_DEBUG
 extern "C" __attribute__((visibility("default"))) int prk_fused_debug_read(unsigned long long* out, int reset) {

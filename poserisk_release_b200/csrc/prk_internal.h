@@ -15,23 +15,7 @@ constexpr int NBETA = PRK_NUM_BETAS;    // 10
 constexpr int NPOSE = PRK_NUM_POSE_FEATS;  // 207
 constexpr int NVC = NV * 3;             // 20670 vertex coordinates
 
-// ---- blend GEMM geometry (DESIGN.md "K1") ---------------------------------
-// D[frame][vc] = sum_k A'[frame][k] * B'[vc][k], bf16 x bf16 -> fp32 (tcgen05 kind::f16).
-// fp32-class accuracy comes from split precision along K:
-//   pose feature p = 9*jj+e (jj = joint-1):  cols 27*jj + {e, 9+e, 18+e} = A:{hi,hi,lo} x B:{hi,lo,hi}
-//   beta b:  cols 621+6b+{0..5} = A:{h,h,m,h,m,l} x B:{h,m,h,l,m,h}   (3-way split, 6 products)
-//   template: cols 681..683 = A:{1,1,1} x B:{h,m,l}                   (exact fp32 v_template)
-//   cols 684..703 zero.
-constexpr int GEMM_K = 704;             // 11 k-blocks of 64 bf16 (128-byte swizzle rows)
-constexpr int GEMM_BK = 64;
-constexpr int GEMM_KBLOCKS = GEMM_K / GEMM_BK;
-constexpr int GEMM_BM = 128;            // frames per tile (TMEM lanes)
-constexpr int GEMM_BN = 256;            // vertex coordinates per tile (TMEM columns)
-constexpr int GEMM_N = 20736;           // 20670 padded to 81 * 256
-constexpr int GEMM_NBLOCKS = GEMM_N / GEMM_BN;
-constexpr int COL_BETA0 = 621;
-constexpr int COL_ONES = 681;
-constexpr int VPOSED_PITCH = GEMM_N;    // floats per frame row of the v_posed scratch
+constexpr int GEMM_N = 20736;           // 20670 vertex coordinates padded to 216 tiles of 96
 
 // ---- fused blend + skinning geometry (DESIGN.md "K12", prk_fused.cu) ---------
 // K12 operand layout: the hi/lo parts of every factor are stored ONCE, in k-steps of 16 bf16:
@@ -41,7 +25,8 @@ constexpr int VPOSED_PITCH = GEMM_N;    // floats per frame row of the v_posed s
 //                 B': shapedirs split q (10 columns) + v_template split q in column 10
 //   columns 464..511 pad the row to 8 chunks of 64 (never multiplied).
 // The MMA issuer pairs  A'hi x B'hi,  A'lo x B'hi,  A'hi x B'lo  and  beta_p x shape_q for p+q <= 2
-// (45 MMAs of K=16 per tile) -- the same products as the 704-column layout of K1.
+// (45 MMAs of K=16 per tile): pose features as hi*hi + lo*hi + hi*lo, betas / shapedirs as 3-way
+// splits (6 products), v_template as an exact 3-way split.
 constexpr int FUSED_K = 512;
 constexpr int FUSED_KCHUNKS = FUSED_K / 64;
 constexpr int FUSED_POSE_STEPS = 13;
@@ -76,18 +61,13 @@ struct prk_model {
     int max_weights = 0;
     prk::PoseConsts pc;                 // host copy, passed by value to the pose kernel
     // device buffers
-    uint16_t* d_Bmat = nullptr;    // [GEMM_N][GEMM_K] bf16 bits, K-major
-    float4* d_wval = nullptr;      // [nnz_groups][NV] weights, 4 per group
-    uint32_t* d_widx = nullptr;
-    float* d_Jc = nullptr;         // J_template[72] | Jdirs[720] | model_betas[10] (lane-per-joint kernel)    // [nnz_groups][NV] joint ids, 4 x u8 per group
-    CUtensorMap tmap_B;            // [GEMM_N][GEMM_K], box 64 x 256, 128B swizzle
+    float* d_Jc = nullptr;         // J_template[72] | Jdirs[720] | model_betas[10] (lane-per-joint pose kernel)
     uint16_t* d_B2 = nullptr;      // [GEMM_N][FUSED_K] bf16 bits, K12 operand layout
     uint8_t* d_wpack = nullptr;    // [FUSED_NT][nnz_groups][FUSED_WGROUP_BYTES] per-tile skinning weights
     CUtensorMap tmap_B2;           // [GEMM_N][FUSED_K], box 64 x 96, 128B swizzle
-    // internal streams/events of the two-stream pipeline (GEMM under skinning, scoring aside)
-    cudaStream_t s_gemm = nullptr, s_score = nullptr;
-    cudaEvent_t ev_pose = nullptr, ev_in = nullptr, ev_score = nullptr;
-    cudaEvent_t ev_gemm[2] = {nullptr, nullptr}, ev_skin[2] = {nullptr, nullptr};
+    // scoring only reads the pose: it runs on its own stream beside the mesh path
+    cudaStream_t s_score = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_score = nullptr;
     // host-buffer pipeline (prk_pipeline_host): copy-in / copy-out streams beside the kernels, two input sets
     cudaStream_t s_in = nullptr, s_out = nullptr;
     cudaEvent_t ev_h2d = nullptr, ev_joints = nullptr, ev_out = nullptr, ev_set_free[2] = {nullptr, nullptr};
@@ -107,31 +87,21 @@ struct BatchFlags {
 cudaError_t launch_batch_flags(const float* d_betas, const float* d_trans, int64_t B,
                                BatchFlags* d_flags, cudaStream_t s);
 
-// K2a: Rodrigues + kinematic chain (+ split-precision GEMM operand rows when full_mesh)
+// K2a: Rodrigues + kinematic chain (+ the fused kernel's per-frame operands when full_mesh)
 cudaError_t launch_pose_chain(const Model& m, const float* d_pose, const float* d_betas,
                               const float* d_trans, const BatchFlags* d_flags, int center_idx,
-                              int64_t B, bool full_mesh, bool fused_layout, uint16_t* d_Arows, float* d_Askin,
+                              int64_t B, bool full_mesh, uint16_t* d_Arows, float* d_Askin,
                               float* d_off, float* d_joints, cudaStream_t s);
 
 bool pose_chain_needs_flags(const Model& m, const float* d_betas, const float* d_trans, int center_idx);
-
-// K1: tcgen05 blend GEMM  (rows_pad = multiple of 128)
-cudaError_t launch_blend_gemm(const Model& m, const CUtensorMap& tmap_A, int64_t rows_pad,
-                              float* d_vposed, cudaStream_t s);
-cudaError_t launch_blend_simt(const Model& m, const uint16_t* d_Arows, int64_t rows,
-                              float* d_vposed, cudaStream_t s);
 
 // K12: fused blend GEMM + skinning (prk_fused.cu); A' rows / AskinT in the K12 layouts, rows_pad = multiple of 128
 cudaError_t launch_fused(const Model& m, const CUtensorMap& tmap_A, int64_t rows_pad, const float* d_AskinT,
                          const float* d_off, int64_t B, float* d_verts, cudaStream_t s);
 
-// K2b: linear-blend skinning
-cudaError_t launch_skin(const Model& m, const float* d_vposed, const float* d_Askin,
-                        const float* d_off, int64_t B, float* d_verts, cudaStream_t s);
-
-// K2b on tensor cores (prk_skin_mma.cu); d_vposed must hold rows_pad >= round_up(B,128) rows
-cudaError_t launch_skin_mma(const Model& m, const float* d_vposed, int64_t rows_pad, const float* d_Askin,
-                            const float* d_off, int64_t B, float* d_verts, cudaStream_t s);
+// verification hooks of prk_debug_blend: plain FFMA evaluation of the same bf16 operands, identity A_j tiles
+cudaError_t launch_blend_simt(const Model& m, const uint16_t* d_Arows, int64_t rows, float* d_vposed, cudaStream_t s);
+cudaError_t launch_identity_askin(float* d_AskinT, float* d_off, int64_t rows_pad, cudaStream_t s);
 
 // K3: Euler angles + REBA/RULA
 cudaError_t launch_score_pose(const void* d_pose, int pose_dtype, const prk_addinfo* d_info,

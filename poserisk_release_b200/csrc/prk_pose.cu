@@ -10,13 +10,15 @@
 //
 // Outputs per frame:
 //   joints [24][3]                                     (always)
-//   A' row [704] bf16: split-precision operand of the blend GEMM (K1)      (full mesh only)
-//   Askin  [24][12] fp32: rows of A_j = [R_g | t_g - R_g j_rest]            (full mesh only)
-//   off    [3]: +trans or -centre joint, applied to vertices by K2b        (full mesh only)
+//   A' row [512] bf16: split-precision operand of the fused kernel's blend GEMM, K12 layout
+//                      (prk_internal.h)                                     (full mesh only)
+//   AskinT [frame/32][288][frame%32] fp32: A_j = [R_g | t_g - R_g j_rest] in the column order
+//                      the fused kernel keeps in tensor memory              (full mesh only)
+//   off    [3]: +trans or -centre joint, applied to vertices by K12        (full mesh only)
 //
 // The chain is walked depth-first with every index a compile-time constant, so the at
 // most three live 3x4 transforms stay in registers; HBM traffic is 288 B pose (+40 betas,
-// +12 trans) in and 288 B joints (+1408 A' +1152 Askin +12 off) out per frame.
+// +12 trans) in and 288 B joints (+928 A' +1152 A_j +12 off) out per frame.
 #include "prk_internal.h"
 
 #include <cuda_bf16.h>
@@ -111,7 +113,7 @@ constexpr uint32_t MODE_FRAME_BETAS_FLAG = 2u;    // betas given, honour flags->
 constexpr uint32_t MODE_TRANS_ALWAYS = 4u;        // trans given, no centre joint configured
 constexpr uint32_t MODE_TRANS_FLAG = 8u;          // trans given and centre joint configured
 
-template <bool kStd, bool kMesh, bool kFused>
+template <bool kStd, bool kMesh>
 __global__ void __launch_bounds__(128)
 pose_chain_kernel(const __grid_constant__ PoseConsts pc, const float* __restrict__ pose,
                   const float* __restrict__ betas, const float* __restrict__ trans,
@@ -134,13 +136,13 @@ pose_chain_kernel(const __grid_constant__ PoseConsts pc, const float* __restrict
     float o0 = 0.f, o1 = 0.f, o2 = 0.f;
     if (add_trans) { o0 = trans[f * 3 + 0]; o1 = trans[f * 3 + 1]; o2 = trans[f * 3 + 2]; }
 
-    // K1 layout: one stream of 704 columns; K12 layout: a hi stream (column 0) and a lo stream (column 208)
+    // K12 operand row: a hi stream (column 0) and a lo stream (column 208)
     RowWriter rw, rw_lo;
-    rw.dst = kMesh ? reinterpret_cast<uint4*>(Arows + f * (kFused ? FUSED_K : GEMM_K)) : nullptr;
+    rw.dst = kMesh ? reinterpret_cast<uint4*>(Arows + f * FUSED_K) : nullptr;
     rw.n = 0;
     rw.buf[0] = rw.buf[1] = rw.buf[2] = rw.buf[3] = 0;
     rw_lo = rw;
-    if (kMesh && kFused) rw_lo.dst = reinterpret_cast<uint4*>(Arows + f * FUSED_K + FUSED_COL_LO);
+    if (kMesh) rw_lo.dst = reinterpret_cast<uint4*>(Arows + f * FUSED_K + FUSED_COL_LO);
 
     const float* p = pose + f * 72;
     float* jout = joints + f * 72;
@@ -164,17 +166,8 @@ pose_chain_kernel(const __grid_constant__ PoseConsts pc, const float* __restrict
                 hi[e] = bf16_bits(v);
                 lo[e] = bf16_bits(v - bf16_val(hi[e]));
             }
-            if (kFused) {
 #pragma unroll
-                for (int e = 0; e < 9; ++e) { rw.push(hi[e]); rw_lo.push(lo[e]); }
-            } else {
-#pragma unroll
-                for (int e = 0; e < 9; ++e) rw.push(hi[e]);
-#pragma unroll
-                for (int e = 0; e < 9; ++e) rw.push(hi[e]);
-#pragma unroll
-                for (int e = 0; e < 9; ++e) rw.push(lo[e]);
-            }
+            for (int e = 0; e < 9; ++e) { rw.push(hi[e]); rw_lo.push(lo[e]); }
         }
 
         // rest joint: J = J_template + Jdirs * beta
@@ -197,19 +190,13 @@ pose_chain_kernel(const __grid_constant__ PoseConsts pc, const float* __restrict
         jout[j * 3 + 2] = __fadd_rn(G[j][11], o2);
         if (j == center_idx) { c0 = G[j][3]; c1 = G[j][7]; c2 = G[j][11]; }
 
-        if (kMesh && kFused) {   // A_j = G_j - pack(G_j @ [j_rest; 0])  (smpl_layer.py:126-132), TMEM-tile layout
+        if (kMesh) {   // A_j = G_j - pack(G_j @ [j_rest; 0])  (smpl_layer.py:126-132), TMEM-tile layout
             float* dst = Askin + ((f >> 5) * FUSED_ASKIN_COLS + j * 12) * 32 + (f & 31);
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
                 dst[askin_col(r, 0) * 32] = G[j][r * 4 + 0]; dst[askin_col(r, 1) * 32] = G[j][r * 4 + 1];
                 dst[askin_col(r, 2) * 32] = G[j][r * 4 + 2]; dst[askin_col(r, 3) * 32] = skin_t(G[j], r, J[j][0], J[j][1], J[j][2]);
             }
-        } else if (kMesh) {
-            float4* dst = reinterpret_cast<float4*>(Askin + (f * NJ + j) * 12);
-#pragma unroll
-            for (int r = 0; r < 3; ++r)
-                dst[r] = make_float4(G[j][r * 4 + 0], G[j][r * 4 + 1], G[j][r * 4 + 2],
-                                     skin_t(G[j], r, J[j][0], J[j][1], J[j][2]));
         }
     }
 
@@ -222,7 +209,7 @@ pose_chain_kernel(const __grid_constant__ PoseConsts pc, const float* __restrict
         }
     }
 
-    if (kMesh && kFused) {
+    if (kMesh) {
         off[f * 3 + 0] = o0; off[f * 3 + 1] = o1; off[f * 3 + 2] = o2;
         rw.push(0); rw_lo.push(0);                   // columns 207 / 415 close the hi / lo blocks
         rw.dst = reinterpret_cast<uint4*>(Arows + f * FUSED_K + FUSED_COL_BETA);
@@ -242,20 +229,6 @@ pose_chain_kernel(const __grid_constant__ PoseConsts pc, const float* __restrict
 #pragma unroll
             for (int k = NBETA + 1; k < 16; ++k) rw.push(0);
         }
-    } else if (kMesh) {
-        off[f * 3 + 0] = o0; off[f * 3 + 1] = o1; off[f * 3 + 2] = o2;
-        // betas: 3-way split, products {h,h,m,h,m,l} x {h,m,h,l,m,h}
-#pragma unroll
-        for (int k = 0; k < NBETA; ++k) {
-            const uint16_t h = bf16_bits(beta[k]);
-            const float r1 = beta[k] - bf16_val(h);
-            const uint16_t m = bf16_bits(r1);
-            const uint16_t l = bf16_bits(r1 - bf16_val(m));
-            rw.push(h); rw.push(h); rw.push(m); rw.push(h); rw.push(m); rw.push(l);
-        }
-        rw.push(0x3F80); rw.push(0x3F80); rw.push(0x3F80);   // 1.0 x {vt_h, vt_m, vt_l}
-#pragma unroll
-        for (int k = COL_ONES + 3; k < GEMM_K; ++k) rw.push(0);
     }
 }
 
@@ -275,14 +248,14 @@ __device__ __constant__ int8_t c_dfs_pos[32] = {0, 1, 5, 9, 2, 6, 10, 3, 7, 11, 
 constexpr int kWarpsPerBlock = 8;
 constexpr int64_t kWarpVariantMaxFrames = 65536;   // above this the thread-per-frame kernel fills the GPU
 
-template <bool kMesh, bool kFused>
+template <bool kMesh>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 pose_chain_warp_kernel(const float* __restrict__ Jc /* J_template[72] | Jdirs[720] | model_betas[10] */,
                        const float* __restrict__ pose, const float* __restrict__ betas,
                        const float* __restrict__ trans, const BatchFlags* __restrict__ flags, uint32_t mode,
                        int center_idx, int64_t B, uint16_t* __restrict__ Arows, float* __restrict__ Askin,
                        float* __restrict__ off, float* __restrict__ joints) {
-    __shared__ __align__(16) uint16_t s_row[kMesh ? kWarpsPerBlock : 1][GEMM_K];
+    __shared__ __align__(16) uint16_t s_row[kMesh ? kWarpsPerBlock : 1][FUSED_K];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t f = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
     if (f >= B) return;
@@ -336,74 +309,42 @@ pose_chain_warp_kernel(const float* __restrict__ Jc /* J_template[72] | Jdirs[72
     }
     if (!kMesh) return;
 
-    if (active && kFused) {   // TMEM-tile layout [frame / 32][12 * joint + e][frame % 32]
+    if (active) {   // TMEM-tile layout [frame / 32][12 * joint + e][frame % 32]
         float* dst = Askin + ((f >> 5) * FUSED_ASKIN_COLS + j * 12) * 32 + (f & 31);
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
             dst[askin_col(r, 0) * 32] = G[r * 4 + 0]; dst[askin_col(r, 1) * 32] = G[r * 4 + 1];
             dst[askin_col(r, 2) * 32] = G[r * 4 + 2]; dst[askin_col(r, 3) * 32] = skin_t(G, r, J[0], J[1], J[2]);
         }
-    } else if (active) {
-        float4* dst = reinterpret_cast<float4*>(Askin + (f * NJ + j) * 12);
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-            dst[r] = make_float4(G[r * 4 + 0], G[r * 4 + 1], G[r * 4 + 2], skin_t(G, r, J[0], J[1], J[2]));
     }
     if (lane == 0) { off[f * 3 + 0] = o0; off[f * 3 + 1] = o1; off[f * 3 + 2] = o2; }
 
     // A' row assembled in shared memory, then written with 16-byte stores
     uint16_t* row = s_row[warp];
-    if (kFused) {
-        if (active && j > 0) {
-            const int base = 9 * (c_dfs_pos[j] - 1);
-#pragma unroll
-            for (int e = 0; e < 9; ++e) {
-                const float v = R[e] - ((e == 0 || e == 4 || e == 8) ? 1.0f : 0.0f);
-                const uint16_t hi = bf16_bits(v);
-                row[base + e] = hi; row[FUSED_COL_LO + base + e] = bf16_bits(v - bf16_val(hi));
-            }
-        }
-        if (lane < 16) {   // beta k-steps 26..28: split q of beta[lane] | 1.0 in column 10 of step 26 | zeros
-            uint16_t h = 0, m = 0, l = 0;
-            if (lane < NBETA) {
-                h = bf16_bits(beta[lane]);
-                const float r1 = beta[lane] - bf16_val(h);
-                m = bf16_bits(r1);
-                l = bf16_bits(r1 - bf16_val(m));
-            } else if (lane == NBETA) h = 0x3F80;
-            row[FUSED_COL_BETA + lane] = h; row[FUSED_COL_BETA + 16 + lane] = m; row[FUSED_COL_BETA + 32 + lane] = l;
-        }
-        if (lane == 31) { row[FUSED_COL_LO - 1] = 0; row[FUSED_COL_BETA - 1] = 0; }
-        __syncwarp();
-        const uint4* src = reinterpret_cast<const uint4*>(row);
-        uint4* dst = reinterpret_cast<uint4*>(Arows + f * FUSED_K);
-        for (int i = lane; i < (FUSED_KSTEPS * 16) / 8; i += 32) dst[i] = src[i];
-        return;
-    }
     if (active && j > 0) {
-        const int base = 27 * (c_dfs_pos[j] - 1);
+        const int base = 9 * (c_dfs_pos[j] - 1);
 #pragma unroll
         for (int e = 0; e < 9; ++e) {
             const float v = R[e] - ((e == 0 || e == 4 || e == 8) ? 1.0f : 0.0f);
             const uint16_t hi = bf16_bits(v);
-            const uint16_t lo = bf16_bits(v - bf16_val(hi));
-            row[base + e] = hi; row[base + 9 + e] = hi; row[base + 18 + e] = lo;
+            row[base + e] = hi; row[FUSED_COL_LO + base + e] = bf16_bits(v - bf16_val(hi));
         }
     }
-    if (lane < NBETA) {
-        const uint16_t h = bf16_bits(beta[lane]);
-        const float r1 = beta[lane] - bf16_val(h);
-        const uint16_t m = bf16_bits(r1);
-        const uint16_t l = bf16_bits(r1 - bf16_val(m));
-        uint16_t* c = row + COL_BETA0 + 6 * lane;
-        c[0] = h; c[1] = h; c[2] = m; c[3] = h; c[4] = m; c[5] = l;
+    if (lane < 16) {   // beta k-steps 26..28: split q of beta[lane] | 1.0 in column 10 of step 26 | zeros
+        uint16_t h = 0, m = 0, l = 0;
+        if (lane < NBETA) {
+            h = bf16_bits(beta[lane]);
+            const float r1 = beta[lane] - bf16_val(h);
+            m = bf16_bits(r1);
+            l = bf16_bits(r1 - bf16_val(m));
+        } else if (lane == NBETA) h = 0x3F80;
+        row[FUSED_COL_BETA + lane] = h; row[FUSED_COL_BETA + 16 + lane] = m; row[FUSED_COL_BETA + 32 + lane] = l;
     }
-    if (lane >= NJ && lane < NJ + 3) row[COL_ONES + (lane - NJ)] = 0x3F80;
-    for (int k = COL_ONES + 3 + lane; k < GEMM_K; k += 32) row[k] = 0;
+    if (lane == 31) { row[FUSED_COL_LO - 1] = 0; row[FUSED_COL_BETA - 1] = 0; }
     __syncwarp();
     const uint4* src = reinterpret_cast<const uint4*>(row);
-    uint4* dst = reinterpret_cast<uint4*>(Arows + f * GEMM_K);
-    for (int i = lane; i < GEMM_K / 8; i += 32) dst[i] = src[i];
+    uint4* dst = reinterpret_cast<uint4*>(Arows + f * FUSED_K);
+    for (int i = lane; i < (FUSED_KSTEPS * 16) / 8; i += 32) dst[i] = src[i];
 }
 
 // Whole-batch tests `torch.norm(x) == 0` (smpl_layer.py:87,148): true iff every x*x is 0
@@ -441,7 +382,7 @@ cudaError_t launch_batch_flags(const float* d_betas, const float* d_trans, int64
 
 cudaError_t launch_pose_chain(const Model& m, const float* d_pose, const float* d_betas,
                               const float* d_trans, const BatchFlags* d_flags, int center_idx,
-                              int64_t B, bool full_mesh, bool fused_layout, uint16_t* d_Arows, float* d_Askin,
+                              int64_t B, bool full_mesh, uint16_t* d_Arows, float* d_Askin,
                               float* d_off, float* d_joints, cudaStream_t s) {
     if (B == 0) return cudaSuccess;
     bool model_betas_zero = true;
@@ -453,23 +394,19 @@ cudaError_t launch_pose_chain(const Model& m, const float* d_pose, const float* 
     const bool std_tree = m.pc.standard_tree != 0;
     if (std_tree && B <= kWarpVariantMaxFrames) {   // latency-bound regime: one warp per frame
         const unsigned g = (unsigned)((B + kWarpsPerBlock - 1) / kWarpsPerBlock);
-#define PRK_LAUNCH_W(MESH, FUSED)                                                                        \
-    pose_chain_warp_kernel<MESH, FUSED><<<g, kWarpsPerBlock * 32, 0, s>>>(m.d_Jc, d_pose, d_betas, d_trans, d_flags, mode, \
-                                                                          center_idx, B, d_Arows, d_Askin, d_off, d_joints)
-        if (!full_mesh) PRK_LAUNCH_W(false, false);
-        else if (fused_layout) PRK_LAUNCH_W(true, true);
-        else PRK_LAUNCH_W(true, false);
+#define PRK_LAUNCH_W(MESH)                                                                                \
+    pose_chain_warp_kernel<MESH><<<g, kWarpsPerBlock * 32, 0, s>>>(m.d_Jc, d_pose, d_betas, d_trans, d_flags, mode, \
+                                                                   center_idx, B, d_Arows, d_Askin, d_off, d_joints)
+        if (full_mesh) PRK_LAUNCH_W(true); else PRK_LAUNCH_W(false);
 #undef PRK_LAUNCH_W
         count_launch();
         return cudaGetLastError();
     }
-#define PRK_LAUNCH(STD, MESH, FUSED)                                                              \
-    pose_chain_kernel<STD, MESH, FUSED><<<grid, 128, 0, s>>>(m.pc, d_pose, d_betas, d_trans, d_flags, \
-                                                             mode, center_idx, B, d_Arows, d_Askin, \
-                                                             d_off, d_joints)
-    if (!full_mesh)        { if (std_tree) PRK_LAUNCH(true, false, false); else PRK_LAUNCH(false, false, false); }
-    else if (fused_layout) { if (std_tree) PRK_LAUNCH(true, true, true);   else PRK_LAUNCH(false, true, true); }
-    else                   { if (std_tree) PRK_LAUNCH(true, true, false);  else PRK_LAUNCH(false, true, false); }
+#define PRK_LAUNCH(STD, MESH)                                                                     \
+    pose_chain_kernel<STD, MESH><<<grid, 128, 0, s>>>(m.pc, d_pose, d_betas, d_trans, d_flags, mode, \
+                                                      center_idx, B, d_Arows, d_Askin, d_off, d_joints)
+    if (std_tree) { if (full_mesh) PRK_LAUNCH(true, true); else PRK_LAUNCH(true, false); }
+    else          { if (full_mesh) PRK_LAUNCH(false, true); else PRK_LAUNCH(false, false); }
 #undef PRK_LAUNCH
     count_launch();
     return cudaGetLastError();

@@ -60,7 +60,8 @@ def same_records(a, b, which=('reba', 'rula')):
 
 # --------------------------------------------------------------------------- blend GEMM
 def test_blend_tcgen05_matches_simt_and_numpy(engine):
-    """The tcgen05/TMA GEMM against a plain FFMA loop over the same bf16 operands, and both
+    """The blend stage of the fused tcgen05 kernel (run with identity skinning transforms, so
+    its vertices are v_posed) against a plain FFMA loop over the same bf16 operands, and both
     against v_template + shapedirs.beta + posedirs.(R-I) in float64."""
     from poserisk_release_b200 import _lib, _runtime
     L = _lib.lib()

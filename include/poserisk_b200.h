@@ -172,7 +172,9 @@ int prk_pipeline(prk_model* model, const float* d_pose, const float* d_betas,
  * the inputs of call i+1 are uploaded while the kernels of call i run (two input sets in
  * the workspace), and joints / scores are downloaded while the vertex kernel of the same
  * call is still running.  The host input buffers are read from the moment of the call
- * until `stream` reaches it; they must already hold the data when the call is made. */
+ * until `stream` reaches it; they must already hold the data when the call is made.
+ * The overlap applies to consecutive prk_pipeline_host calls of one handle on the same
+ * workspace; that workspace must not be handed to other work in between. */
 size_t prk_host_workspace_bytes(const prk_model* model, int64_t B, uint32_t flags);
 int prk_pipeline_host(prk_model* model, const float* h_pose, const float* h_betas,
                       const float* h_trans, int center_idx, const prk_addinfo* h_info,

@@ -45,6 +45,10 @@ class _Workspace:
         with self._lock:
             b = self._buf.get(key)
             if b is None or b.numel() < nbytes + 1024:
+                if b is not None:
+                    # the library also works on its own streams, which the caching allocator does not
+                    # know about: nothing may still be using the old buffer when it is released
+                    torch.cuda.synchronize(device)
                 b = torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=device)
                 self._buf[key] = b
         base = b.data_ptr()
@@ -53,6 +57,7 @@ class _Workspace:
 
 
 workspace = _Workspace()
+host_workspace = _Workspace()     # staging + scratch of the host-buffer path, never shared with device-API calls
 
 
 class ModelHandle:

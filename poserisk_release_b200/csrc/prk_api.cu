@@ -403,6 +403,7 @@ int prk_smpl_forward(prk_model* model, const float* d_pose, const float* d_betas
                      void* stream) {
     Model* m = model;
     if (!m) { set_detail("prk_smpl_forward", "null model"); return PRK_ERR_INVALID_ARG; }
+    m->chained_ws = nullptr;
     PRK_CUDA(cudaSetDevice(m->device));
     return forward_impl(m, d_pose, d_betas, d_trans, center_idx, B, d_verts, d_joints, ws, ws_bytes,
                         static_cast<cudaStream_t>(stream));
@@ -463,6 +464,7 @@ int prk_pipeline(prk_model* model, const float* d_pose, const float* d_betas, co
                  prk_score_rec* d_scores, void* ws, size_t ws_bytes, void* stream) {
     Model* m = model;
     if (!m || !d_info || (B > 0 && !d_scores)) { set_detail("prk_pipeline", "invalid argument"); return PRK_ERR_INVALID_ARG; }
+    m->chained_ws = nullptr;
     PRK_CUDA(cudaSetDevice(m->device));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     // scoring only reads the pose: it runs on the model's scoring stream, beside the mesh path
@@ -542,7 +544,14 @@ int prk_pipeline_host(prk_model* model, const float* h_pose, const float* h_beta
 
     // ---- copy-in stream: inputs of this call land while the kernels of the previous call run (the
     // host buffers must be ready when the call is made, as for any host argument).  The set was
-    // last read by the call before the previous one (ev_set_free).
+    // last read by the call before the previous one (ev_set_free).  Only a chain of host calls on
+    // the same workspace is known to leave the staging area alone: after anything else the copy
+    // waits for the work already queued on the caller's stream.
+    if (m->chained_ws != ws) {
+        PRK_CUDA(cudaEventRecord(m->ev_in, s));
+        PRK_CUDA(cudaStreamWaitEvent(m->s_in, m->ev_in, 0));
+    }
+    m->chained_ws = ws;
     PRK_CUDA(cudaStreamWaitEvent(m->s_in, m->ev_set_free[set], 0));
     PRK_CUDA(cudaMemcpyAsync(d_pose, h_pose, (size_t)B * 72 * 4, cudaMemcpyHostToDevice, m->s_in));
     if (h_betas) PRK_CUDA(cudaMemcpyAsync(d_betas, h_betas, (size_t)B * NBETA * 4, cudaMemcpyHostToDevice, m->s_in));

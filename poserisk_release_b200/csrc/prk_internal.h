@@ -72,6 +72,7 @@ struct prk_model {
     cudaStream_t s_in = nullptr, s_out = nullptr;
     cudaEvent_t ev_h2d = nullptr, ev_joints = nullptr, ev_out = nullptr, ev_set_free[2] = {nullptr, nullptr};
     uint64_t host_calls = 0;
+    const void* chained_ws = nullptr;   // workspace of the previous call if that was a prk_pipeline_host call
 };
 
 namespace prk {

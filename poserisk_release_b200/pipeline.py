@@ -3,7 +3,7 @@ Python (Euler angles, SMPL forward, REBA, RULA) done for whole batches on one GP
 
 ``PoseRiskEngine.run`` takes device tensors, ``run_host`` takes (pinned) host arrays
 and goes through ``prk_pipeline_host`` (host->device copies, kernels, device->host
-copies of scores and joints on one stream).  Multi-person tracks with different
+copies of scores and joints; back-to-back calls overlap their copies with the kernels).  Multi-person tracks with different
 genders / additional information are handled by grouping frames per gender
 (BASELINE.json config 4).
 """
@@ -29,15 +29,24 @@ class PoseRiskEngine:
         self._host_ws = None
 
     # ------------------------------------------------------------------ device path
+    def _dev_f32(self, t, B, n):
+        """(B, n) float32 contiguous tensor on the engine's device (no copy when it already is one)."""
+        if t is None:
+            return None
+        if not (t.device == self.device and t.dtype == torch.float32 and t.is_contiguous()):
+            t = t.to(self.device, torch.float32).contiguous()
+        return t.reshape(B, n)
+
     def run(self, pose, betas=None, trans=None, add_info=None, track_of_frame=None, gender='neutral',
-            want_verts=True, center_idx=None, verts_out=None):
+            want_verts=True, center_idx=None, verts_out=None, joints_out=None, scores_out=None):
         """pose (B,72) float32 CUDA tensor.  Returns dict(verts|None, joints, scores) where
-        scores is a (B,32) uint8 tensor of prk_score_rec."""
+        scores is a (B,32) uint8 tensor of prk_score_rec.  The *_out tensors, when given, receive
+        the results (no allocation in the call)."""
         dev = self.device
         B = pose.shape[0]
-        pose = pose.to(dev, torch.float32).reshape(B, 72).contiguous()
-        betas = None if betas is None else betas.to(dev, torch.float32).reshape(B, 10).contiguous()
-        trans = None if trans is None else trans.to(dev, torch.float32).reshape(B, 3).contiguous()
+        pose = self._dev_f32(pose, B, 72)
+        betas = self._dev_f32(betas, B, 10)
+        trans = self._dev_f32(trans, B, 3)
         info = add_info if isinstance(add_info, torch.Tensor) else _runtime.addinfo_tensor(add_info, dev)
         track = None if track_of_frame is None else torch.as_tensor(track_of_frame, dtype=torch.int32).to(dev).contiguous()
         h = self.models[gender]
@@ -45,10 +54,13 @@ class PoseRiskEngine:
             verts = None
             if want_verts:
                 verts = verts_out if verts_out is not None else torch.empty((B, 6890, 3), dtype=torch.float32, device=dev)
-            joints = torch.empty((B, 24, 3), dtype=torch.float32, device=dev)
-            scores = torch.empty((B, 32), dtype=torch.uint8, device=dev)
+            joints = joints_out if joints_out is not None else torch.empty((B, 24, 3), dtype=torch.float32, device=dev)
+            scores = scores_out if scores_out is not None else torch.empty((B, 32), dtype=torch.uint8, device=dev)
             if B > 0:
-                ws, ws_bytes, _keep = _runtime.workspace.get(dev, h.workspace_bytes(B, not want_verts))
+                key = (B, want_verts, gender)
+                if getattr(self, '_ws_key', None) != key:      # workspace size per (batch, mode): queried once
+                    self._ws_key, self._ws_bytes = key, h.workspace_bytes(B, not want_verts)
+                ws, ws_bytes, _keep = _runtime.workspace.get(dev, self._ws_bytes)
                 _lib.check(_lib.lib().prk_pipeline(
                     h.handle, _runtime.ptr(pose), _runtime.ptr(betas), _runtime.ptr(trans),
                     -1 if center_idx is None else int(center_idx), _runtime.ptr(info), _runtime.ptr(track), B,
@@ -113,7 +125,7 @@ class PoseRiskEngine:
         track = None if track_of_frame is None else np.ascontiguousarray(track_of_frame, np.int32)
         joints_only = verts_out is None
         with torch.cuda.device(dev):
-            ws, ws_bytes, _keep = _runtime.workspace.get(dev, h.host_workspace_bytes(B, joints_only))
+            ws, ws_bytes, _keep = _runtime.host_workspace.get(dev, h.host_workspace_bytes(B, joints_only))
             _lib.check(_lib.lib().prk_pipeline_host(
                 h.handle, _runtime.ptr(pose), _runtime.ptr(betas), _runtime.ptr(trans),
                 -1 if center_idx is None else int(center_idx), info.ctypes.data_as(C.c_void_p), info.shape[0],

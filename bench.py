@@ -210,21 +210,37 @@ def run_gpu_arm(args):
     h_joints = torch.empty((B, 24, 3), dtype=torch.float32).pin_memory()
     h_scores = torch.empty((B, 32), dtype=torch.uint8).pin_memory()
 
+    # N > 1: the all-gather of step i's 32-byte score records is issued with async_op=True (it runs on the
+    # process group's own stream) and is waited for one step later, so it overlaps the kernels of step i+1;
+    # every step still gathers inside the timed region and barrier() waits for the last one.
+    pending = []
+
+    def gather_scores(scores_dev):
+        out = torch.empty((world * B, 32), dtype=torch.uint8, device=dev)
+        work = dist.all_gather_into_tensor(out, scores_dev, async_op=True)
+        pending.append((work, out, scores_dev))
+        while len(pending) > 1:
+            pending.pop(0)[0].wait()
+
     def step_device(i):
         p, b, t = dev_in[i % n_rot]
         out = eng.run(p, b, t, add_info=info_dev, verts_out=verts, joints_out=d_joints, scores_out=d_scores)
         if world > 1:
-            all_gather_rows(out['scores'], B * world)
+            # the next step overwrites d_scores: gather a snapshot taken on the compute stream
+            gather_scores(out['scores'].clone())
         return out
 
     def step_host(i):
         p, b, t = host_in[i % n_rot]
         eng.run_host(p, b, t, EXAMPLE_INFO, None, h_joints, h_scores, verts_out=verts)
         if world > 1:
-            all_gather_rows(h_scores.to(dev, non_blocking=True), B * world)
+            gather_scores(eng.host_scores_device.clone())
 
     def barrier():
         if world > 1:
+            while pending:
+                pending.pop(0)[0].wait()
+            torch.cuda.synchronize(dev)
             dist.barrier()
         torch.cuda.synchronize(dev)
 

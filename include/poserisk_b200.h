@@ -176,6 +176,10 @@ int prk_pipeline(prk_model* model, const float* d_pose, const float* d_betas,
  * The overlap applies to consecutive prk_pipeline_host calls of one handle on the same
  * workspace; that workspace must not be handed to other work in between. */
 size_t prk_host_workspace_bytes(const prk_model* model, int64_t B, uint32_t flags);
+/* byte offset, inside the workspace of a prk_pipeline_host call of B frames, of the DEVICE copy
+ * of the B score records (valid once `stream` has reached the call): what a multi-GPU caller
+ * all-gathers without a second host->device copy. */
+size_t prk_host_scores_offset(const prk_model* model, int64_t B);
 int prk_pipeline_host(prk_model* model, const float* h_pose, const float* h_betas,
                       const float* h_trans, int center_idx, const prk_addinfo* h_info,
                       int32_t n_tracks, const int32_t* h_track_of_frame, int64_t B,

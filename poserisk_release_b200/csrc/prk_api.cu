@@ -516,6 +516,8 @@ size_t prk_host_workspace_bytes(const prk_model* model, int64_t B, uint32_t flag
     return host_stage(B, 4096, prk_workspace_bytes(model, B, flags)).total;
 }
 
+size_t prk_host_scores_offset(const prk_model*, int64_t B) { return host_stage(B, 4096, 0).scores; }
+
 int prk_pipeline_host(prk_model* model, const float* h_pose, const float* h_betas, const float* h_trans,
                       int center_idx, const prk_addinfo* h_info, int32_t n_tracks, const int32_t* h_track, int64_t B,
                       float* d_verts, float* h_joints, prk_score_rec* h_scores, void* ws, size_t ws_bytes,
@@ -547,10 +549,8 @@ int prk_pipeline_host(prk_model* model, const float* h_pose, const float* h_beta
     // last read by the call before the previous one (ev_set_free).  Only a chain of host calls on
     // the same workspace is known to leave the staging area alone: after anything else the copy
     // waits for the work already queued on the caller's stream.
-    if (m->chained_ws != ws) {
-        PRK_CUDA(cudaEventRecord(m->ev_in, s));
-        PRK_CUDA(cudaStreamWaitEvent(m->s_in, m->ev_in, 0));
-    }
+    PRK_CUDA(cudaEventRecord(m->ev_in, s));
+    if (m->chained_ws != ws) PRK_CUDA(cudaStreamWaitEvent(m->s_in, m->ev_in, 0));
     m->chained_ws = ws;
     PRK_CUDA(cudaStreamWaitEvent(m->s_in, m->ev_set_free[set], 0));
     PRK_CUDA(cudaMemcpyAsync(d_pose, h_pose, (size_t)B * 72 * 4, cudaMemcpyHostToDevice, m->s_in));
@@ -563,7 +563,9 @@ int prk_pipeline_host(prk_model* model, const float* h_pose, const float* h_beta
     // ---- scoring on its own stream, pose chain + vertex kernels on the caller's stream
     cudaStream_t ss = m->s_score;
     PRK_CUDA(cudaStreamWaitEvent(ss, m->ev_h2d, 0));
-    PRK_CUDA(cudaStreamWaitEvent(ss, m->ev_out, 0));        // d_scores of the previous call has been copied out
+    // the staged score records of the previous call may still be read by work the caller queued
+    // after it (prk_host_scores_offset): scoring starts where the caller's stream stands now
+    PRK_CUDA(cudaStreamWaitEvent(ss, m->ev_in, 0));
     {
         StageScope sc(3, ss);
         PRK_CUDA(launch_score_pose(d_pose, PRK_DTYPE_F32, d_info, d_track, B, PRK_SCORE_REBA | PRK_SCORE_RULA, d_scores,

@@ -132,6 +132,10 @@ class PoseRiskEngine:
                 None if track is None else track.ctypes.data_as(C.c_void_p), B, _runtime.ptr(verts_out),
                 _runtime.ptr(joints_out), _runtime.ptr(scores_out), ws, ws_bytes, _runtime.stream_ptr(dev)))
         self._keep = (info, track)   # pageable host arrays must outlive the async copies
+        # device copy of the score records inside the workspace (what a multi-GPU caller all-gathers)
+        base = ws.value - _keep.data_ptr()
+        off = base + int(_lib.lib().prk_host_scores_offset(h.handle, B))
+        self.host_scores_device = _keep[off:off + B * 32].view(B, 32)
         return joints_out, scores_out
 
     # ------------------------------------------------------------------ aggregation

@@ -245,20 +245,27 @@ __device__ __constant__ int8_t c_depth[32] = {0, 1, 1, 1, 2, 2, 2, 3, 3, 3, 4, 4
 // position of joint j in the depth-first order used for the A' column blocks
 __device__ __constant__ int8_t c_dfs_pos[32] = {0, 1, 5, 9, 2, 6, 10, 3, 7, 11, 4, 8, 12, 14, 19, 13, 15, 20, 16, 21, 17, 22, 18, 23,
                                                 0, 0, 0, 0, 0, 0, 0, 0};
-constexpr int kWarpsPerBlock = 8;
+constexpr int kWarpsPerBlock = 8;        // joints-only variant
+constexpr int kWarpsPerBlockMesh = 16;   // full-mesh variant: 16 consecutive frames per block, so that the block
+                                         // writes its AskinT columns as 64-byte runs (two full sectors) instead of
+                                         // 288 scattered 4-byte stores per frame
 constexpr int64_t kWarpVariantMaxFrames = 65536;   // above this the thread-per-frame kernel fills the GPU
 
 template <bool kMesh>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__((kMesh ? kWarpsPerBlockMesh : kWarpsPerBlock) * 32)
 pose_chain_warp_kernel(const float* __restrict__ Jc /* J_template[72] | Jdirs[720] | model_betas[10] */,
                        const float* __restrict__ pose, const float* __restrict__ betas,
                        const float* __restrict__ trans, const BatchFlags* __restrict__ flags, uint32_t mode,
                        int center_idx, int64_t B, uint16_t* __restrict__ Arows, float* __restrict__ Askin,
                        float* __restrict__ off, float* __restrict__ joints) {
-    __shared__ __align__(16) uint16_t s_row[kMesh ? kWarpsPerBlock : 1][FUSED_K];
+    constexpr int kW = kMesh ? kWarpsPerBlockMesh : kWarpsPerBlock;
+    __shared__ __align__(16) uint16_t s_row[kMesh ? kW : 1][FUSED_K];
+    __shared__ float s_askin[kMesh ? FUSED_ASKIN_COLS : 1][kMesh ? kW + 1 : 1];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t f = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
-    if (f >= B) return;
+    const int64_t f_own = (int64_t)blockIdx.x * kW + warp;
+    const bool valid = f_own < B;                 // warp-uniform; invalid warps compute on the last frame and store nothing
+    if (!kMesh && !valid) return;
+    const int64_t f = valid ? f_own : B - 1;
     const unsigned FULL = 0xffffffffu;
 
     bool frame_betas = (mode & MODE_FRAME_BETAS_ALWAYS) != 0;
@@ -303,20 +310,30 @@ pose_chain_warp_kernel(const float* __restrict__ Jc /* J_template[72] | Jdirs[72
         o2 = -__shfl_sync(FULL, G[11], center_idx);
         x0 = __fadd_rn(x0, o0); x1 = __fadd_rn(x1, o1); x2 = __fadd_rn(x2, o2);
     }
-    if (active) {
+    if (active && valid) {
         float* jo = joints + f * 72 + j * 3;
         jo[0] = x0; jo[1] = x1; jo[2] = x2;
     }
     if (!kMesh) return;
 
-    if (active) {   // TMEM-tile layout [frame / 32][12 * joint + e][frame % 32]
-        float* dst = Askin + ((f >> 5) * FUSED_ASKIN_COLS + j * 12) * 32 + (f & 31);
+    if (active) {   // A_j columns of this frame into the block's staging tile [12 * joint + e][frame in block]
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
-            dst[askin_col(r, 0) * 32] = G[r * 4 + 0]; dst[askin_col(r, 1) * 32] = G[r * 4 + 1];
-            dst[askin_col(r, 2) * 32] = G[r * 4 + 2]; dst[askin_col(r, 3) * 32] = skin_t(G, r, J[0], J[1], J[2]);
+            s_askin[j * 12 + askin_col(r, 0)][warp] = G[r * 4 + 0]; s_askin[j * 12 + askin_col(r, 1)][warp] = G[r * 4 + 1];
+            s_askin[j * 12 + askin_col(r, 2)][warp] = G[r * 4 + 2];
+            s_askin[j * 12 + askin_col(r, 3)][warp] = skin_t(G, r, J[0], J[1], J[2]);
         }
     }
+    __syncthreads();
+    {   // TMEM-tile layout [frame / 32][288][frame % 32]: the block's 16 frames are one half of every 128-byte line
+        const int64_t f0 = (int64_t)blockIdx.x * kW;
+        float* dst = Askin + (f0 >> 5) * FUSED_ASKIN_COLS * 32 + (f0 & 31);
+        for (int idx = threadIdx.x; idx < FUSED_ASKIN_COLS * kW; idx += kW * 32) {
+            const int col = idx / kW, fl = idx - col * kW;
+            dst[col * 32 + fl] = s_askin[col][fl];
+        }
+    }
+    if (!valid) return;
     if (lane == 0) { off[f * 3 + 0] = o0; off[f * 3 + 1] = o1; off[f * 3 + 2] = o2; }
 
     // A' row assembled in shared memory, then written with 16-byte stores
@@ -393,10 +410,11 @@ cudaError_t launch_pose_chain(const Model& m, const float* d_pose, const float* 
     const unsigned grid = (unsigned)((B + 127) / 128);
     const bool std_tree = m.pc.standard_tree != 0;
     if (std_tree && B <= kWarpVariantMaxFrames) {   // latency-bound regime: one warp per frame
-        const unsigned g = (unsigned)((B + kWarpsPerBlock - 1) / kWarpsPerBlock);
+        const int wpb = full_mesh ? kWarpsPerBlockMesh : kWarpsPerBlock;
+        const unsigned g = (unsigned)((B + wpb - 1) / wpb);
 #define PRK_LAUNCH_W(MESH)                                                                                \
-    pose_chain_warp_kernel<MESH><<<g, kWarpsPerBlock * 32, 0, s>>>(m.d_Jc, d_pose, d_betas, d_trans, d_flags, mode, \
-                                                                   center_idx, B, d_Arows, d_Askin, d_off, d_joints)
+    pose_chain_warp_kernel<MESH><<<g, wpb * 32, 0, s>>>(m.d_Jc, d_pose, d_betas, d_trans, d_flags, mode, \
+                                                        center_idx, B, d_Arows, d_Askin, d_off, d_joints)
         if (full_mesh) PRK_LAUNCH_W(true); else PRK_LAUNCH_W(false);
 #undef PRK_LAUNCH_W
         count_launch();

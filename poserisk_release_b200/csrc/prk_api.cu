@@ -298,12 +298,14 @@ int prk_model_create(prk_model** out, int device, const float* vt, const float* 
             }
         }
         uint16_t sp[3];
+        uint16_t* x = row + FUSED_COL_BETA;          // k-steps 26..29 (prk_internal.h "K12 operand layout")
         for (int b = 0; b < NBETA; ++b) {
             split3(sd[(size_t)n * NBETA + b], sp[0], sp[1], sp[2]);
-            for (int q = 0; q < 3; ++q) row[FUSED_COL_BETA + 16 * q + b] = sp[q];
+            x[b] = sp[0]; x[16 + b] = sp[0]; x[32 + b] = sp[1]; x[48 + b] = sp[2];
+            if (b < 5) x[NBETA + b] = sp[0]; else x[16 + NBETA + (b - 5)] = sp[0];
         }
         split3(vt[n], sp[0], sp[1], sp[2]);
-        for (int q = 0; q < 3; ++q) row[FUSED_COL_BETA + 16 * q + NBETA] = sp[q];
+        x[15] = sp[0]; x[32 + 15] = sp[1]; x[48 + 15] = sp[2];
     }
 
     // compacted skinning weights

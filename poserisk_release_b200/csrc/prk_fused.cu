@@ -17,15 +17,15 @@
 //     (scripts/ubench_tmem.cu), twice what shared memory gives the same gather.
 //   * the blend GEMM runs on tcgen05 (kind::f16, bf16 x bf16 -> fp32) with fp32-class accuracy
 //     from split precision, but the hi/lo parts are stored ONCE (prk_internal.h "K12 operand
-//     layout"): the A' tile of the 128 frames (29 k-steps, 128 KB) stays resident in shared
-//     memory for the whole frame tile, only the 12 KB B' chunks stream through a TMA ring, and
-//     each B' k-step is multiplied with every A' k-step it pairs with (45 MMAs per unit).
+//     layout"): the A' tile of the 128 frames stays resident in shared
+//     memory for the whole frame tile (28 k-steps, 112 KB), only the 12 KB B' chunks stream through a TMA ring, and
+//     each B' k-step is multiplied with every A' k-step it pairs with (44 MMAs per unit).
 //   * accumulators are double buffered in TMEM (columns 288..383 / 384..479), so the MMAs of
 //     unit i+1 run under the skinning of unit i.
 //   * vertices leave through a per-warp shared-memory transpose so that every global store
 //     instruction writes contiguous 48-byte runs of a frame's row.
 // HBM traffic per frame: 82,680 B of vertices out, ~2.2 KB of operands in (B' is L2 resident)
-// -> HBM roofline; executed MMA work 2*45*16*96*... = 29.9 MFLOP/frame.
+// -> HBM roofline; executed MMA work 216 tiles x 44 MMAs x 2*96*16 = 29.2 MFLOP/frame.
 //
 // Warp roles (576 threads): warps 0-15 epilogue (TMEM lane quarter = warp & 3, vertex octet =
 // warp >> 2), warp 16 TMA producer, warp 17 TMEM allocator + MMA issuer.  All mbarrier waits
@@ -48,7 +48,7 @@ using namespace tc;
 #endif
 
 constexpr int kAChunkBytes = FUSED_BM * 128;                     // 128 frames x 64 bf16
-constexpr int kABytes = FUSED_KCHUNKS * kAChunkBytes;            // 131,072: resident A' tile
+constexpr int kABytes = FUSED_A_CHUNKS * kAChunkBytes;           // 114,688: resident A' tile
 constexpr int kBChunkBytes = FUSED_BN * 128;                     // 96 vertex coords x 64 bf16 = 12,288
 constexpr int kEpiWarps = 16;
 constexpr int kOutPitch = 52;                                    // floats per staged frame row: 16 vertices x 3 (+4: conflict-free float4)
@@ -236,7 +236,7 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
                 if (n_ft > 0) MBAR_WAIT(aempty_bar, (n_ft - 1) & 1);
                 if (elect_one()) {
                     mbar_expect_tx(afull_bar, kABytes);
-                    for (int c = 0; c < FUSED_KCHUNKS; ++c)
+                    for (int c = 0; c < FUSED_A_CHUNKS; ++c)
                         tma_load_2d(&tmap_A, afull_bar, sA + c * kAChunkBytes, c * 64, (int)(ft * FUSED_BM));
                 }
                 ++n_ft;
@@ -251,7 +251,7 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
                 bulk_load_1d(sW + (i & (kWSlots - 1)) * wbytes, wpack + (size_t)vt * wbytes, wbytes, wb);
             }
 #pragma unroll 1
-            for (int c = 0; c < FUSED_KCHUNKS; ++c) {
+            for (int c = 0; c < FUSED_B_CHUNKS; ++c) {
                 MBAR_WAIT(&empty_bar[stage], phase ^ 1);
                 if (elect_one()) {
                     if (DBG(16)) { mbar_arrive(&full_bar[stage]); }
@@ -290,7 +290,7 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
             tcgen05_fence_after();
             const uint32_t d_tmem = tmem_base + kAccCol0 + (uint32_t)acc * FUSED_BN;
 #pragma unroll
-            for (int c = 0; c < FUSED_KCHUNKS; ++c) {
+            for (int c = 0; c < FUSED_B_CHUNKS; ++c) {
                 MBAR_WAIT(&full_bar[stage], phase);
                 tcgen05_fence_after();
                 const uint32_t b_lo = b_lo0 + (uint32_t)stage * (kBChunkBytes >> 4);
@@ -304,16 +304,15 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
                             umma_bf16_lohi(d_tmem, a_lo + a_step_off(FUSED_POSE_STEPS + b), bl, d_hi, idesc, true);
                         } else if (b < 2 * FUSED_POSE_STEPS) {    // posedirs lo: x pose hi
                             umma_bf16_lohi(d_tmem, a_lo + a_step_off(b - FUSED_POSE_STEPS), bl, d_hi, idesc, true);
-                        } else if (b < FUSED_KSTEPS) {            // shapedirs/template split q: x beta splits 0..2-q
-                            const int q = b - 2 * FUSED_POSE_STEPS;
-#pragma unroll
-                            for (int p = 0; p < 3; ++p)
-                                if (p + q < 3)
-                                    umma_bf16_lohi(d_tmem, a_lo + a_step_off(2 * FUSED_POSE_STEPS + p), bl, d_hi, idesc, true);
+                        } else if (b < FUSED_B_STEPS) {           // the five beta x shapedirs (+ template) products
+                            constexpr int A26 = 2 * FUSED_POSE_STEPS, A27 = A26 + 1;
+                            const int q = b - 2 * FUSED_POSE_STEPS;      // 0: s1|s1a|t1  1: s1|s1b  2: s2|t2  3: s3|t3
+                            if (q != 1) umma_bf16_lohi(d_tmem, a_lo + a_step_off(A26), bl, d_hi, idesc, true);
+                            if (q == 1 || q == 2) umma_bf16_lohi(d_tmem, a_lo + a_step_off(A27), bl, d_hi, idesc, true);
                         }
                     }
                     tcgen05_commit(&empty_bar[stage]);            // frees the ring slot when the MMAs retire
-                    if (c == FUSED_KCHUNKS - 1) {
+                    if (c == FUSED_B_CHUNKS - 1) {
 #pragma unroll
                         for (int w = 0; w < kEpiWarps; ++w) tcgen05_commit(&tfull_bar[acc * kEpiWarps + w]);
                     }
@@ -572,8 +571,10 @@ blend_simt_kernel(const uint16_t* __restrict__ Arows, const uint16_t* __restrict
         acc = step(FUSED_POSE_STEPS + i, i, acc);                // lo x hi
         acc = step(i, FUSED_POSE_STEPS + i, acc);                // hi x lo
     }
-    for (int q = 0; q < 3; ++q)
-        for (int p = 0; p + q < 3; ++p) acc = step(2 * FUSED_POSE_STEPS + p, 2 * FUSED_POSE_STEPS + q, acc);
+    const int A26 = 2 * FUSED_POSE_STEPS, A27 = A26 + 1, B26 = A26;
+    acc = step(A26, B26, acc); acc = step(A27, B26 + 1, acc);
+    acc = step(A26, B26 + 2, acc); acc = step(A27, B26 + 2, acc);
+    acc = step(A26, B26 + 3, acc);
     vposed[f * NVC + n] = acc;
 }
 

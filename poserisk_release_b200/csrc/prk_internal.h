@@ -18,19 +18,29 @@ constexpr int NVC = NV * 3;             // 20670 vertex coordinates
 constexpr int GEMM_N = 20736;           // 20670 vertex coordinates padded to 216 tiles of 96
 
 // ---- fused blend + skinning geometry (DESIGN.md "K12", prk_fused.cu) ---------
-// K12 operand layout: the hi/lo parts of every factor are stored ONCE, in k-steps of 16 bf16:
-//   steps  0..12  pose features hi   (207 + 1 zero column; feature p = 9*(pos-1)+e, pos = DFS position)
-//   steps 13..25  pose features lo
-//   steps 26..28  A': beta split q (10 columns) [+ 1.0 in column 10 of step 26]
-//                 B': shapedirs split q (10 columns) + v_template split q in column 10
-//   columns 464..511 pad the row to 8 chunks of 64 (never multiplied).
-// The MMA issuer pairs  A'hi x B'hi,  A'lo x B'hi,  A'hi x B'lo  and  beta_p x shape_q for p+q <= 2
-// (45 MMAs of K=16 per tile): pose features as hi*hi + lo*hi + hi*lo, betas / shapedirs as 3-way
-// splits (6 products), v_template as an exact 3-way split.
-constexpr int FUSED_K = 512;
-constexpr int FUSED_KCHUNKS = FUSED_K / 64;
+// K12 operand layout: the hi/lo parts of every factor are stored ONCE, in k-steps of 16 bf16.
+// With (b1,b2,b3) / (s1,s2,s3) / (t1,t2,t3) the 3-way bf16 splits of a beta, a shapedirs entry and a
+// v_template entry:
+//   A' row (per frame, 28 k-steps = 7 chunks of 64 columns):
+//     steps  0..12  pose features hi   (207 + 1 zero column; feature p = 9*(pos-1)+e, pos = DFS position)
+//     steps 13..25  pose features lo
+//     step  26      b1[0..9] | b3[0..4] | 1.0
+//     step  27      b2[0..9] | b3[5..9] | 0
+//   B' row (per vertex coordinate, 30 k-steps, rows padded to 8 chunks):
+//     steps  0..12  posedirs hi            steps 13..25  posedirs lo
+//     step  26      s1[0..9] | s1[0..4] | t1        (x A26: b1.s1 + b3.s1 (first half) + t1)
+//     step  27      s1[0..9] | s1[5..9] | 0         (x A27: b2.s1 + b3.s1 (second half))
+//     step  28      s2[0..9] | 0 x 5    | t2        (x A26: b1.s2 + t2;  x A27: b2.s2)
+//     step  29      s3[0..9] | 0 x 5    | t3        (x A26: b1.s3 + t3)
+// The MMA issuer pairs  A'hi x B'hi,  A'lo x B'hi,  A'hi x B'lo  and the five beta products above:
+// 44 MMAs of K=16 per tile.  Pose features: hi*hi + lo*hi + hi*lo; betas x shapedirs: the six
+// products b_p.s_q with p+q <= 4 (1-based); v_template exact in three terms.
+constexpr int FUSED_K = 512;                             // bf16 columns per stored row (A' rows use 448 of them)
 constexpr int FUSED_POSE_STEPS = 13;
-constexpr int FUSED_KSTEPS = 2 * FUSED_POSE_STEPS + 3;   // 29
+constexpr int FUSED_A_STEPS = 2 * FUSED_POSE_STEPS + 2;  // 28
+constexpr int FUSED_B_STEPS = 2 * FUSED_POSE_STEPS + 4;  // 30
+constexpr int FUSED_A_CHUNKS = FUSED_A_STEPS / 4;        // 7 resident chunks of 64 columns
+constexpr int FUSED_B_CHUNKS = (FUSED_B_STEPS + 3) / 4;  // 8 streamed chunks (the last holds two k-steps)
 constexpr int FUSED_COL_LO = 16 * FUSED_POSE_STEPS;      // 208
 constexpr int FUSED_COL_BETA = 2 * FUSED_COL_LO;         // 416
 constexpr int FUSED_BM = 128;            // frames per tile (TMEM lanes)

@@ -10,7 +10,7 @@
 //
 // Outputs per frame:
 //   joints [24][3]                                     (always)
-//   A' row [512] bf16: split-precision operand of the fused kernel's blend GEMM, K12 layout
+//   A' row [448 of 512] bf16: split-precision operand of the fused kernel's blend GEMM, K12 layout
 //                      (prk_internal.h)                                     (full mesh only)
 //   AskinT [frame/32][288][frame%32] fp32: A_j = [R_g | t_g - R_g j_rest] in the column order
 //                      the fused kernel keeps in tensor memory              (full mesh only)
@@ -18,7 +18,7 @@
 //
 // The chain is walked depth-first with every index a compile-time constant, so the at
 // most three live 3x4 transforms stay in registers; HBM traffic is 288 B pose (+40 betas,
-// +12 trans) in and 288 B joints (+928 A' +1152 A_j +12 off) out per frame.
+// +12 trans) in and 288 B joints (+896 A' +1152 A_j +12 off) out per frame.
 #include "prk_internal.h"
 
 #include <cuda_bf16.h>
@@ -221,14 +221,17 @@ pose_chain_kernel(const __grid_constant__ PoseConsts pc, const float* __restrict
             bs[1][k] = bf16_bits(r1);
             bs[2][k] = bf16_bits(r1 - bf16_val(bs[1][k]));
         }
+        // k-step 26: b1 | b3[0..4] | 1.0      k-step 27: b2 | b3[5..9] | 0
 #pragma unroll
-        for (int q = 0; q < 3; ++q) {
+        for (int k = 0; k < NBETA; ++k) rw.push(bs[0][k]);
 #pragma unroll
-            for (int k = 0; k < NBETA; ++k) rw.push(bs[q][k]);
-            rw.push(q == 0 ? 0x3F80 : 0);            // 1.0 x v_template splits (k-step 26 only)
+        for (int k = 0; k < 5; ++k) rw.push(bs[2][k]);
+        rw.push(0x3F80);
 #pragma unroll
-            for (int k = NBETA + 1; k < 16; ++k) rw.push(0);
-        }
+        for (int k = 0; k < NBETA; ++k) rw.push(bs[1][k]);
+#pragma unroll
+        for (int k = 5; k < NBETA; ++k) rw.push(bs[2][k]);
+        rw.push(0);
     }
 }
 
@@ -347,21 +350,21 @@ pose_chain_warp_kernel(const float* __restrict__ Jc /* J_template[72] | Jdirs[72
             row[base + e] = hi; row[FUSED_COL_LO + base + e] = bf16_bits(v - bf16_val(hi));
         }
     }
-    if (lane < 16) {   // beta k-steps 26..28: split q of beta[lane] | 1.0 in column 10 of step 26 | zeros
-        uint16_t h = 0, m = 0, l = 0;
-        if (lane < NBETA) {
-            h = bf16_bits(beta[lane]);
-            const float r1 = beta[lane] - bf16_val(h);
-            m = bf16_bits(r1);
-            l = bf16_bits(r1 - bf16_val(m));
-        } else if (lane == NBETA) h = 0x3F80;
-        row[FUSED_COL_BETA + lane] = h; row[FUSED_COL_BETA + 16 + lane] = m; row[FUSED_COL_BETA + 32 + lane] = l;
+    if (lane < NBETA) {   // k-step 26: b1 | b3[0..4] | 1.0      k-step 27: b2 | b3[5..9] | 0
+        const uint16_t h = bf16_bits(beta[lane]);
+        const float r1 = beta[lane] - bf16_val(h);
+        const uint16_t m = bf16_bits(r1);
+        const uint16_t l = bf16_bits(r1 - bf16_val(m));
+        row[FUSED_COL_BETA + lane] = h; row[FUSED_COL_BETA + 16 + lane] = m;
+        row[FUSED_COL_BETA + (lane < 5 ? NBETA + lane : 16 + NBETA + (lane - 5))] = l;
+    } else if (lane == NBETA) {
+        row[FUSED_COL_BETA + 15] = 0x3F80; row[FUSED_COL_BETA + 31] = 0;
     }
     if (lane == 31) { row[FUSED_COL_LO - 1] = 0; row[FUSED_COL_BETA - 1] = 0; }
     __syncwarp();
     const uint4* src = reinterpret_cast<const uint4*>(row);
     uint4* dst = reinterpret_cast<uint4*>(Arows + f * FUSED_K);
-    for (int i = lane; i < (FUSED_KSTEPS * 16) / 8; i += 32) dst[i] = src[i];
+    for (int i = lane; i < (FUSED_A_STEPS * 16) / 8; i += 32) dst[i] = src[i];
 }
 
 // Whole-batch tests `torch.norm(x) == 0` (smpl_layer.py:87,148): true iff every x*x is 0

@@ -181,6 +181,10 @@ static int forward_impl(Model* m, const float* d_pose, const float* d_betas, con
     }
     if (B == 0) return PRK_OK;
     const bool mesh = d_verts != nullptr;
+    if (mesh && (reinterpret_cast<uintptr_t>(d_verts) & 7)) {   // frame rows are written in 8- and 16-byte pieces
+        set_detail("prk_smpl_forward", "d_verts must be 8-byte aligned");
+        return PRK_ERR_INVALID_ARG;
+    }
     if (!ws || (reinterpret_cast<uintptr_t>(ws) & 1023)) {
         set_detail("prk_smpl_forward", "workspace missing or not 1024-byte aligned");
         return PRK_ERR_WORKSPACE;

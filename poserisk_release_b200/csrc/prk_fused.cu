@@ -432,15 +432,18 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
                 const uint4* cols = reinterpret_cast<const uint4*>(wslot + 512) + oct * 4;
                 const float4* wgt = reinterpret_cast<const float4*>(wslot) + oct * 4;
                 constexpr int kTileV[8] = {0, 1, 2, 3, 16, 17, 18, 19};
-                uint32_t buf[2][12], p[2][4];
+                uint32_t buf[2][12], p[24];
                 uint4 cj = DBG(64) ? make_uint4(12, 36, 120, 240) : cols[0];
                 TCLK(tg0);
-#ifdef PRK_FUSED_DEBUG
-                for (int z = 0; z < 12; ++z) { buf[0][z] = 0x3f000000u + z; buf[1][z] = 0x3f100000u + z; }
-                for (int z = 0; z < 4; ++z) { p[0][z] = 0x3e000000u + z; p[1][z] = 0x3e100000u + z; }
-#endif
-                if (!DBG(256)) tmem_ld_x4(t_acc, p[0]);
-                if (!DBG(8)) { tmem_ld_x8(t_lane + cj.x, buf[0]); tmem_ld_x4(t_lane + cj.x + 8, buf[0] + 8); }
+                // v_posed of the warp's 8 vertices (2 x 12 accumulator columns) in one go: the accumulator
+                // is handed back to the MMA warp right away, so the MMAs of unit i+2 start ~3000 clk earlier
+                tmem_ld_x8(t_acc, p);           tmem_ld_x4(t_acc + 8, p + 8);
+                tmem_ld_x8(t_acc + 48, p + 12); tmem_ld_x4(t_acc + 56, p + 20);
+                tmem_ld_x8(t_lane + cj.x, buf[0]); tmem_ld_x4(t_lane + cj.x + 8, buf[0] + 8);
+                tmem_ld_wait();
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
                 float res[12];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
@@ -452,9 +455,9 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const int n = k * 4 + q;
-                        if (!DBG(512)) tmem_ld_wait();                // item n (and p of vertex k) have landed
+                        if (n > 0) tmem_ld_wait();                    // item n has landed
                         if (q == 0) {
-                            const uint32_t* pk = p[k & 1];
+                            const uint32_t* pk = p + k * 3;
                             pxx = pack2(pk[0], pk[0]); pyy = pack2(pk[1], pk[1]); pzz = pack2(pk[2], pk[2]);
                             pxy = pack2(pk[0], pk[1]); pz1 = pack2(pk[2], 0x3f800000u);
                         }
@@ -463,18 +466,11 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
                             const uint32_t col = q == 0 ? cj.y : (q == 1 ? cj.z : cj.w);
                             if (!DBG(8)) { tmem_ld_x8(t_lane + col, nb); tmem_ld_x4(t_lane + col + 8, nb + 8); }
                         } else if (k < 7) {
-                            if (!DBG(256)) tmem_ld_x4(t_acc + (uint32_t)(kTileV[k + 1] * 3), p[(k + 1) & 1]);
                             if (!DBG(8)) { tmem_ld_x8(t_lane + cj_next.x, nb); tmem_ld_x4(t_lane + cj_next.x + 8, nb + 8); }
                         }
                         if (DBG(32)) accxy = fma2(ww[q], pack2(buf[n & 1][0], buf[n & 1][11]), accxy);
                         else
                         joint_math(buf[n & 1], ww[q], pxx, pyy, pzz, pxy, pz1, accxy, accz);
-                        if (k == 7 && q == 0) {
-                            // the last accumulator columns are in registers: hand the buffer back to the MMA warp
-                            tcgen05_fence_before();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-                        }
                     }
                     cj = cj_next;
                     float zl, zh;

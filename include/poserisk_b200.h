@@ -154,6 +154,13 @@ int prk_score_euler(const double* d_euler, const prk_addinfo* d_info,
 int prk_euler(const void* d_pose, int pose_dtype, int64_t n_rot, double* d_euler,
               uint8_t* d_bad, void* stream);
 
+/* rot_to_angle (coord_utils.py:24-30, called per frame at base.py:222-231): n_rot row-major 3x3
+ * rotation matrices (float32 or float64, e.g. SPIN's pred_rotmat [B][24][3][3]) -> n_rot rotation
+ * vectors of the same type, cv2.Rodrigues semantics (the matrix is first replaced by its nearest
+ * orthogonal matrix).  d_bad [n_rot] uint8 (1 = singular or non-finite matrix, rvec = 0) or NULL. */
+int prk_rot_to_angle(const void* d_rotmat, int dtype, int64_t n_rot, void* d_rvec, uint8_t* d_bad,
+                     void* stream);
+
 /* The whole per-frame path of lib/core/base.py:225-239,151,168 in one call on device
  * buffers: prk_smpl_forward + prk_score_pose on the same float32 pose. */
 int prk_pipeline(prk_model* model, const float* d_pose, const float* d_betas,

@@ -75,6 +75,17 @@ def euler(pose: np.ndarray):
     return out, bad.reshape(pose.shape[:-1])
 
 
+def rot_to_angle(rotmat: np.ndarray):
+    """rot_to_angle (coord_utils.py:24-30) over (...,3,3) rotation matrices; result has their dtype."""
+    R = np.ascontiguousarray(rotmat)
+    assert R.dtype in (np.float32, np.float64) and R.shape[-2:] == (3, 3)
+    n = R.size // 9
+    out = np.empty(R.shape[:-2] + (3,), R.dtype)
+    bad = np.empty(n, np.uint8)
+    lib().orc_rot_to_angle(_p(R), C.c_int(R.dtype == np.float32), C.c_int64(n), _p(out), _p(bad))
+    return out, bad.reshape(R.shape[:-2])
+
+
 def score_euler(euler_deg: np.ndarray, add_infos, track_of_frame=None) -> np.ndarray:
     e = np.ascontiguousarray(euler_deg, np.float64).reshape(-1, 24, 3)
     info = addinfo_array(add_infos)

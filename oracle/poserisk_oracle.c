@@ -158,6 +158,79 @@ void orc_euler(const void* pose, int is_f32, int64_t n_rot, double* euler, uint8
 }
 
 /* ===========================================================================
+ * rot_to_angle: lib/utils/coord_utils.py:24-30  (cv2.Rodrigues(3x3) -> rotation vector)
+ *
+ * The arithmetic lives in opencv-python (unpinned in requirements.txt:10, 4.13.0 in the build
+ * container), not in the reference tree.  Published algorithm of cv::Rodrigues for a matrix
+ * input (calib3d): convert to double, replace R by the orthogonal factor U*Vt of its SVD,
+ * r = (R21-R12, R02-R20, R10-R01), s = |r|/2, c = (trace-1)/2 clamped to [-1,1], theta = acos(c);
+ * s >= 1e-5: rvec = r * theta/(2s);  s < 1e-5 and c > 0: rvec = 0;  otherwise (theta ~ pi) the
+ * axis comes from the diagonal with signs from R01, R02 (and R12).  The result is converted back
+ * to the input's type.  U*Vt is the orthogonal polar factor of R; it is computed here by Newton's
+ * iteration X <- (X + X^-T)/2 instead of an SVD.  Pinned against cv2 itself: tests/golden/rotmat.npz
+ * (tests/golden/make_golden.py) -- 99.8 % of float32 results are bit-identical, the rest differ by
+ * one float32 ulp (2.4e-7 rad).
+ * ======================================================================== */
+static int inv3_transpose(const double* X, double* Y) {   /* Y = X^-T = cofactor matrix / det; returns 0 if singular */
+    const double c00 = X[4] * X[8] - X[5] * X[7], c01 = X[5] * X[6] - X[3] * X[8], c02 = X[3] * X[7] - X[4] * X[6];
+    const double det = X[0] * c00 + X[1] * c01 + X[2] * c02;
+    if (!(fabs(det) > 1e-300) || !isfinite(det)) return 0;
+    const double id = 1.0 / det;
+    Y[0] = c00 * id; Y[1] = c01 * id; Y[2] = c02 * id;
+    Y[3] = (X[2] * X[7] - X[1] * X[8]) * id; Y[4] = (X[0] * X[8] - X[2] * X[6]) * id; Y[5] = (X[1] * X[6] - X[0] * X[7]) * id;
+    Y[6] = (X[1] * X[5] - X[2] * X[4]) * id; Y[7] = (X[2] * X[3] - X[0] * X[5]) * id; Y[8] = (X[0] * X[4] - X[1] * X[3]) * id;
+    return 1;
+}
+
+/* one matrix (row-major, double) -> rotation vector; returns 1 when the matrix is singular / not finite */
+static int rot_to_angle_one(const double* Rin, double* rvec) {
+    double R[9], Y[9];
+    for (int i = 0; i < 9; ++i) R[i] = Rin[i];
+    for (int it = 0; it < 16; ++it) {                      /* orthogonal polar factor = U*Vt */
+        if (!inv3_transpose(R, Y)) { rvec[0] = rvec[1] = rvec[2] = 0.0; return 1; }
+        double d = 0.0;
+        for (int i = 0; i < 9; ++i) { const double n = 0.5 * (R[i] + Y[i]); d = fmax(d, fabs(n - R[i])); R[i] = n; }
+        if (d < 1e-16) break;
+    }
+    double rx = R[7] - R[5], ry = R[2] - R[6], rz = R[3] - R[1];
+    const double s = sqrt((rx * rx + ry * ry + rz * rz) * 0.25);
+    double c = (R[0] + R[4] + R[8] - 1.0) * 0.5;
+    c = c > 1.0 ? 1.0 : (c < -1.0 ? -1.0 : c);
+    double theta = acos(c);
+    if (s < 1e-5) {
+        if (c > 0) { rx = ry = rz = 0.0; }
+        else {
+            double t = (R[0] + 1.0) * 0.5; rx = sqrt(t > 0.0 ? t : 0.0);
+            t = (R[4] + 1.0) * 0.5; ry = sqrt(t > 0.0 ? t : 0.0) * (R[1] < 0 ? -1.0 : 1.0);
+            t = (R[8] + 1.0) * 0.5; rz = sqrt(t > 0.0 ? t : 0.0) * (R[2] < 0 ? -1.0 : 1.0);
+            if (fabs(rx) < fabs(ry) && fabs(rx) < fabs(rz) && ((R[5] > 0) != (ry * rz > 0))) rz = -rz;
+            theta /= sqrt(rx * rx + ry * ry + rz * rz);
+            rx *= theta; ry *= theta; rz *= theta;
+        }
+    } else {
+        const double vth = theta / (2.0 * s);
+        rx *= vth; ry *= vth; rz *= vth;
+    }
+    rvec[0] = rx; rvec[1] = ry; rvec[2] = rz;
+    return 0;
+}
+
+/* rot_to_angle over n_rot row-major 3x3 matrices (coord_utils.py:24-30); rvec has the matrices' type */
+void orc_rot_to_angle(const void* rotmat, int is_f32, int64_t n_rot, void* rvec, uint8_t* bad) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n_rot; ++i) {
+        double R[9], r[3];
+        for (int k = 0; k < 9; ++k)
+            R[k] = is_f32 ? (double)((const float*)rotmat)[i * 9 + k] : ((const double*)rotmat)[i * 9 + k];
+        const int b = rot_to_angle_one(R, r);
+        for (int k = 0; k < 3; ++k) {
+            if (is_f32) ((float*)rvec)[i * 3 + k] = (float)r[k]; else ((double*)rvec)[i * 3 + k] = r[k];
+        }
+        if (bad) bad[i] = (uint8_t)b;
+    }
+}
+
+/* ===========================================================================
  * REBA: lib/utils/reba.py
  * ======================================================================== */
 static const int8_t REBA_TA[5][3][4] = {  /* reba.py:13-19 */

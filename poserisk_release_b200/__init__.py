@@ -4,14 +4,14 @@ Drop-in surface (same names and call contracts as the reference, see INTEGRATION
     SMPL_Layer                         lib/smplpytorch/smplpytorch/pytorch/smpl_layer.py
     SMPL                               lib/utils/smpl.py
     REBA, RULA                         lib/utils/reba.py, lib/utils/rula.py
-    get_joint_cam, axis_angle_to_euler_angle   lib/utils/coord_utils.py
+    get_joint_cam, rot_to_angle, axis_angle_to_euler_angle   lib/utils/coord_utils.py
 plus the batched :class:`PoseRiskEngine`.  Everything computes in
 csrc/libposerisk_b200.so (hand-written sm_100a CUDA behind a C ABI); importing the
 compute classes without that library raises ImportError.
 """
 from .model_provider import SMPLModelData, get_model_data, synthetic_smpl  # noqa: F401
 
-__all__ = ['SMPL_Layer', 'SMPL', 'REBA', 'RULA', 'get_joint_cam', 'axis_angle_to_euler_angle',
+__all__ = ['SMPL_Layer', 'SMPL', 'REBA', 'RULA', 'get_joint_cam', 'rot_to_angle', 'axis_angle_to_euler_angle',
            'PoseRiskEngine', 'synthetic_smpl', 'get_model_data', 'SMPLModelData']
 
 
@@ -29,7 +29,7 @@ def __getattr__(name):
     if name == 'RULA':
         from .rula import RULA
         return RULA
-    if name in ('get_joint_cam', 'axis_angle_to_euler_angle'):
+    if name in ('get_joint_cam', 'rot_to_angle', 'axis_angle_to_euler_angle'):
         from . import coord_utils
         return getattr(coord_utils, name)
     if name == 'PoseRiskEngine':

@@ -35,7 +35,7 @@ EXPORTS = (
     'prk_abi_version', 'prk_strerror', 'prk_last_error_detail', 'prk_model_create',
     'prk_model_destroy', 'prk_model_device', 'prk_model_max_weights', 'prk_workspace_bytes',
     'prk_smpl_forward', 'prk_score_pose', 'prk_score_euler', 'prk_euler', 'prk_pipeline',
-    'prk_host_workspace_bytes', 'prk_host_scores_offset', 'prk_pipeline_host', 'prk_score_histogram', 'prk_debug_blend',
+    'prk_rot_to_angle', 'prk_host_workspace_bytes', 'prk_host_scores_offset', 'prk_pipeline_host', 'prk_score_histogram', 'prk_debug_blend',
     'prk_vposed_pitch', 'prk_launch_count', 'prk_profile_begin', 'prk_profile_end')
 
 
@@ -80,6 +80,8 @@ def lib():
     L.prk_euler.argtypes = [vp, i32, i64, vp, vp, vp]
     L.prk_pipeline.restype = i32
     L.prk_pipeline.argtypes = [vp, vp, vp, vp, i32, vp, vp, i64, vp, vp, vp, vp, sz, vp]
+    L.prk_rot_to_angle.restype = i32
+    L.prk_rot_to_angle.argtypes = [vp, i32, i64, vp, vp, vp]
     L.prk_host_workspace_bytes.restype = sz
     L.prk_host_workspace_bytes.argtypes = [vp, i64, u32]
     L.prk_host_scores_offset.restype = sz

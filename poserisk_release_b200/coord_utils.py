@@ -1,8 +1,9 @@
 """Drop-ins for the hot-path functions of the reference's ``lib/utils/coord_utils.py``.
 
   get_joint_cam              coord_utils.py:7-21   (SMPL joints in mm, pelvis-relative)
+  rot_to_angle               coord_utils.py:24-30  (cv2.Rodrigues: rotation matrices -> axis-angle)
   axis_angle_to_euler_angle  coord_utils.py:83-95  (cv2.Rodrigues + Euler XYZ, degrees)
-Both are batched on the GPU instead of looping per frame in Python; the results are
+All are batched on the GPU instead of looping per frame in Python; the results are
 what the per-frame loops of the reference produce.
 """
 from __future__ import annotations
@@ -47,6 +48,39 @@ def axis_angle_to_euler_angle(pose):
                 _runtime.ptr(t), _lib.PRK_DTYPE_F32 if t.dtype == torch.float32 else _lib.PRK_DTYPE_F64,
                 n, _runtime.ptr(out), _runtime.ptr(bad), _runtime.stream_ptr(device)))
         assert not bool(bad.any()), 'isRotationMatrix(R) failed'   # coord_utils.py:70
+    return out.cpu().numpy() if return_numpy else out
+
+
+def rot_to_angle(rotmat):
+    """rotmat: (..., 3, 3) rotation matrices, float32 or float64 -- one frame's (24, 3, 3) as in the
+    reference (base.py:226) or a whole batch (N, 24, 3, 3).  Returns the rotation vectors (..., 3) in
+    the input's dtype: a numpy array for numpy input (what the reference returns), a CUDA tensor for
+    tensor input (SPIN's pred_rotmat can stay on the device).  Like cv2.Rodrigues, a matrix that is
+    not exactly orthonormal is first replaced by the nearest orthogonal matrix."""
+    if isinstance(rotmat, torch.Tensor):
+        t = rotmat
+        if t.dtype not in (torch.float32, torch.float64):
+            raise TypeError('rotmat must be float32 or float64')
+        device = _runtime.require_cuda(t.device)
+        t = t.to(device).contiguous()
+        return_numpy = False
+    else:
+        arr = np.asarray(rotmat)
+        if arr.dtype not in (np.float32, np.float64):
+            raise TypeError('rotmat must be float32 or float64 (cv2.Rodrigues accepts nothing else)')
+        device = _runtime.require_cuda(None)
+        t = torch.from_numpy(np.ascontiguousarray(arr)).to(device)
+        return_numpy = True
+    shape = tuple(t.shape)
+    if len(shape) < 2 or shape[-2:] != (3, 3):
+        raise ValueError('rotmat must have trailing dimensions (3, 3)')
+    n = t.numel() // 9
+    out = torch.empty(shape[:-2] + (3,), dtype=t.dtype, device=device)
+    if n > 0:
+        with torch.cuda.device(device):
+            _lib.check(_lib.lib().prk_rot_to_angle(
+                _runtime.ptr(t), _lib.PRK_DTYPE_F32 if t.dtype == torch.float32 else _lib.PRK_DTYPE_F64,
+                n, _runtime.ptr(out), None, _runtime.stream_ptr(device)))
     return out.cpu().numpy() if return_numpy else out
 
 

@@ -465,6 +465,15 @@ int prk_euler(const void* d_pose, int pose_dtype, int64_t n_rot, double* d_euler
     return PRK_OK;
 }
 
+int prk_rot_to_angle(const void* d_rotmat, int dtype, int64_t n_rot, void* d_rvec, uint8_t* d_bad, void* stream) {
+    if (n_rot < 0 || (n_rot > 0 && (!d_rotmat || !d_rvec)) || (dtype != PRK_DTYPE_F32 && dtype != PRK_DTYPE_F64)) {
+        set_detail("prk_rot_to_angle", "invalid argument");
+        return PRK_ERR_INVALID_ARG;
+    }
+    PRK_CUDA(launch_rot_to_angle(d_rotmat, dtype, n_rot, d_rvec, d_bad, static_cast<cudaStream_t>(stream)));
+    return PRK_OK;
+}
+
 int prk_pipeline(prk_model* model, const float* d_pose, const float* d_betas, const float* d_trans, int center_idx,
                  const prk_addinfo* d_info, const int32_t* d_track, int64_t B, float* d_verts, float* d_joints,
                  prk_score_rec* d_scores, void* ws, size_t ws_bytes, void* stream) {

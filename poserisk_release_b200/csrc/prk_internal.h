@@ -124,6 +124,8 @@ cudaError_t launch_score_euler(const double* d_euler, const prk_addinfo* d_info,
                                prk_score_rec* d_out, cudaStream_t s);
 cudaError_t launch_euler(const void* d_pose, int pose_dtype, int64_t n_rot, double* d_euler,
                          uint8_t* d_bad, cudaStream_t s);
+cudaError_t launch_rot_to_angle(const void* d_rotmat, int dtype, int64_t n_rot, void* d_rvec, uint8_t* d_bad,
+                                cudaStream_t s);
 cudaError_t launch_score_hist(const prk_score_rec* d_scores, int64_t B, uint32_t which,
                               unsigned long long* d_hist, cudaStream_t s);
 

@@ -253,6 +253,33 @@ def test_euler_large_vs_oracle_and_asserts():
 
 
 # --------------------------------------------------------------------------- scores
+def test_rot_to_angle_golden_and_oracle():
+    """rot_to_angle drop-in (coord_utils.py:24-30): against the reference's own output (cv2 4.13.0) and
+    the oracle, numpy per-frame call as in base.py:226 and a whole batch as a CUDA tensor."""
+    from poserisk_release_b200 import rot_to_angle, axis_angle_to_euler_angle
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'rotmat.npz'))
+    one = rot_to_angle(g['rotmat'][0])                                   # (24,3,3) numpy -> (24,3) numpy
+    assert isinstance(one, np.ndarray) and one.shape == (24, 3) and one.dtype == np.float32
+    out = rot_to_angle(torch.from_numpy(g['rotmat']).cuda())             # (96,24,3,3) tensor -> tensor
+    assert out.is_cuda and tuple(out.shape) == (96, 24, 3)
+    out = out.cpu().numpy()
+    assert np.array_equal(out[0], one)
+    assert np.abs(out - g['pose']).max() <= 2.4e-7                       # one float32 ulp
+    ref, _ = oracle.rot_to_angle(g['rotmat'])
+    assert np.abs(out - ref).max() <= 2.4e-7 and (out.view(np.uint32) == ref.view(np.uint32)).mean() > 0.998
+    o64 = rot_to_angle(g['rotmat64'])
+    assert o64.dtype == np.float64 and np.abs(o64 - g['pose64']).max() < 1e-6
+    e = axis_angle_to_euler_angle(out)
+    assert np.abs(e - g['euler']).max() < 1e-3                           # the chain of base.py:225-229
+    # large random batch against the oracle
+    rng = np.random.default_rng(3)
+    from scipy.spatial.transform import Rotation
+    R = Rotation.from_rotvec(rng.normal(0, 1.0, (200000, 3))).as_matrix().astype(np.float32)
+    big = rot_to_angle(torch.from_numpy(R).cuda()).cpu().numpy()
+    ref, _ = oracle.rot_to_angle(R)
+    assert np.abs(big - ref).max() <= 4.8e-7
+
+
 def test_reba_rula_dropin_cfg1(golden):
     """REBA()/RULA() __call__ return exactly the reference's list of dicts (config 1)."""
     from poserisk_release_b200 import REBA, RULA

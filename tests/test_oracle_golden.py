@@ -1,5 +1,7 @@
 """Pin the C oracle (oracle/poserisk_oracle.c) against golden vectors produced by the
 unmodified reference (tests/golden/make_golden.py).  Runs on every box, no GPU."""
+import os
+
 import numpy as np
 import pytest
 
@@ -103,3 +105,21 @@ def test_get_joint_cam_golden(golden):
     jc = j * 1000
     jc = jc - jc[:, :1]
     assert np.abs(jc - g['F_joint_cam']).max() / np.abs(g['F_joint_cam']).max() < 1e-5
+
+
+def test_rot_to_angle_golden():
+    """oracle rot_to_angle against the reference's rot_to_angle (cv2.Rodrigues 4.13.0) on float32 and
+    float64 matrices incl. half turns, near-identity and not-quite-orthonormal input; then the chain
+    rot_to_angle -> axis_angle_to_euler_angle of base.py:225-229."""
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'rotmat.npz'))
+    out, bad = oracle.rot_to_angle(g['rotmat'])
+    assert out.dtype == np.float32 and not bad.any()
+    assert np.abs(out - g['pose']).max() <= 2.4e-7                       # one float32 ulp at |rvec| < pi
+    assert (out.view(np.uint32) == g['pose'].view(np.uint32)).mean() > 0.998
+    o64, _ = oracle.rot_to_angle(g['rotmat64'])
+    assert np.abs(o64 - g['pose64']).max() < 1e-6
+    e, _ = oracle.euler(out)
+    assert np.abs(e - g['euler']).max() < 1e-3
+    # singular input is flagged, not propagated
+    _, bad = oracle.rot_to_angle(np.zeros((1, 3, 3), np.float32))
+    assert bad.all()

@@ -180,6 +180,9 @@ class ClockSampler(threading.Thread):
 
 # ----------------------------------------------------------------------------- GPU arm
 def run_gpu_arm(args):
+    if os.environ.get('PRK_BENCH_DEBUG'):      # stacks of every thread after N seconds (hang diagnosis)
+        import faulthandler
+        faulthandler.dump_traceback_later(float(os.environ['PRK_BENCH_DEBUG']), exit=True)
     import torch
     import torch.distributed as dist
     from poserisk_release_b200 import _lib, _runtime
@@ -210,36 +213,25 @@ def run_gpu_arm(args):
     h_joints = torch.empty((B, 24, 3), dtype=torch.float32).pin_memory()
     h_scores = torch.empty((B, 32), dtype=torch.uint8).pin_memory()
 
-    # N > 1: the all-gather of step i's 32-byte score records is issued with async_op=True (it runs on the
-    # process group's own stream) and is waited for one step later, so it overlaps the kernels of step i+1;
-    # every step still gathers inside the timed region and barrier() waits for the last one.
-    pending = []
-
+    # N > 1: every step all-gathers its 32-byte score records on the compute stream, inside the timed region
     def gather_scores(scores_dev):
-        out = torch.empty((world * B, 32), dtype=torch.uint8, device=dev)
-        work = dist.all_gather_into_tensor(out, scores_dev, async_op=True)
-        pending.append((work, out, scores_dev))
-        while len(pending) > 1:
-            pending.pop(0)[0].wait()
+        all_gather_rows(scores_dev, B * world)
 
     def step_device(i):
         p, b, t = dev_in[i % n_rot]
         out = eng.run(p, b, t, add_info=info_dev, verts_out=verts, joints_out=d_joints, scores_out=d_scores)
         if world > 1:
-            # the next step overwrites d_scores: gather a snapshot taken on the compute stream
-            gather_scores(out['scores'].clone())
+            gather_scores(out['scores'])
         return out
 
     def step_host(i):
         p, b, t = host_in[i % n_rot]
         eng.run_host(p, b, t, EXAMPLE_INFO, None, h_joints, h_scores, verts_out=verts)
         if world > 1:
-            gather_scores(eng.host_scores_device.clone())
+            gather_scores(eng.host_scores_device)
 
     def barrier():
         if world > 1:
-            while pending:
-                pending.pop(0)[0].wait()
             torch.cuda.synchronize(dev)
             dist.barrier()
         torch.cuda.synchronize(dev)
@@ -262,11 +254,13 @@ def run_gpu_arm(args):
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-    # preload: keep the GPU busy ~1.5 s so clocks settle and the sampler sees load (not warm-up steps)
+    # preload: keep the GPU busy ~1.5 s so clocks settle and the sampler sees load (not warm-up steps).
+    # Time-bounded, so every rank runs its own number of iterations: NO collective in here.
     t_end = time.perf_counter() + float(os.environ.get('PRK_BENCH_PRELOAD_S', '1.5'))
     i = 0
     while time.perf_counter() < t_end:
-        step_device(i)
+        p, b, t = dev_in[i % n_rot]
+        eng.run(p, b, t, add_info=info_dev, verts_out=verts, joints_out=d_joints, scores_out=d_scores)
         i += 1
         if i % 64 == 0:
             torch.cuda.synchronize(dev)

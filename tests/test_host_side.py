@@ -222,3 +222,28 @@ def test_bench_reference_arm_prints_contract_line():
     assert line['impl'] == 'reference' and line['unit'] == 'frames/s' and line['value'] > 0
     assert line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['cores'] >= 1
     assert line['e2e']['h2d_bytes_per_step'] == 0 and line['e2e']['value'] == line['value']
+
+
+def test_report_writers_known_answers(tmp_path):
+    """report.py (base.py:329-397 text files) without the reference tree: exact cell text and row layout."""
+    import csv
+    from poserisk_release_b200 import report
+    e = np.array([[[1.23456, -0.0004, 179.9996], [0.0, 10.0, -20.5]]])
+    assert report.pose_to_str(e) == [['(1.235, -0.000, 180.000)', '(0.000, 10.000, -20.500)']]
+    ts = (0, np.array([1, 3]), 5)
+    results = [{'score': np.int64(4), 'log_score': [2, 1, 1, '2,3']}, {'score': np.int64(7), 'log_score': [3, 2, 1, '4,4']}]
+    final, scores, logs = report.post_processing(results)
+    assert final[0] == 5.5 and final[3] == 7 and final[4] == 4 and np.isnan(final[2]) and list(scores) == [4, 7]
+    report.save_csv([['a', 'b']] * 2, ts, scores, ['Trunk', 'Neck', 'Leg', 'Arm'], logs,
+                    [{'k1': 'x', 'k2': 'y'}, {'k1': 'z', 'k2': 'w'}], str(tmp_path), title='REBA')
+    rows = list(csv.reader(open(tmp_path / 'REBA_score_log.csv')))
+    assert rows[0] == ['Frame', 'Final_score', 'Joint Score', 'Trunk', 'Neck', 'Leg', 'Arm']
+    assert rows[1] == ['0'] and rows[2] == ['1', '4', '', '2', '1', '1', '2,3'] and rows[4] == ['3', '7', '', '3', '2', '1', '4,4']
+    assert len(rows) == 6
+    rows = list(csv.reader(open(tmp_path / 'REBA_eval_pose_log.csv')))
+    assert rows[0] == ['Frame', '', 'k1', 'k2'] and rows[2] == ['1', '', 'x', 'y']
+    report.save_csv_pose_log([['p0', 'p1', 'p2']] * 2, ts, str(tmp_path), ['Neck'], ['PELVIS', 'NECK', 'HEAD'])
+    rows = list(csv.reader(open(tmp_path / 'pose_log.csv')))
+    assert rows[0] == ['Frame', 'Joint Pose', 'Neck'] and rows[2] == ['1', '', 'p1']
+    txt = report.result_text((5.5, 7.0, float('nan'), 7, 4), 3, 'Medium risk.', 'RULA')
+    assert txt.startswith('AVG Score: 5.5 \n%50 Score: 7.0 \n%10 Score: nan ') and txt.endswith('Action: Medium risk.')

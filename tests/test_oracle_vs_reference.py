@@ -78,3 +78,68 @@ def test_euler_random_and_rotmat_roundtrip():
     e_ref = ref.coord_utils.axis_angle_to_euler_angle(p)
     e, bad = oracle.euler(p)
     assert not bad.any() and np.abs(e - e_ref).max() < 1e-9
+
+
+def test_report_writers_match_reference_text(tmp_path):
+    """report.py against the reference's own writers (lib/core/base.py:329-397, :158-165, :242-271 and
+    lib/utils/vis_utils.py:9-16), run from their source: base.py / vis_utils.py cannot be imported here
+    (matplotlib, SPIN, tracker), so the function bodies are compiled from the files as they are."""
+    import ast, csv, filecmp, os.path as osp
+    from ref_harness import REF_ROOT
+    from poserisk_release_b200 import report
+
+    def functions_of(path, names, cls=None):
+        tree = ast.parse(open(path).read())
+        body = tree.body
+        if cls:
+            body = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == cls).body
+        picked = [n for n in body if isinstance(n, ast.FunctionDef) and n.name in names]
+        mod = ast.Module(body=picked, type_ignores=[])
+        from scipy.stats import mode
+
+        class _Plt:                                # the score plot is out of scope: swallow it
+            def __getattr__(self, _):
+                return lambda *a, **k: None
+        ns = {'np': np, 'csv': csv, 'osp': osp, 'mode': mode, 'plt': _Plt()}
+        exec(compile(mod, path, 'exec'), ns)
+        return ns
+
+    base = functions_of(osp.join(REF_ROOT, 'lib', 'core', 'base.py'),
+                        {'save_csv_pose_log', 'save_csv', 'post_processing'}, cls='Predictor')
+    vis = functions_of(osp.join(REF_ROOT, 'lib', 'utils', 'vis_utils.py'), {'pose_to_str'})
+    ref = load_reference()
+    rng = np.random.default_rng(5)
+    n = 40
+    frames = np.sort(rng.choice(np.arange(3, 60), n, replace=False))
+    timestamp = (0, frames, 64)
+    euler = rng.uniform(-180, 180, (n, 24, 3))
+    with open(os.path.join(REF_ROOT, 'example', 'additional_information.json')) as f:
+        info = json.load(f)
+    pose_str_ref = vis['pose_to_str'](euler)
+    assert report.pose_to_str(euler) == pose_str_ref
+    joints_upper = [j.upper() for j in ref.REBA().joint_name] if hasattr(ref.REBA(), 'joint_name') else None
+    assert joints_upper is not None
+    self_ = types.SimpleNamespace(debug_joints=['Neck', 'L_Shoulder', 'Torso'],
+                                  smpl_model=types.SimpleNamespace(joints_name_upper=joints_upper))
+    d_ref, d_new = tmp_path / 'ref', tmp_path / 'new'
+    d_ref.mkdir(); d_new.mkdir()
+    base['save_csv_pose_log'](self_, pose_str_ref, timestamp, str(d_ref))
+    report.save_csv_pose_log(pose_str_ref, timestamp, str(d_new), self_.debug_joints, joints_upper)
+    assert filecmp.cmp(d_ref / 'pose_log.csv', d_new / 'pose_log.csv', shallow=False)
+    for title, scorer in (('REBA', ref.REBA(True)), ('RULA', ref.RULA(True))):
+        results = scorer(euler, np.zeros((n, 1)), info)
+        fin_ref, sc_ref, lg_ref = base['post_processing'](self_, results, scorer.eval_items, timestamp, str(d_ref), title=title)
+        fin_new, sc_new, lg_new = report.post_processing(results)
+        assert fin_new == fin_ref and (sc_new == sc_ref).all() and (lg_new == lg_ref).all()
+        base['save_csv'](self_, pose_str_ref, timestamp, sc_ref, scorer.eval_items, lg_ref, scorer.log, str(d_ref), title=title)
+        report.save_csv(pose_str_ref, timestamp, sc_new, scorer.eval_items, lg_new, scorer.log, str(d_new), title=title)
+        for name in (title + '_score_log.csv', title + '_eval_pose_log.csv'):
+            assert filecmp.cmp(d_ref / name, d_new / name, shallow=False), name
+    # result text: the reference builds it inline (base.py:162-163 / :179-180); evaluate those very lines
+    lines = open(osp.join(REF_ROOT, 'lib', 'core', 'base.py')).read().split('\n')
+    for title, var in (('REBA', 'reba'), ('RULA', 'rula')):
+        i = next(k for k, l in enumerate(lines) if 'data = f"AVG Score' in l and f'final_score_{var}' in l)
+        expr = (lines[i] + '\n' + lines[i + 1]).strip()[len('data = '):]
+        final = (4.123, 5.5, 7.0, 9, 4)
+        ns = {f'final_score_{var}': final, f'{var}_action_level': 3, f'{var}_action_name': 'Medium risk.'}
+        assert report.result_text(final, 3, 'Medium risk.', title) == eval(expr, ns)

@@ -74,17 +74,26 @@ def make_inputs(seed, B):
 
 
 # ----------------------------------------------------------------------------- CPU arm
-def cpu_throughput(frames, repeats=1):
-    """Oracle port of the reference path (SMPL forward + Euler + REBA + RULA), all host threads."""
-    from oracle import oracle
+def cpu_inputs(frames):
     from poserisk_release_b200.model_provider import synthetic_smpl
-    m = synthetic_smpl('neutral')
-    pose, betas, trans = (x.numpy() for x in make_inputs(1234, frames))
+    return (synthetic_smpl('neutral'),) + tuple(x.numpy() for x in make_inputs(1234, frames))
+
+
+def cpu_step(inputs):
+    """One pass of the oracle port of the reference path (SMPL forward + Euler + REBA + RULA), all host threads."""
+    from oracle import oracle
+    m, pose, betas, trans = inputs
+    oracle.smpl_forward(m, pose, betas, trans)
+    oracle.score_pose(pose, EXAMPLE_INFO)
+
+
+def cpu_throughput(frames, repeats=1):
+    from oracle import oracle
+    inputs = cpu_inputs(frames)
     best = None
     for _ in range(repeats):
         t0 = time.perf_counter()
-        oracle.smpl_forward(m, pose, betas, trans)
-        oracle.score_pose(pose, EXAMPLE_INFO)
+        cpu_step(inputs)
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
     return frames / best, best, oracle.num_threads()
@@ -97,14 +106,15 @@ def run_reference_arm(args):
     from oracle import oracle
     oracle.build()
     oracle.use_all_cores()
-    # size one step so that it takes about a second on this host
-    fps0, _, threads = cpu_throughput(256)
-    frames = int(min(FRAMES_PER_STEP, max(256, fps0 * 1.0)))
+    # one step = the GPU arm's batch (4096 frames), shrunk only if this host needs more than ~2 s for it
+    fps0, _, threads = cpu_throughput(512, repeats=2)
+    frames = int(min(FRAMES_PER_STEP, max(256, fps0 * 2.0)))
+    inputs = cpu_inputs(frames)                      # synthetic inputs are made once, outside the timed steps
     for _ in range(args.warmup):
-        cpu_throughput(frames)
+        cpu_step(inputs)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_throughput(frames)
+        cpu_step(inputs)
     dt = time.perf_counter() - t0
     value = frames * args.steps / dt
     sample = f"{frames} frames per step (same distribution as the GPU arm), {args.steps} steps"

@@ -26,3 +26,14 @@ for name, fn in (('joints + scores', run), ('scores + debug Euler of 4 joints', 
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
     print(f'{name}: {ms:.3f} ms per 1M frames = {n / ms / 1e3:.1f} M frames/s')
+
+# per-kernel split (CUDA-event pairs around each launch)
+import numpy as np
+from poserisk_release_b200 import _lib
+L = _lib.lib()
+_lib.check(L.prk_profile_begin())
+for _ in range(10): run()
+torch.cuda.synchronize()
+ms = np.zeros(4); cnt = np.zeros(4, np.int64)
+_lib.check(L.prk_profile_end(ms.ctypes.data, cnt.ctypes.data))
+print(f'pose chain (joints only): {ms[0] / 10:.3f} ms   scoring: {ms[3] / 10:.3f} ms  per 1M frames')

@@ -7,10 +7,10 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
-LIB = os.path.join(CSRC, 'libposerisk_b200.so')
+# PRK_LIB: development override (A/B runs of kernel variants built by scripts/build_variants.py)
+LIB = os.environ.get('PRK_LIB') or os.path.join(CSRC, 'libposerisk_b200.so')
 
-import os as _os
-NVCC_FLAGS = (['-DPRK_FUSED_DEBUG'] if _os.environ.get('PRK_FUSED_DEBUG') else []) + (['-DPRK_FUSED_SPIN'] if _os.environ.get('PRK_FUSED_SPIN') else []) + ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
+NVCC_FLAGS = (['-DPRK_FUSED_DEBUG'] if os.environ.get('PRK_FUSED_DEBUG') else []) + os.environ.get('PRK_NVCC_EXTRA', '').split() + ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-shared', '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden',
               '--expt-relaxed-constexpr']
 
@@ -20,6 +20,8 @@ def sources():
 
 
 def needs_build() -> bool:
+    if os.environ.get('PRK_LIB'):
+        return not os.path.isfile(LIB)
     if not os.path.isfile(LIB):
         return True
     t = os.path.getmtime(LIB)

@@ -345,8 +345,10 @@ int prk_model_create(prk_model** out, int device, const float* vt, const float* 
             memcpy(base + vl * 16, &wv[(size_t)g * NV + v], 16);
             const uint32_t id = wi[(size_t)g * NV + v];
             uint32_t cols[4];
-            for (int k = 0; k < 4; ++k) cols[k] = ((id >> (8 * k)) & 0xFFu) * 12u;
-            memcpy(base + FUSED_VT * 16 + vl * 16, cols, 16);
+            for (int qc = 0; qc < FUSED_WCOL_COPIES; ++qc) {
+                for (int k = 0; k < 4; ++k) cols[k] = ((id >> (8 * k)) & 0xFFu) * 12u + ((uint32_t)(32 * qc) << 16);
+                memcpy(base + FUSED_VT * 16 * (1 + qc) + vl * 16, cols, 16);
+            }
         }
     }
 

@@ -22,8 +22,11 @@
 //     each B' k-step is multiplied with every A' k-step it pairs with (44 MMAs per unit).
 //   * accumulators are double buffered in TMEM (columns 288..383 / 384..479), so the MMAs of
 //     unit i+1 run under the skinning of unit i.
-//   * vertices leave through a per-warp shared-memory transpose so that every global store
-//     instruction writes contiguous 48-byte runs of a frame's row.
+//   * vertices leave through a staging tile shared by the four warps of a TMEM lane quarter, so every
+//     frame row is written as one 192-byte run, with evict-first stores.
+//   * per (vertex, joint) item the epilogue issues 2 gathers + 6 packed FMAs: x, y are accumulated per
+//     joint, the z row of the blended transform is accumulated first and applied once per vertex; the
+//     per-tile column table holds absolute tensor-memory addresses per lane quarter.
 // HBM traffic per frame: 82,680 B of vertices out, ~2.2 KB of operands in (B' is L2 resident)
 // -> HBM roofline; executed MMA work 216 tiles x 44 MMAs x 2*96*16 = 29.2 MFLOP/frame.
 //
@@ -71,6 +74,11 @@ __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+// 339 MB of vertices stream through the L2 that also holds the 21 MB blend matrix every frame tile re-reads:
+// vertex stores are evict-first (st.global.cs).  (An evict_last hint on the B' loads measured no gain.)
+__device__ __forceinline__ void store_vertex_pair(float* dst, float2 v) {
+    __stcs(reinterpret_cast<float2*>(dst), v);                  // st.global.cs: evict-first
 }
 __device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t* r) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -122,13 +130,18 @@ __device__ __forceinline__ void umma_bf16_lohi(uint32_t d_tmem, uint32_t a_lo, u
 // Build with -DPRK_FUSED_DEBUG to get run-time switches (env PRK_FUSED_DBG) that knock out one side
 // of the pipeline at a time: 1 = no MMAs issued, 2 = epilogue skips gather+math, 4 = no global stores,
 // 8 = no TMEM gather of A_j (math on stale registers), 16 = no B' loads (producer only signals).
+// -DPRK_FUSED_KNOCK: the switches only (no phase timers, which cost ~50 % themselves).
 #ifdef PRK_FUSED_DEBUG
 #define DBG(bit) (dbg & (bit))
 __device__ unsigned long long g_fdbg[8];
 #define TCLK(var) const long long var = clock64()
 #define TACC(k, a, b) t_sum[k] += (b) - (a)
 #else
+#ifdef PRK_FUSED_KNOCK
+#define DBG(bit) (dbg & (bit))
+#else
 #define DBG(bit) 0
+#endif
 #define TCLK(var)
 #define TACC(k, a, b)
 #endif
@@ -162,6 +175,8 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 // kGroups: weight groups of 4 per vertex known at compile time (1 = SMPL), 0 = run-time `groups`
+#define GATHER_ADDR(col) (col)                 // the table holds absolute tensor-memory addresses
+
 template <int kGroups>
 __global__ void __launch_bounds__(kThreads, 1)
 fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid_constant__ CUtensorMap tmap_B,
@@ -217,6 +232,7 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_holder, 0);
+    if (tmem_base != 0) __trap();              // all 512 columns are ours: the allocation can only start at 0
 
     // contiguous unit range of this CTA; unit u = frame tile (u / 216), vertex tile (u % 216)
     const int64_t u0 = (int64_t)blockIdx.x * n_units / gridDim.x;
@@ -401,12 +417,21 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
                 quarter_barrier(quarter);                           // all four warps' columns are staged
                 const int c_first = c_unit + half * 48;             // first vertex coordinate of this half
                 float* vhalf = vrow + half * 48;
+                if (rows_valid == 32 && c_first + 48 <= NVC && !DBG(4)) {   // warp-uniform: all but the edge tiles
 #pragma unroll
-                for (int it = 0; it < 6; ++it) {
-                    const int j = it % 3, up = (it / 3) * 4;
-                    const float2 val = *reinterpret_cast<const float2*>(q_out + rb_smem[j] + up * kOutPitch);
-                    if (rb_row[j] + up < rows_valid && c_first + rb_c2[j] < NVC && !DBG(4))
-                        *reinterpret_cast<float2*>(vhalf + rb_glob[j] + up * NVC) = val;
+                    for (int it = 0; it < 6; ++it) {
+                        const int j = it % 3, up = (it / 3) * 4;
+                        store_vertex_pair(vhalf + rb_glob[j] + up * NVC,
+                                          *reinterpret_cast<const float2*>(q_out + rb_smem[j] + up * kOutPitch));
+                    }
+                } else {
+#pragma unroll
+                    for (int it = 0; it < 6; ++it) {
+                        const int j = it % 3, up = (it / 3) * 4;
+                        const float2 val = *reinterpret_cast<const float2*>(q_out + rb_smem[j] + up * kOutPitch);
+                        if (rb_row[j] + up < rows_valid && c_first + rb_c2[j] < NVC && !DBG(4))
+                            store_vertex_pair(vhalf + rb_glob[j] + up * NVC, val);
+                    }
                 }
                 quarter_barrier(quarter);                           // tile may be overwritten by the next half
                 TCLK(ts1);
@@ -429,7 +454,7 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
                 // n+1 is in flight while item n is multiplied, with two 12-register buffers -- TMEM
                 // read bandwidth is the bound of this kernel, so it must never sit idle.
                 // the warp's k-th vertex is tile vertex 16 (k >> 2) + 4 oct + (k & 3)
-                const uint4* cols = reinterpret_cast<const uint4*>(wslot + 512) + oct * 4;
+                const uint4* cols = reinterpret_cast<const uint4*>(wslot + 512 + (FUSED_WCOL_COPIES > 1 ? quarter * 512 : 0)) + oct * 4;
                 const float4* wgt = reinterpret_cast<const float4*>(wslot) + oct * 4;
                 constexpr int kTileV[8] = {0, 1, 2, 3, 16, 17, 18, 19};
                 uint32_t buf[2][12], p[24];
@@ -439,7 +464,7 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
                 // is handed back to the MMA warp right away, so the MMAs of unit i+2 start ~3000 clk earlier
                 tmem_ld_x8(t_acc, p);           tmem_ld_x4(t_acc + 8, p + 8);
                 tmem_ld_x8(t_acc + 48, p + 12); tmem_ld_x4(t_acc + 56, p + 20);
-                tmem_ld_x8(t_lane + cj.x, buf[0]); tmem_ld_x4(t_lane + cj.x + 8, buf[0] + 8);
+                tmem_ld_x8(GATHER_ADDR(cj.x), buf[0]); tmem_ld_x4(GATHER_ADDR(cj.x) + 8, buf[0] + 8);
                 tmem_ld_wait();
                 tcgen05_fence_before();
                 __syncwarp();
@@ -450,8 +475,9 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
                     const float4 w4 = DBG(64) ? make_float4(.25f, .25f, .25f, .25f) : wgt[kTileV[k]];
                     const uint64_t ww[4] = {pack2f(w4.x, w4.x), pack2f(w4.y, w4.y), pack2f(w4.z, w4.z), pack2f(w4.w, w4.w)};
                     const uint4 cj_next = DBG(64) ? make_uint4(24, 48, 132, 252) : cols[kTileV[k < 7 ? k + 1 : 7]];
-                    uint64_t accxy = pack2f(o0, o1), accz = pack2f(o2, 0.f);
+                    uint64_t accxy = pack2f(o0, o1);
                     uint64_t pxx = 0, pyy = 0, pzz = 0, pxy = 0, pz1 = 0;
+                    uint64_t tz01 = 0, tz23 = pack2f(0.f, o2);       // sum_j w_j (R20, R21) and (R22, t2) [+ offset z]
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const int n = k * 4 + q;
@@ -464,15 +490,23 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
                         uint32_t* nb = buf[(n + 1) & 1];
                         if (q < 3) {
                             const uint32_t col = q == 0 ? cj.y : (q == 1 ? cj.z : cj.w);
-                            if (!DBG(8)) { tmem_ld_x8(t_lane + col, nb); tmem_ld_x4(t_lane + col + 8, nb + 8); }
+                            if (!DBG(8)) { tmem_ld_x8(GATHER_ADDR(col), nb); tmem_ld_x4(GATHER_ADDR(col) + 8, nb + 8); }
                         } else if (k < 7) {
-                            if (!DBG(8)) { tmem_ld_x8(t_lane + cj_next.x, nb); tmem_ld_x4(t_lane + cj_next.x + 8, nb + 8); }
+                            if (!DBG(8)) { tmem_ld_x8(GATHER_ADDR(cj_next.x), nb); tmem_ld_x4(GATHER_ADDR(cj_next.x) + 8, nb + 8); }
                         }
-                        if (DBG(32)) accxy = fma2(ww[q], pack2(buf[n & 1][0], buf[n & 1][11]), accxy);
-                        else
-                        joint_math(buf[n & 1], ww[q], pxx, pyy, pzz, pxy, pz1, accxy, accz);
+                        {   // x, y per joint; the z row is blended first and applied once per vertex:
+                            // 6 packed FMAs per item, every operand straight out of the gather registers
+                            const uint32_t* a = buf[n & 1];
+                            uint64_t xy = fma2(pack2(a[0], a[1]), pxx, pack2(a[6], a[7]));
+                            xy = fma2(pack2(a[2], a[3]), pyy, xy);
+                            xy = fma2(pack2(a[4], a[5]), pzz, xy);
+                            accxy = fma2(ww[q], xy, accxy);
+                            tz01 = q == 0 ? mul2(ww[q], pack2(a[8], a[9])) : fma2(ww[q], pack2(a[8], a[9]), tz01);
+                            tz23 = fma2(ww[q], pack2(a[10], a[11]), tz23);
+                        }
                     }
                     cj = cj_next;
+                    const uint64_t accz = fma2(tz23, pz1, mul2(tz01, pxy));   // (T20 px + T22 pz, T21 py + t2): z = lo + hi
                     float zl, zh;
                     unpack2(accxy, res[(k & 3) * 3 + 0], res[(k & 3) * 3 + 1]);
                     unpack2(accz, zl, zh);
@@ -497,12 +531,12 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
 #pragma unroll 1
                         for (int g = 0; g < groups; ++g) {
                             const uint8_t* wg = wslot + g * FUSED_WGROUP_BYTES;
-                            const uint4 cj = reinterpret_cast<const uint4*>(wg + 512)[vl];      // 12 * joint, 4 joints
+                            const uint4 cj = reinterpret_cast<const uint4*>(wg + 512 + (FUSED_WCOL_COPIES > 1 ? quarter * 512 : 0))[vl];   // 12 * joint, 4 joints
                             uint32_t r[48];
-                            tmem_ld_x8(t_lane + cj.x, r +  0); tmem_ld_x4(t_lane + cj.x + 8, r +  8);
-                            tmem_ld_x8(t_lane + cj.y, r + 12); tmem_ld_x4(t_lane + cj.y + 8, r + 20);
-                            tmem_ld_x8(t_lane + cj.z, r + 24); tmem_ld_x4(t_lane + cj.z + 8, r + 32);
-                            tmem_ld_x8(t_lane + cj.w, r + 36); tmem_ld_x4(t_lane + cj.w + 8, r + 44);
+                            tmem_ld_x8(GATHER_ADDR(cj.x), r +  0); tmem_ld_x4(GATHER_ADDR(cj.x) + 8, r +  8);
+                            tmem_ld_x8(GATHER_ADDR(cj.y), r + 12); tmem_ld_x4(GATHER_ADDR(cj.y) + 8, r + 20);
+                            tmem_ld_x8(GATHER_ADDR(cj.z), r + 24); tmem_ld_x4(GATHER_ADDR(cj.z) + 8, r + 32);
+                            tmem_ld_x8(GATHER_ADDR(cj.w), r + 36); tmem_ld_x4(GATHER_ADDR(cj.w) + 8, r + 44);
                             const float4 w4 = reinterpret_cast<const float4*>(wg)[vl];
                             tmem_ld_wait();
                             if (g == 0) {
@@ -612,6 +646,9 @@ extern "C" __attribute__((visibility("default"))) int prk_fused_debug_read(unsig
 
 int fused_stages(int groups) {
     int stages = kMaxStages;
+#ifdef PRK_STAGE_CAP
+    stages = PRK_STAGE_CAP;
+#endif
     while (stages > 2 && fused_smem_bytes(stages, groups) > kSmemLimit) --stages;
     return stages;
 }
@@ -632,7 +669,7 @@ cudaError_t launch_fused(const Model& m, const CUtensorMap& tmap_A, int64_t rows
         attr_set[m.device] = smem;
     }
     int dbg = 0;
-#ifdef PRK_FUSED_DEBUG
+#if defined(PRK_FUSED_DEBUG) || defined(PRK_FUSED_KNOCK)
     if (const char* e = getenv("PRK_FUSED_DBG")) dbg = atoi(e);
 #endif
     const int64_t n_units = (rows_pad / FUSED_BM) * FUSED_NT;

@@ -49,7 +49,10 @@ constexpr int FUSED_BN = FUSED_VT * 3;   // 96 accumulator columns
 constexpr int FUSED_NT = GEMM_N / FUSED_BN;   // 216 vertex tiles (6912 vertex slots)
 constexpr int FUSED_ASKIN_COLS = NJ * 12;     // 288 TMEM columns of A_j per frame
 // per tile and group of 4 weights: 32 x float4 weights | 32 x uint4 TMEM columns (12 * joint)
-constexpr int FUSED_WGROUP_BYTES = FUSED_VT * 32;
+// ... with the column table repeated per TMEM lane quarter as ABSOLUTE tensor-memory addresses
+// ((32 * quarter) << 16 | 12 * joint; the kernel owns all 512 columns, so its allocation starts at 0)
+constexpr int FUSED_WCOL_COPIES = 4;
+constexpr int FUSED_WGROUP_BYTES = FUSED_VT * 16 * (1 + FUSED_WCOL_COPIES);
 
 // Rest joints as an affine function of betas: J = J_template + Jdirs * beta
 // (folds J_regressor @ (v_template + shapedirs beta), smpl_layer.py:91,95).

@@ -87,6 +87,43 @@ def cpu_step(inputs):
     oracle.score_pose(pose, EXAMPLE_INFO)
 
 
+# every angle threshold of the REBA/RULA ladders, degrees
+THRESHOLDS = np.array([0, 1, -1, 5, -5, 10, -10, 15, -15, 20, -20, 30, 45, -45, 60, -60, 70, -70, 90, -90,
+                       100, -100, 110, -110], dtype=np.float64)
+SCORED_JOINTS = [3, 4, 5, 12, 13, 14, 16, 17, 18, 19, 20, 21]
+
+
+def parity_report(eng, frames, dev):
+    """GPU results against the oracle on the CPU leg's own sample (last row): vertex / joint error,
+    Euler error, exact-match rate of the scores, frames with a scored angle within 1e-3 degrees of a ladder threshold
+    and how many of those differ.  Part of the cpu_baseline leg: the oracle is the checker here, never the product."""
+    import torch
+    from oracle import oracle
+    from poserisk_release_b200 import _runtime
+    m, pose, betas, trans = cpu_inputs(frames)
+    v_ref, j_ref = oracle.smpl_forward(m, pose, betas, trans)
+    rec_ref, eul_ref = oracle.score_pose(pose, EXAMPLE_INFO, want_euler=True)
+    tp = torch.from_numpy(pose).to(dev)
+    out = eng.run(tp, torch.from_numpy(betas).to(dev), torch.from_numpy(trans).to(dev), add_info=EXAMPLE_INFO)
+    _, eul = eng.euler_debug(tp, list(range(24)), EXAMPLE_INFO)
+    torch.cuda.synchronize(dev)
+    v = out['verts'].cpu().numpy(); j = out['joints'].cpu().numpy()
+    rec = _runtime.records_to_numpy(out['scores'])
+    eul = eul.cpu().numpy().reshape(frames, 24, 3)
+    eul_ref = np.asarray(eul_ref).reshape(frames, 24, 3)
+    same = ((rec['reba_score'] == rec_ref['reba_score']) & (rec['rula_score'] == rec_ref['rula_score'])
+            & (rec['reba_parts'] == rec_ref['reba_parts']).all(axis=1) & (rec['rula_parts'] == rec_ref['rula_parts']).all(axis=1))
+    used = eul_ref[:, SCORED_JOINTS, :].reshape(frames, -1)
+    near = (np.abs(used[:, :, None] - THRESHOLDS[None, None, :]).min(axis=2) < 1e-3).any(axis=1)
+    return {"frames": int(frames), "against": "oracle/poserisk_oracle.c on the same inputs",
+            "verts_max_abs_over_max_abs_ref": float(np.abs(v - v_ref).max() / np.abs(v_ref).max()),
+            "verts_frobenius_rel": float(np.linalg.norm((v - v_ref).ravel()) / np.linalg.norm(v_ref.ravel())),
+            "joints_max_abs_over_max_abs_ref": float(np.abs(j - j_ref).max() / np.abs(j_ref).max()),
+            "euler_max_abs_err_deg": float(np.abs(eul - eul_ref).max()),
+            "scores_exact_match_rate": float(same.mean()),
+            "frames_near_threshold_1e-3deg": int(near.sum()), "of_those_differing": int((near & ~same).sum())}
+
+
 def cpu_throughput(frames, repeats=1):
     from oracle import oracle
     inputs = cpu_inputs(frames)
@@ -324,13 +361,14 @@ def run_gpu_arm(args):
                                   "note": "bf16 split precision (hi*hi + lo*hi + hi*lo, 3-way for betas) + N padding: "
                                           "29.2 MFLOP executed per 8.97 MFLOP algorithmic"},
                  "peak_source": peaks['source'] + " (sustained bf16, kernel timed inside a long step)"}
-        cpu_baseline = None
+        cpu_baseline = parity = None
         if world == 1:   # bounded CPU sample of the same workload (rank 0 at N=1 only)
             from oracle import oracle
             oracle.use_all_cores()
             fps0, _, threads = cpu_throughput(256)
             n_cpu = int(min(8 * FRAMES_PER_STEP, max(512, fps0 * 12)))
             cpu_fps, cpu_dt, threads = cpu_throughput(n_cpu)
+            parity = parity_report(eng, min(n_cpu, FRAMES_PER_STEP), dev)
             cpu_baseline = {"value": cpu_fps, "unit": UNIT, "cores": threads, "kind": "port",
                             "sample": f"{n_cpu} frames of the same workload, {cpu_dt:.1f} s, C/OpenMP oracle "
                                       f"port of the reference path (oracle/poserisk_oracle.c)"}
@@ -343,7 +381,7 @@ def run_gpu_arm(args):
                         "note": "vertices stay in HBM (the reference reads them only for a debug .obj)"},
                 "gpu_launches": int(launches),
                 "roofline": dominant, "roofline_other": other, "stages": per_stage,
-                "cpu_baseline": cpu_baseline}
+                "cpu_baseline": cpu_baseline, "parity": parity}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

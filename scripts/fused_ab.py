@@ -39,6 +39,14 @@ def worker():
         run(i)
     torch.cuda.synchronize()
     best = None
+    nv = None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        nv = pynvml.nvmlDeviceGetHandleByIndex(0)
+    except Exception:
+        pass
+    clk = pw = 0
     for rep in range(3):
         _lib.check(L.prk_profile_begin())
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -46,6 +54,11 @@ def worker():
         for i in range(steps):
             run(i)
         e1.record()
+        if nv is not None and steps >= 1000:      # long runs: clocks / power while the queue is still draining
+            import time
+            time.sleep(0.05)
+            clk = pynvml.nvmlDeviceGetClockInfo(nv, pynvml.NVML_CLOCK_SM)
+            pw = pynvml.nvmlDeviceGetPowerUsage(nv) / 1000.0
         torch.cuda.synchronize()
         ms = np.zeros(4); n = np.zeros(4, np.int64)
         _lib.check(L.prk_profile_end(ms.ctypes.data, n.ctypes.data))
@@ -57,8 +70,8 @@ def worker():
     torch.cuda.synchronize()
     v = verts.double()
     chk = float(v.sum().item()); chk2 = float((v * v).sum().item())
-    print('fused best %.1f last %.1f us | pose %.1f score %.1f | step %.1f us | checksum %.9e %.9e'
-          % (best[1], last[0][1], last[0][0], last[0][3], last[1], chk, chk2), flush=True)
+    print('fused best %.1f last %.1f us | pose %.1f score %.1f | step %.1f us | checksum %.9e %.9e | %d MHz %.0f W'
+          % (best[1], last[0][1], last[0][0], last[0][3], last[1], chk, chk2, clk, pw), flush=True)
 
 
 if __name__ == '__main__':

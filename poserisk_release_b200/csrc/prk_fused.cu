@@ -23,7 +23,9 @@
 //   * accumulators are double buffered in TMEM (columns 288..383 / 384..479), so the MMAs of
 //     unit i+1 run under the skinning of unit i.
 //   * vertices leave through a staging tile shared by the four warps of a TMEM lane quarter, so every
-//     frame row is written as one 192-byte run, with evict-first stores.
+//     frame row is written as one 192-byte run, with evict-first stores; the read-back + store of a half
+//     unit is issued in the middle of the next half's gathers, and the tile is handed over through
+//     split-phase mbarriers, so the store phase hides under the tensor-memory gathers.
 //   * per (vertex, joint) item the epilogue issues 2 gathers + 6 packed FMAs: x, y are accumulated per
 //     joint, the z row of the blended transform is accumulated first and applied once per vertex; the
 //     per-tile column table holds absolute tensor-memory addresses per lane quarter.
@@ -59,7 +61,7 @@ constexpr int kOutBytesPerQuarter = 32 * kOutPitch * 4;          // 32 frames of
 constexpr int kOutBytes = 4 * kOutBytesPerQuarter;               // 26,624
 constexpr int kWSlots = 4;
 constexpr int kMaxStages = 6;
-constexpr int kNumBars = 2 * kMaxStages + 2 * kEpiWarps + 2 + kWSlots + 2;
+constexpr int kNumBars = 2 * kMaxStages + 2 * kEpiWarps + 2 + kWSlots + 2 + 8;
 constexpr int kThreads = (kEpiWarps + 2) * 32;                   // 576
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kAccCol0 = 288;                               // accumulators behind the 24 x 12 A_j columns
@@ -202,7 +204,11 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
     uint64_t* wfull_bar = tempty_bar + 2;                         // [kWSlots]
     uint64_t* afull_bar = wfull_bar + kWSlots;
     uint64_t* aempty_bar = afull_bar + 1;
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(aempty_bar + 1);
+    // staging tile of a lane quarter: "staged" (all four warps wrote half h) / "flushed" (all four read it back);
+    // arrive and wait are far apart in the instruction stream, so the four warps need not run in lock-step
+    uint64_t* qstaged_bar = aempty_bar + 1;                       // [4 quarters]
+    uint64_t* qflushed_bar = qstaged_bar + 4;                     // [4 quarters]
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(qflushed_bar + 4);
 
     // The warp index is broadcast from lane 0 so the compiler knows it is warp-uniform: role
     // branches stay convergent and the MMA / TMA warps compute their operands in uniform registers.
@@ -220,6 +226,7 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
         for (int i = 0; i < kWSlots; ++i) mbar_init(&wfull_bar[i], 1);
         mbar_init(afull_bar, 1);
         mbar_init(aempty_bar, 1);
+        for (int i = 0; i < 4; ++i) { mbar_init(&qstaged_bar[i], 4); mbar_init(&qflushed_bar[i], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kEpiWarps + 1) {
@@ -357,6 +364,26 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
             rb_glob[it] = rb_row[it] * NVC + rb_c2[it];           // float offset from the tile's first frame row
         }
 
+        // Deferred read-back (kGroups == 1): the global stores of a staged half are issued in the middle of the NEXT
+        // half's gather + math, so the store phase of a lane quarter runs under its tensor-memory gathers instead of
+        // after them.  `pend` = first element of the pending half's frame rows (nullptr: nothing pending).  The tile
+        // hand-over between the four warps uses two mbarriers per quarter ("staged", "flushed") whose arrive and wait
+        // sit half a half apart, so a warp rarely blocks and the four warps drift apart instead of marching in lock-step.
+        float* pend = nullptr;
+        uint32_t n_staged = 0;                                        // halves this warp has staged so far
+        auto flush_pending = [&]() {
+            if (pend == nullptr) return;                              // warp-uniform
+            MBAR_WAIT(&qstaged_bar[quarter], (n_staged - 1) & 1);    // all four warps staged the pending half
+#pragma unroll
+            for (int it = 0; it < 6; ++it) {
+                const int j = it % 3, up = (it / 3) * 4;
+                store_vertex_pair(pend + rb_glob[j] + up * NVC,
+                                  *reinterpret_cast<const float2*>(q_out + rb_smem[j] + up * kOutPitch));
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&qflushed_bar[quarter]);      // my rows of that half are in registers / on their way
+            pend = nullptr;
+        };
         int64_t ft = ft0; int vt = vt0;
         float o0 = 0.f, o1 = 0.f, o2 = 0.f;
 #ifdef PRK_FUSED_DEBUG
@@ -472,6 +499,7 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
                 float res[12];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
+                    if ((k & 3) == 1) flush_pending();              // the previous half leaves under this half's gathers
                     const float4 w4 = DBG(64) ? make_float4(.25f, .25f, .25f, .25f) : wgt[kTileV[k]];
                     const uint64_t ww[4] = {pack2f(w4.x, w4.x), pack2f(w4.y, w4.y), pack2f(w4.z, w4.z), pack2f(w4.w, w4.w)};
                     const uint4 cj_next = DBG(64) ? make_uint4(24, 48, 132, 252) : cols[kTileV[k < 7 ? k + 1 : 7]];
@@ -514,7 +542,31 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
                     if ((k & 3) == 3) {
                         TCLK(tg1);
                         TACC(2, tg0, tg1);
-                        store_half(res, k >> 2);
+                        const int half = k >> 2;
+                        if (n_staged > 0) MBAR_WAIT(&qflushed_bar[quarter], (n_staged - 1) & 1);   // tile is free
+                        float4* dst = reinterpret_cast<float4*>(q_out + lane * kOutPitch + oct * 12);
+                        dst[0] = make_float4(res[0], res[1], res[2], res[3]);
+                        dst[1] = make_float4(res[4], res[5], res[6], res[7]);
+                        dst[2] = make_float4(res[8], res[9], res[10], res[11]);
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&qstaged_bar[quarter]);
+                        ++n_staged;
+                        const int c_first = c_unit + half * 48;
+                        float* vhalf = vrow + half * 48;
+                        if (rows_valid == 32 && c_first + 48 <= NVC) {
+                            pend = vhalf;                           // interior tile: stored during the next half
+                        } else {                                    // edge tile: predicated stores right away
+                            MBAR_WAIT(&qstaged_bar[quarter], (n_staged - 1) & 1);
+#pragma unroll
+                            for (int it = 0; it < 6; ++it) {
+                                const int j = it % 3, up = (it / 3) * 4;
+                                const float2 val = *reinterpret_cast<const float2*>(q_out + rb_smem[j] + up * kOutPitch);
+                                if (rb_row[j] + up < rows_valid && c_first + rb_c2[j] < NVC)
+                                    store_vertex_pair(vhalf + rb_glob[j] + up * NVC, val);
+                            }
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&qflushed_bar[quarter]);
+                        }
                     }
                 }
             } else {
@@ -563,6 +615,7 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
             }
             if (++vt == FUSED_NT) { vt = 0; ++ft; }
         }
+        flush_pending();
 #ifdef PRK_FUSED_DEBUG
         if (lane == 0) {
             t_sum[4] = clock64() - t_begin;

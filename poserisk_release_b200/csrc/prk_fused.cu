@@ -431,7 +431,12 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
             const uint32_t t_acc = t_lane + kAccCol0 + (uint32_t)acc * FUSED_BN + (uint32_t)(oct * 12);
             const int c_unit = vt * FUSED_VT * 3;                   // first vertex coordinate of the tile
             float* vrow = verts + (size_t)(ft * FUSED_BM + quarter * 32) * NVC + c_unit;
-            const int rows_valid = (int)((B - (ft * FUSED_BM + quarter * 32)) < 32 ? (B - (ft * FUSED_BM + quarter * 32)) : 32);
+            // recomputed where it is used (two integer ops) instead of living in a register across the unit body
+            auto rows_valid_now = [&]() {
+                const int left = (int)B - ((int)ft * FUSED_BM + quarter * 32);
+                return left < 32 ? left : 32;
+            };
+#define rows_valid rows_valid_now()
 
             // transposed store of the quarter's 16 finished vertices (48 floats per frame) of half unit `half`
             auto store_half = [&](const float* res, int half) {
@@ -484,18 +489,15 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
                 const uint4* cols = reinterpret_cast<const uint4*>(wslot + 512 + (FUSED_WCOL_COPIES > 1 ? quarter * 512 : 0)) + oct * 4;
                 const float4* wgt = reinterpret_cast<const float4*>(wslot) + oct * 4;
                 constexpr int kTileV[8] = {0, 1, 2, 3, 16, 17, 18, 19};
-                uint32_t buf[2][12], p[24];
+                uint32_t buf[2][12], p[12];
                 uint4 cj = DBG(64) ? make_uint4(12, 36, 120, 240) : cols[0];
                 TCLK(tg0);
-                // v_posed of the warp's 8 vertices (2 x 12 accumulator columns) in one go: the accumulator
-                // is handed back to the MMA warp right away, so the MMAs of unit i+2 start ~3000 clk earlier
-                tmem_ld_x8(t_acc, p);           tmem_ld_x4(t_acc + 8, p + 8);
-                tmem_ld_x8(t_acc + 48, p + 12); tmem_ld_x4(t_acc + 56, p + 20);
+                // v_posed of the warp's 4 vertices of a half (12 accumulator columns) at a time: 12 registers instead
+                // of 24 (the kernel sits at the 96-register cap of an 18-warp CTA).  The accumulator goes back to the
+                // MMA warp once the second half's columns are in registers; the other buffer serves unit i+1 meanwhile.
+                tmem_ld_x8(t_acc, p); tmem_ld_x4(t_acc + 8, p + 8);
                 tmem_ld_x8(GATHER_ADDR(cj.x), buf[0]); tmem_ld_x4(GATHER_ADDR(cj.x) + 8, buf[0] + 8);
                 tmem_ld_wait();
-                tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
                 float res[12];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
@@ -510,8 +512,13 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
                     for (int q = 0; q < 4; ++q) {
                         const int n = k * 4 + q;
                         if (n > 0) tmem_ld_wait();                    // item n has landed
+                        if (n == 16) {                                // ... and so have the second half's v_posed columns
+                            tcgen05_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                        }
                         if (q == 0) {
-                            const uint32_t* pk = p + k * 3;
+                            const uint32_t* pk = p + (k & 3) * 3;
                             pxx = pack2(pk[0], pk[0]); pyy = pack2(pk[1], pk[1]); pzz = pack2(pk[2], pk[2]);
                             pxy = pack2(pk[0], pk[1]); pz1 = pack2(pk[2], 0x3f800000u);
                         }
@@ -543,6 +550,7 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
                         TCLK(tg1);
                         TACC(2, tg0, tg1);
                         const int half = k >> 2;
+                        if (k == 3) { tmem_ld_x8(t_acc + 48, p); tmem_ld_x4(t_acc + 56, p + 8); }   // next half's v_posed
                         if (n_staged > 0) MBAR_WAIT(&qflushed_bar[quarter], (n_staged - 1) & 1);   // tile is free
                         float4* dst = reinterpret_cast<float4*>(q_out + lane * kOutPitch + oct * 12);
                         dst[0] = make_float4(res[0], res[1], res[2], res[3]);
@@ -613,6 +621,7 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
                     store_half(res, half);
                 }
             }
+#undef rows_valid
             if (++vt == FUSED_NT) { vt = 0; ++ft; }
         }
         flush_pending();

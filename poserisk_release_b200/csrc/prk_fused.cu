@@ -239,6 +239,9 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_holder, 0);
+    // everything above ran while the previous kernel of the stream (the pose chain) was still draining; its
+    // outputs (A' rows, A_j tiles, offsets) are visible from here on (no-op without a programmatic dependency)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (tmem_base != 0) __trap();              // all 512 columns are ours: the allocation can only start at 0
 
     // contiguous unit range of this CTA; unit u = frame tile (u / 216), vertex tile (u % 216)
@@ -737,14 +740,30 @@ cudaError_t launch_fused(const Model& m, const CUtensorMap& tmap_A, int64_t rows
     const int64_t n_units = (rows_pad / FUSED_BM) * FUSED_NT;
     int grid = m.sm_count > 0 ? m.sm_count : 148;
     if (grid > n_units) grid = (int)n_units;
+    // Programmatic dependent launch: the CTAs become resident and run their prologue (barrier init, tensor-memory
+    // allocation, descriptor prefetch) while the pose-chain kernel in front of them drains; every thread passes
+    // griddepcontrol.wait before it touches that kernel's outputs.  PRK_PDL=0 launches without the attribute.
+    static const bool pdl = [] { const char* e = getenv("PRK_PDL"); return !e || atoi(e) != 0; }();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    const uint8_t* wpack = m.d_wpack;
+    cudaError_t e;
     if (groups == 1)
-        fused_blend_skin_kernel<1><<<grid, kThreads, smem, s>>>(tmap_A, m.tmap_B2, d_AskinT, d_off, m.d_wpack, groups, stages,
-                                                                B, n_units, d_verts, dbg);
+        e = cudaLaunchKernelEx(&cfg, fused_blend_skin_kernel<1>, tmap_A, m.tmap_B2, d_AskinT, d_off, wpack, groups, stages, B,
+                               n_units, d_verts, dbg);
     else
-        fused_blend_skin_kernel<0><<<grid, kThreads, smem, s>>>(tmap_A, m.tmap_B2, d_AskinT, d_off, m.d_wpack, groups, stages,
-                                                                B, n_units, d_verts, dbg);
+        e = cudaLaunchKernelEx(&cfg, fused_blend_skin_kernel<0>, tmap_A, m.tmap_B2, d_AskinT, d_off, wpack, groups, stages, B,
+                               n_units, d_verts, dbg);
     count_launch();
-    return cudaGetLastError();
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 }  // namespace prk

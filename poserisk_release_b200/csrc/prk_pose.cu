@@ -270,6 +270,9 @@ pose_chain_warp_kernel(const float* __restrict__ Jc /* J_template[72] | Jdirs[72
     if (!kMesh && !valid) return;
     const int64_t f = valid ? f_own : B - 1;
     const unsigned FULL = 0xffffffffu;
+    // the vertex kernel behind this one is launched with a programmatic dependency: let its CTAs become resident and
+    // run their prologue as soon as SMs free up (it waits with griddepcontrol.wait before reading our outputs)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     bool frame_betas = (mode & MODE_FRAME_BETAS_ALWAYS) != 0;
     bool add_trans = (mode & MODE_TRANS_ALWAYS) != 0;

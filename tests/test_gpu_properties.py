@@ -121,3 +121,30 @@ def test_joints_only_one_million_frames_with_debug_euler(engine):
         small = engine.run(pose[lo:lo + 700], betas[lo:lo + 700], None, add_info=EXAMPLE_INFO, want_verts=False)
         assert torch.equal(small['joints'], out['joints'][lo:lo + 700])
         assert torch.equal(small['scores'], out['scores'][lo:lo + 700])
+
+
+@pytest.mark.parametrize('B', [1, 33, 129, 4096 + 77])
+def test_vertex_stores_stay_inside_the_output(engine, B):
+    """The vertex kernel stores frame rows in 8-byte pieces, part of them deferred into the next work unit
+    (prk_fused.cu): a guard band on either side of the output must stay untouched, every output element
+    must be written, and a second run into a NaN-filled buffer must give the same bits (no stale or missing
+    store), for ragged batches whose last frame tile and last vertex tile are partial."""
+    g = torch.Generator().manual_seed(B)
+    pose = (torch.randn(B, 72, generator=g) * 0.35).cuda()
+    betas = torch.randn(B, 10, generator=g).cuda()
+    trans = (torch.randn(B, 3, generator=g) * 0.1).cuda()
+    n, pad = B * 6890 * 3, 4096
+    runs = []
+    for fill in (float('nan'), 12345.0):
+        flat = torch.full((n + 2 * pad,), fill, dtype=torch.float32, device='cuda')
+        view = flat[pad:pad + n].view(B, 6890, 3)
+        out = engine.run(pose, betas, trans, add_info=EXAMPLE_INFO, verts_out=view)
+        torch.cuda.synchronize()
+        assert out['verts'].data_ptr() == view.data_ptr()
+        guard = torch.cat([flat[:pad], flat[pad + n:]])
+        assert bool(torch.isnan(guard).all()) if fill != fill else bool((guard == fill).all())
+        body = flat[pad:pad + n]
+        assert not bool(torch.isnan(body).any())
+        assert not bool((body == 12345.0).any())
+        runs.append(body.clone())
+    assert torch.equal(runs[0], runs[1])

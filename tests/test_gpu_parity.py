@@ -486,3 +486,30 @@ def test_launch_counter_counts_our_kernels(engine):
     engine.run(pose, add_info=EXAMPLE_INFO)
     torch.cuda.synchronize()
     assert _lib.launch_count() - before == 3      # pose chain, fused blend GEMM + skinning, scoring
+
+
+def test_forward_with_a_small_workspace_runs_in_chunks(engine):
+    """prk_smpl_forward shrinks its launch pairs (pose chain -> vertex kernel, chained by a programmatic dependent
+    launch) to what the caller's workspace holds: a workspace sized for 256 frames must give the same bits for
+    700 frames as the usual one-pair run."""
+    from poserisk_release_b200 import _lib, _runtime
+    L = _lib.lib()
+    h = engine.models['neutral']
+    B = 700
+    g = torch.Generator().manual_seed(5)
+    pose = (torch.randn(B, 72, generator=g) * 0.35).cuda()
+    betas = torch.randn(B, 10, generator=g).cuda()
+    trans = (torch.randn(B, 3, generator=g) * 0.1).cuda()
+    ref = engine.run(pose, betas, trans, add_info=EXAMPLE_INFO)
+    torch.cuda.synchronize()
+    small = int(L.prk_workspace_bytes(h.handle, 256, 0))
+    assert small < int(L.prk_workspace_bytes(h.handle, B, 0))
+    buf = torch.empty(small + 1024, dtype=torch.uint8, device='cuda')
+    ws = C.c_void_p(buf.data_ptr() + (-buf.data_ptr()) % 1024)
+    verts = torch.full((B, 6890, 3), float('nan'), device='cuda')
+    joints = torch.empty((B, 24, 3), device='cuda')
+    _lib.check(L.prk_smpl_forward(h.handle, _runtime.ptr(pose), _runtime.ptr(betas), _runtime.ptr(trans), -1, B,
+                                  _runtime.ptr(verts), _runtime.ptr(joints), ws, small,
+                                  _runtime.stream_ptr(torch.device('cuda:0'))))
+    torch.cuda.synchronize()
+    assert torch.equal(verts, ref['verts']) and torch.equal(joints, ref['joints'])

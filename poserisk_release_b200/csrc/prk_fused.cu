@@ -435,11 +435,10 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
             const int c_unit = vt * FUSED_VT * 3;                   // first vertex coordinate of the tile
             float* vrow = verts + (size_t)(ft * FUSED_BM + quarter * 32) * NVC + c_unit;
             // recomputed where it is used (two integer ops) instead of living in a register across the unit body
-            auto rows_valid_now = [&]() {
+            auto rows_valid = [&]() {
                 const int left = (int)B - ((int)ft * FUSED_BM + quarter * 32);
                 return left < 32 ? left : 32;
             };
-#define rows_valid rows_valid_now()
 
             // transposed store of the quarter's 16 finished vertices (48 floats per frame) of half unit `half`
             auto store_half = [&](const float* res, int half) {
@@ -452,7 +451,7 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
                 quarter_barrier(quarter);                           // all four warps' columns are staged
                 const int c_first = c_unit + half * 48;             // first vertex coordinate of this half
                 float* vhalf = vrow + half * 48;
-                if (rows_valid == 32 && c_first + 48 <= NVC && !DBG(4)) {   // warp-uniform: all but the edge tiles
+                if (rows_valid() == 32 && c_first + 48 <= NVC && !DBG(4)) {   // warp-uniform: all but the edge tiles
 #pragma unroll
                     for (int it = 0; it < 6; ++it) {
                         const int j = it % 3, up = (it / 3) * 4;
@@ -464,7 +463,7 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
                     for (int it = 0; it < 6; ++it) {
                         const int j = it % 3, up = (it / 3) * 4;
                         const float2 val = *reinterpret_cast<const float2*>(q_out + rb_smem[j] + up * kOutPitch);
-                        if (rb_row[j] + up < rows_valid && c_first + rb_c2[j] < NVC && !DBG(4))
+                        if (rb_row[j] + up < rows_valid() && c_first + rb_c2[j] < NVC && !DBG(4))
                             store_vertex_pair(vhalf + rb_glob[j] + up * NVC, val);
                     }
                 }
@@ -564,7 +563,7 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
                         ++n_staged;
                         const int c_first = c_unit + half * 48;
                         float* vhalf = vrow + half * 48;
-                        if (rows_valid == 32 && c_first + 48 <= NVC) {
+                        if (rows_valid() == 32 && c_first + 48 <= NVC) {
                             pend = vhalf;                           // interior tile: stored during the next half
                         } else {                                    // edge tile: predicated stores right away
                             MBAR_WAIT(&qstaged_bar[quarter], (n_staged - 1) & 1);
@@ -572,7 +571,7 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
                             for (int it = 0; it < 6; ++it) {
                                 const int j = it % 3, up = (it / 3) * 4;
                                 const float2 val = *reinterpret_cast<const float2*>(q_out + rb_smem[j] + up * kOutPitch);
-                                if (rb_row[j] + up < rows_valid && c_first + rb_c2[j] < NVC)
+                                if (rb_row[j] + up < rows_valid() && c_first + rb_c2[j] < NVC)
                                     store_vertex_pair(vhalf + rb_glob[j] + up * NVC, val);
                             }
                             __syncwarp();
@@ -624,7 +623,6 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
                     store_half(res, half);
                 }
             }
-#undef rows_valid
             if (++vt == FUSED_NT) { vt = 0; ++ft; }
         }
         flush_pending();

@@ -289,9 +289,10 @@ int prk_model_create(prk_model** out, int device, const float* vt, const float* 
         }
 
     // K12 operand (prk_internal.h "K12 operand layout"): every hi/lo part stored once
-    std::vector<uint16_t> B2((size_t)GEMM_N * FUSED_K, 0);
+    std::vector<uint16_t> B2((size_t)GEMM_N * FUSED_K, 0), B2row(FUSED_K);
     for (int n = 0; n < NVC; ++n) {
-        uint16_t* row = &B2[(size_t)n * FUSED_K];
+        uint16_t* row = B2row.data();
+        std::fill(B2row.begin(), B2row.end(), (uint16_t)0);
         for (int pos = 1; pos < NJ; ++pos) {
             const int j = std_tree ? kSmplDfs[pos] : pos;
             for (int e = 0; e < 9; ++e) {
@@ -310,6 +311,7 @@ int prk_model_create(prk_model** out, int device, const float* vt, const float* 
         }
         split3(vt[n], sp[0], sp[1], sp[2]);
         x[15] = sp[0]; x[32 + 15] = sp[1]; x[48 + 15] = sp[2];
+        for (int k = 0; k < FUSED_K; ++k) B2[fused_b2_index(n, k)] = row[k];   // into the pre-swizzled chunk images
     }
 
     // compacted skinning weights
@@ -376,8 +378,6 @@ int prk_model_create(prk_model** out, int device, const float* vt, const float* 
     PRK_M(cudaEventCreateWithFlags(&m->ev_joints, cudaEventDisableTiming));
     PRK_M(cudaEventCreateWithFlags(&m->ev_out, cudaEventDisableTiming));
 #undef PRK_M
-    int rc = encode_tmap_2d_bf16(&m->tmap_B2, m->d_B2, GEMM_N, FUSED_K, FUSED_BN, 64);
-    if (rc != PRK_OK) { prk_model_destroy(m); return rc; }
     *out = m;
     return PRK_OK;
 }

@@ -20,6 +20,7 @@
 //     layout"): the A' tile of the 128 frames stays resident in shared
 //     memory for the whole frame tile (28 k-steps, 112 KB), only the 12 KB B' chunks stream through a TMA ring, and
 //     each B' k-step is multiplied with every A' k-step it pairs with (44 MMAs per unit).
+//   * B' is stored as pre-swizzled chunk images, so every 12 KB chunk arrives with one linear bulk copy.
 //   * accumulators are double buffered in TMEM (columns 288..383 / 384..479), so the MMAs of
 //     unit i+1 run under the skinning of unit i.
 //   * vertices leave through a staging tile shared by the four warps of a TMEM lane quarter, so every
@@ -181,7 +182,7 @@ __device__ __forceinline__ bool elect_one() {
 
 template <int kGroups>
 __global__ void __launch_bounds__(kThreads, 1)
-fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid_constant__ CUtensorMap tmap_B,
+fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const uint16_t* __restrict__ B2img,
                         const float* __restrict__ AskinT, const float* __restrict__ off,
                         const uint8_t* __restrict__ wpack, int groups_rt, int stages, int64_t B, int64_t n_units,
                         float* __restrict__ verts, int dbg) {
@@ -219,7 +220,6 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
 
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_A)) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_B)) : "memory");
         for (int i = 0; i < kMaxStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
         for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&tfull_bar[i], 1);
         for (int i = 0; i < 2; ++i) mbar_init(&tempty_bar[i], kEpiWarps);
@@ -282,8 +282,10 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
                 if (elect_one()) {
                     if (DBG(16)) { mbar_arrive(&full_bar[stage]); }
                     else {
+                        // one contiguous 12 KB block of the pre-swizzled B' image (prk_internal.h fused_b2_index)
                         mbar_expect_tx(&full_bar[stage], kBChunkBytes);
-                        tma_load_2d(&tmap_B, &full_bar[stage], sB + stage * kBChunkBytes, c * 64, vt * FUSED_BN);
+                        bulk_load_1d(sB + stage * kBChunkBytes,
+                                     B2img + ((size_t)vt * FUSED_B_CHUNKS + c) * (kBChunkBytes / 2), kBChunkBytes, &full_bar[stage]);
                     }
                 }
                 if (++stage == stages) { stage = 0; phase ^= 1; }
@@ -652,10 +654,9 @@ blend_simt_kernel(const uint16_t* __restrict__ Arows, const uint16_t* __restrict
     const int64_t f = blockIdx.y;
     if (n >= NVC || f >= rows) return;
     const uint16_t* a = Arows + f * FUSED_K;
-    const uint16_t* b = B2 + (size_t)n * FUSED_K;
     auto bf = [](uint16_t v) { return __uint_as_float((uint32_t)v << 16); };
     auto step = [&](int sa, int sb, float acc) {
-        for (int k = 0; k < 16; ++k) acc = fmaf(bf(a[sa * 16 + k]), bf(b[sb * 16 + k]), acc);
+        for (int k = 0; k < 16; ++k) acc = fmaf(bf(a[sa * 16 + k]), bf(B2[fused_b2_index(n, sb * 16 + k)]), acc);
         return acc;
     };
     float acc = 0.f;
@@ -753,12 +754,13 @@ cudaError_t launch_fused(const Model& m, const CUtensorMap& tmap_A, int64_t rows
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
     const uint8_t* wpack = m.d_wpack;
+    const uint16_t* b2img = m.d_B2;
     cudaError_t e;
     if (groups == 1)
-        e = cudaLaunchKernelEx(&cfg, fused_blend_skin_kernel<1>, tmap_A, m.tmap_B2, d_AskinT, d_off, wpack, groups, stages, B,
+        e = cudaLaunchKernelEx(&cfg, fused_blend_skin_kernel<1>, tmap_A, b2img, d_AskinT, d_off, wpack, groups, stages, B,
                                n_units, d_verts, dbg);
     else
-        e = cudaLaunchKernelEx(&cfg, fused_blend_skin_kernel<0>, tmap_A, m.tmap_B2, d_AskinT, d_off, wpack, groups, stages, B,
+        e = cudaLaunchKernelEx(&cfg, fused_blend_skin_kernel<0>, tmap_A, b2img, d_AskinT, d_off, wpack, groups, stages, B,
                                n_units, d_verts, dbg);
     count_launch();
     return e != cudaSuccess ? e : cudaGetLastError();

@@ -53,6 +53,11 @@ constexpr int FUSED_ASKIN_COLS = NJ * 12;     // 288 TMEM columns of A_j per fra
 // ((32 * quarter) << 16 | 12 * joint; the kernel owns all 512 columns, so its allocation starts at 0)
 constexpr int FUSED_WCOL_COPIES = 4;
 constexpr int FUSED_WGROUP_BYTES = FUSED_VT * 16 * (1 + FUSED_WCOL_COPIES);
+// element index of B'[n][k] (vertex coordinate n, K12 column k) inside the chunk-image layout of prk_model::d_B2
+__host__ __device__ constexpr size_t fused_b2_index(int n, int k) {
+    const int tile = n / FUSED_BN, r = n % FUSED_BN, chunk = k / 64, kk = k % 64;
+    return (((size_t)tile * FUSED_B_CHUNKS + chunk) * FUSED_BN + r) * 64 + (size_t)((((kk >> 3) ^ (r & 7)) << 3) | (kk & 7));
+}
 
 // Rest joints as an affine function of betas: J = J_template + Jdirs * beta
 // (folds J_regressor @ (v_template + shapedirs beta), smpl_layer.py:91,95).
@@ -75,9 +80,11 @@ struct prk_model {
     prk::PoseConsts pc;                 // host copy, passed by value to the pose kernel
     // device buffers
     float* d_Jc = nullptr;         // J_template[72] | Jdirs[720] | model_betas[10] (lane-per-joint pose kernel)
-    uint16_t* d_B2 = nullptr;      // [GEMM_N][FUSED_K] bf16 bits, K12 operand layout
+    // B' as the shared-memory IMAGES of its TMA chunks: [vertex tile][chunk][96 rows][64 bf16], every chunk one
+    // contiguous 12 KB block with the 128-byte swizzle already applied (16-byte unit j of row r sits at j ^ (r & 7)),
+    // so a chunk is fetched with ONE linear bulk copy instead of a 96-row tensor box (fused_b2_index)
+    uint16_t* d_B2 = nullptr;
     uint8_t* d_wpack = nullptr;    // [FUSED_NT][nnz_groups][FUSED_WGROUP_BYTES] per-tile skinning weights
-    CUtensorMap tmap_B2;           // [GEMM_N][FUSED_K], box 64 x 96, 128B swizzle
     // scoring only reads the pose: it runs on its own stream beside the mesh path
     cudaStream_t s_score = nullptr;
     cudaEvent_t ev_in = nullptr, ev_score = nullptr;

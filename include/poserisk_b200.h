@@ -29,7 +29,7 @@ extern "C" {
 #pragma GCC visibility push(default)
 #endif
 
-#define PRK_ABI_VERSION 1
+#define PRK_ABI_VERSION 2
 
 #define PRK_NUM_VERTS 6890
 #define PRK_NUM_JOINTS 24
@@ -42,7 +42,8 @@ enum prk_status {
     PRK_ERR_CUDA = 2,
     PRK_ERR_WORKSPACE = 3,   /* workspace too small or misaligned */
     PRK_ERR_UNSUPPORTED = 4,
-    PRK_ERR_DRIVER = 5       /* cuTensorMapEncodeTiled unavailable / failed */
+    PRK_ERR_DRIVER = 5,      /* cuTensorMapEncodeTiled unavailable / failed */
+    PRK_ERR_PEER = 6         /* peer-memory exchange: a peer did not arrive in time / handle could not be opened */
 };
 
 /* additional_information.json (example/additional_information.json:1-25), one per track.
@@ -62,7 +63,10 @@ typedef struct prk_addinfo {
  * reba_parts: trunk, neck, leg, upper_arm L,R, lower_arm L,R, wrist L,R
  * rula_parts: upper_arm L,R, lower_arm L,R, wrist L,R, wrist_twist L,R, neck, trunk, leg
  * flags bit0: a scored joint's rotation matrix is not finite, i.e. the reference
- *             would stop at assert(isRotationMatrix(R)) (lib/utils/coord_utils.py:70). */
+ *             would stop at assert(isRotationMatrix(R)) (lib/utils/coord_utils.py:70).
+ * flags bit1: the frame's track id was outside [0, n_tracks): the reference would raise an
+ *             IndexError picking that person's additional information; the frame is scored
+ *             with track 0's values so that no out-of-bounds read happens. */
 typedef struct prk_score_rec {
     int16_t reba_score;
     int16_t rula_score;
@@ -84,6 +88,7 @@ typedef struct prk_score_rec {
 #define PRK_FLAG_JOINTS_ONLY 1u   /* no vertex output: blend GEMM and skinning are skipped */
 
 typedef struct prk_model prk_model;
+struct prk_comm;   /* multi-GPU exchange handle, see below */
 
 int prk_abi_version(void);
 const char* prk_strerror(int status);
@@ -131,12 +136,13 @@ int prk_smpl_forward(prk_model* model, const float* d_pose, const float* d_betas
  * RULA.__call__ (lib/utils/reba.py:50-81, lib/utils/rula.py:66-98) per frame, i.e. the
  * loop body of lib/core/base.py:225-229 followed by :151 and :168.
  *   d_pose  [B*72] axis-angle, float32 or float64 (pose_dtype)
- *   d_info  [n_tracks]; d_track_of_frame [B] int32 or NULL (every frame uses d_info[0])
+ *   d_info  [n_tracks]; d_track_of_frame [B] int32 or NULL (every frame uses d_info[0]);
+ *           ids outside [0, n_tracks) set flags bit1 (see prk_score_rec)
  *   which   PRK_SCORE_REBA | PRK_SCORE_RULA
  *   d_out   [B] records
  *   d_euler_out [B][n_debug][3] float64 degrees or NULL: Euler angles of the joints
  *           listed in h_debug_joint_ids (the --debug_joints sequences, base.py:144-146) */
-int prk_score_pose(const void* d_pose, int pose_dtype, const prk_addinfo* d_info,
+int prk_score_pose(const void* d_pose, int pose_dtype, const prk_addinfo* d_info, int32_t n_tracks,
                    const int32_t* d_track_of_frame, int64_t B, uint32_t which,
                    prk_score_rec* d_out, double* d_euler_out, const int32_t* h_debug_joint_ids,
                    int n_debug, void* stream);
@@ -144,7 +150,7 @@ int prk_score_pose(const void* d_pose, int pose_dtype, const prk_addinfo* d_info
 /* REBA.__call__(poses, joint_cams, add_info) / RULA.__call__ on Euler degrees
  * (reba.py:50, rula.py:66): d_euler [B*24*3] float64.  joint_cams is never read by the
  * reference (only inside dead string literals, reba.py:262-290) and has no parameter. */
-int prk_score_euler(const double* d_euler, const prk_addinfo* d_info,
+int prk_score_euler(const double* d_euler, const prk_addinfo* d_info, int32_t n_tracks,
                     const int32_t* d_track_of_frame, int64_t B, uint32_t which,
                     prk_score_rec* d_out, void* stream);
 
@@ -162,12 +168,19 @@ int prk_rot_to_angle(const void* d_rotmat, int dtype, int64_t n_rot, void* d_rve
                      void* stream);
 
 /* The whole per-frame path of lib/core/base.py:225-239,151,168 in one call on device
- * buffers: prk_smpl_forward + prk_score_pose on the same float32 pose. */
+ * buffers: prk_smpl_forward + prk_score_pose on the same float32 pose (scoring runs beside the
+ * body-model kernels on the handle's own stream and is joined before the call's place in `stream`).
+ * d_euler_out / h_debug_joint_ids / n_debug as for prk_score_pose (NULL, NULL, 0: no debug sequences).
+ * comm_scores / comm_euler (may be NULL): multi-GPU runs, see "multi-GPU exchange" below -- the B score records
+ * (and the B x n_debug x 3 Euler angles) are all-gathered into every rank's buffer at frame `frame_offset`;
+ * a rank with B = 0 still takes part.
+ * All arguments and the workspace size are checked before anything is launched. */
 int prk_pipeline(prk_model* model, const float* d_pose, const float* d_betas,
-                 const float* d_trans, int center_idx, const prk_addinfo* d_info,
+                 const float* d_trans, int center_idx, const prk_addinfo* d_info, int32_t n_tracks,
                  const int32_t* d_track_of_frame, int64_t B, float* d_verts, float* d_joints,
-                 prk_score_rec* d_scores, void* d_workspace, size_t workspace_bytes,
-                 void* stream);
+                 prk_score_rec* d_scores, double* d_euler_out, const int32_t* h_debug_joint_ids,
+                 int n_debug, struct prk_comm* comm_scores, struct prk_comm* comm_euler,
+                 int64_t frame_offset, void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* Same, from HOST buffers (what a reference caller holds, base.py:222): copies pose /
  * betas / trans host->device, runs prk_pipeline, copies scores and joints device->host.
@@ -191,6 +204,7 @@ int prk_pipeline_host(prk_model* model, const float* h_pose, const float* h_beta
                       const float* h_trans, int center_idx, const prk_addinfo* h_info,
                       int32_t n_tracks, const int32_t* h_track_of_frame, int64_t B,
                       float* d_verts, float* h_joints, prk_score_rec* h_scores,
+                      struct prk_comm* comm_scores, int64_t frame_offset,
                       void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* Predictor.post_processing aggregation (lib/core/base.py:260-271) over one scorer's
@@ -199,6 +213,44 @@ int prk_pipeline_host(prk_model* model, const float* h_pose, const float* h_beta
  * the host.  which = PRK_SCORE_REBA or PRK_SCORE_RULA.  d_hist is zeroed by the call. */
 int prk_score_histogram(const prk_score_rec* d_scores, int64_t B, uint32_t which,
                         unsigned long long* d_hist, void* stream);
+
+/* ---- multi-GPU exchange: frames are sharded over the GPUs of one box, one process per
+ * GPU, and the only exchange is an all-gather of the per-frame score records and, optionally, of the debug
+ * Euler sequences (the reference keeps both as per-frame Python lists: lib/core/base.py:144-151,168).
+ * The gather runs over peer memory: every rank owns a gather buffer that its peers map through CUDA IPC
+ * (or address directly when they live in the same process); prk_allgather_rows stores this rank's rows into
+ * EVERY rank's buffer over NVLink, raises one flag per peer, and waits for the peers' flags -- no host
+ * round trip, no NCCL kernel competing for SMs.  torch.distributed / MPI / files are only needed once, to
+ * hand the opaque handles round.
+ *
+ *   prk_comm_create        allocates the gather buffer (two slots of slot_bytes each) and the flags
+ *   prk_comm_handle_bytes  size of one rank's opaque handle
+ *   prk_comm_get_handle    this rank's handle (HOST buffer of prk_comm_handle_bytes())
+ *   prk_comm_open_peers    h_all_handles = the world's handles in rank order (world * handle bytes)
+ *   prk_allgather_rows     d_local: n_local rows of row_bytes that belong at row
+ *                          `row_offset` of the gathered array (row_bytes: a multiple of 8); every rank must call it the same number of
+ *                          times.  On return (stream order) *d_gathered_out = the device pointer of the
+ *                          slot holding all ranks' rows; it stays valid until this rank's next-but-one call.
+ *                          A peer that does not arrive within ~20 s makes a later prk_comm_status()
+ *                          return PRK_ERR_PEER.
+ *   prk_allgather_scores   the same for prk_score_rec rows (row_bytes = 32)
+ *   prk_comm_gathered      device pointer of the slot written by the most recent exchange
+ *   prk_comm_status        PRK_OK, or PRK_ERR_PEER once a wait has timed out (reads a host-mapped flag)
+ * prk_pipeline / prk_pipeline_host take the communicators directly (comm_scores, comm_euler, frame_offset): the
+ * exchange then runs on the handle's scoring stream right behind the scoring kernel, i.e. underneath the vertex
+ * kernel, and is joined into the caller's stream with the rest of the call. */
+typedef struct prk_comm prk_comm;
+int prk_comm_create(prk_comm** out, int rank, int world, int device, size_t slot_bytes);
+void prk_comm_destroy(prk_comm* comm);
+size_t prk_comm_handle_bytes(void);
+int prk_comm_get_handle(prk_comm* comm, void* h_handle_out);
+int prk_comm_open_peers(prk_comm* comm, const void* h_all_handles);
+void* prk_comm_gathered(prk_comm* comm);
+int prk_allgather_rows(prk_comm* comm, const void* d_local, int64_t n_local, int64_t row_offset,
+                       int64_t row_bytes, void** d_gathered_out, void* stream);
+int prk_allgather_scores(prk_comm* comm, const prk_score_rec* d_local, int64_t n_local,
+                         int64_t frame_offset, prk_score_rec** d_gathered_out, void* stream);
+int prk_comm_status(prk_comm* comm);
 
 /* ---- verification hooks (used by tests only; not on the product path) ---- */
 /* blend-shape stage alone: v_posed [B][prk_vposed_pitch()] float32 into d_vposed (room for

@@ -19,6 +19,8 @@ PRK_SCORE_RULA = 2
 PRK_DTYPE_F32 = 0
 PRK_DTYPE_F64 = 1
 PRK_FLAG_JOINTS_ONLY = 1
+PRK_ERR_PEER = 6
+ABI_VERSION = 2
 
 REBA_KEYS = ("Legs_bilateral_weight_bearing/walking", "Sitting", "Load/Force Score",
              "Arm_supported_leaning_L", "Arm_supported_leaning_R", "Coupling", "Activity_Score")
@@ -36,7 +38,9 @@ EXPORTS = (
     'prk_model_destroy', 'prk_model_device', 'prk_model_max_weights', 'prk_workspace_bytes',
     'prk_smpl_forward', 'prk_score_pose', 'prk_score_euler', 'prk_euler', 'prk_pipeline',
     'prk_rot_to_angle', 'prk_host_workspace_bytes', 'prk_host_scores_offset', 'prk_pipeline_host', 'prk_score_histogram', 'prk_debug_blend',
-    'prk_vposed_pitch', 'prk_launch_count', 'prk_profile_begin', 'prk_profile_end')
+    'prk_vposed_pitch', 'prk_launch_count', 'prk_profile_begin', 'prk_profile_end',
+    'prk_comm_create', 'prk_comm_destroy', 'prk_comm_handle_bytes', 'prk_comm_get_handle', 'prk_comm_open_peers',
+    'prk_comm_gathered', 'prk_allgather_rows', 'prk_allgather_scores', 'prk_comm_status')
 
 
 class PoseRiskError(RuntimeError):
@@ -73,13 +77,13 @@ def lib():
     L.prk_smpl_forward.restype = i32
     L.prk_smpl_forward.argtypes = [vp, vp, vp, vp, i32, i64, vp, vp, vp, sz, vp]
     L.prk_score_pose.restype = i32
-    L.prk_score_pose.argtypes = [vp, i32, vp, vp, i64, u32, vp, vp, vp, i32, vp]
+    L.prk_score_pose.argtypes = [vp, i32, vp, i32, vp, i64, u32, vp, vp, vp, i32, vp]
     L.prk_score_euler.restype = i32
-    L.prk_score_euler.argtypes = [vp, vp, vp, i64, u32, vp, vp]
+    L.prk_score_euler.argtypes = [vp, vp, i32, vp, i64, u32, vp, vp]
     L.prk_euler.restype = i32
     L.prk_euler.argtypes = [vp, i32, i64, vp, vp, vp]
     L.prk_pipeline.restype = i32
-    L.prk_pipeline.argtypes = [vp, vp, vp, vp, i32, vp, vp, i64, vp, vp, vp, vp, sz, vp]
+    L.prk_pipeline.argtypes = [vp, vp, vp, vp, i32, vp, i32, vp, i64, vp, vp, vp, vp, vp, i32, vp, vp, i64, vp, sz, vp]
     L.prk_rot_to_angle.restype = i32
     L.prk_rot_to_angle.argtypes = [vp, i32, i64, vp, vp, vp]
     L.prk_host_workspace_bytes.restype = sz
@@ -87,7 +91,7 @@ def lib():
     L.prk_host_scores_offset.restype = sz
     L.prk_host_scores_offset.argtypes = [vp, i64]
     L.prk_pipeline_host.restype = i32
-    L.prk_pipeline_host.argtypes = [vp, vp, vp, vp, i32, vp, i32, vp, i64, vp, vp, vp, vp, sz, vp]
+    L.prk_pipeline_host.argtypes = [vp, vp, vp, vp, i32, vp, i32, vp, i64, vp, vp, vp, vp, i64, vp, sz, vp]
     L.prk_score_histogram.restype = i32
     L.prk_score_histogram.argtypes = [vp, i64, u32, vp, vp]
     L.prk_debug_blend.restype = i32
@@ -97,16 +101,39 @@ def lib():
     L.prk_profile_begin.restype = i32
     L.prk_profile_end.restype = i32
     L.prk_profile_end.argtypes = [vp, vp]
-    if L.prk_abi_version() != 1:
-        raise ImportError('libposerisk_b200.so ABI version mismatch')
+    L.prk_comm_create.restype = i32
+    L.prk_comm_create.argtypes = [C.POINTER(vp), i32, i32, i32, sz]
+    L.prk_comm_destroy.restype = None
+    L.prk_comm_destroy.argtypes = [vp]
+    L.prk_comm_handle_bytes.restype = sz
+    L.prk_comm_get_handle.restype = i32
+    L.prk_comm_get_handle.argtypes = [vp, vp]
+    L.prk_comm_open_peers.restype = i32
+    L.prk_comm_open_peers.argtypes = [vp, vp]
+    L.prk_comm_gathered.restype = vp
+    L.prk_comm_gathered.argtypes = [vp]
+    L.prk_allgather_rows.restype = i32
+    L.prk_allgather_rows.argtypes = [vp, vp, i64, i64, i64, C.POINTER(vp), vp]
+    L.prk_allgather_scores.restype = i32
+    L.prk_allgather_scores.argtypes = [vp, vp, i64, i64, C.POINTER(vp), vp]
+    L.prk_comm_status.restype = i32
+    L.prk_comm_status.argtypes = [vp]
+    if L.prk_abi_version() != ABI_VERSION:
+        raise ImportError(f'libposerisk_b200.so has ABI version {L.prk_abi_version()}, this package needs {ABI_VERSION}: '
+                          'rebuild it with `python -m poserisk_release_b200.build`')
     _lib = L
     return L
+
+
+class PeerExchangeError(PoseRiskError):
+    """The peer-memory exchange is unavailable (CUDA IPC refused, no peer access, a peer timed out)."""
 
 
 def check(rc: int):
     if rc != PRK_OK:
         L = lib()
-        raise PoseRiskError(f'{L.prk_strerror(rc).decode()} ({L.prk_last_error_detail().decode()})')
+        cls = PeerExchangeError if rc == PRK_ERR_PEER else PoseRiskError
+        raise cls(f'{L.prk_strerror(rc).decode()} ({L.prk_last_error_detail().decode()})')
 
 
 def launch_count() -> int:

@@ -34,14 +34,15 @@ def ptr(t) -> C.c_void_p:
 
 
 class _Workspace:
-    """One growable, 1024-byte aligned scratch buffer per device."""
+    """One growable, 1024-byte aligned scratch buffer per (device, stream): calls queued on different streams
+    may run at the same time and must not share the A' / A_j scratch or the host-path staging area."""
 
     def __init__(self):
         self._buf = {}
         self._lock = threading.Lock()
 
     def get(self, device: torch.device, nbytes: int):
-        key = device.index
+        key = (device.index, torch.cuda.current_stream(device).cuda_stream)
         with self._lock:
             b = self._buf.get(key)
             if b is None or b.numel() < nbytes + 1024:
@@ -95,3 +96,71 @@ def records_to_numpy(rec_u8: torch.Tensor) -> np.ndarray:
 
 def addinfo_tensor(add_infos, device: torch.device) -> torch.Tensor:
     return torch.from_numpy(_lib.addinfo_array(add_infos)).to(device)
+
+
+class PeerComm:
+    """Owns one prk_comm: this rank's gather buffer for the peer-memory all-gather (csrc/prk_comm.cu).
+
+    `exchange_handles(blob) -> list of blobs in rank order` is the only thing the host transport has to do
+    (torch.distributed.all_gather_object, MPI, ...)."""
+
+    def __init__(self, rank: int, world: int, device: torch.device, slot_bytes: int, exchange_handles=None):
+        L = _lib.lib()
+        h = C.c_void_p()
+        _lib.check(L.prk_comm_create(C.byref(h), rank, world, device.index, slot_bytes))
+        self.handle = h
+        self.rank, self.world, self.device, self.slot_bytes = rank, world, device, int(slot_bytes)
+        self._finalizer = weakref.finalize(self, L.prk_comm_destroy, h)
+        if world > 1:
+            if exchange_handles is None:
+                raise ValueError('exchange_handles is required when world > 1')
+            self.open(exchange_handles(self.handle_blob()))
+
+    def handle_blob(self) -> bytes:
+        L = _lib.lib()
+        buf = C.create_string_buffer(int(L.prk_comm_handle_bytes()))
+        _lib.check(L.prk_comm_get_handle(self.handle, buf))
+        return buf.raw
+
+    def open(self, blobs):
+        joined = b''.join(blobs)
+        _lib.check(_lib.lib().prk_comm_open_peers(self.handle, joined))
+
+    def allgather(self, local: torch.Tensor, row_offset: int, n_total_rows: int) -> torch.Tensor:
+        """local: (n_local, ...) contiguous CUDA tensor whose rows belong at `row_offset`; returns a view of the
+        gathered (n_total_rows, ...) array in this rank's buffer (valid until the next-but-one exchange)."""
+        local = local.contiguous()
+        row_shape = tuple(local.shape[1:])
+        row_bytes = local.element_size() * int(np.prod(row_shape, dtype=np.int64)) if row_shape else local.element_size()
+        out = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().prk_allgather_rows(self.handle, ptr(local) if local.numel() else None, local.shape[0],
+                                                     row_offset, row_bytes, C.byref(out), stream_ptr(self.device)))
+        return self.view(n_total_rows, row_shape, local.dtype, out.value)
+
+    def gathered(self, n_rows: int, row_shape, dtype) -> torch.Tensor:
+        """View of the slot written by the most recent exchange (e.g. one issued inside prk_pipeline)."""
+        return self.view(n_rows, tuple(row_shape), dtype, _lib.lib().prk_comm_gathered(self.handle))
+
+    def view(self, n_rows, row_shape, dtype, address):
+        n_el = int(n_rows) * (int(np.prod(row_shape, dtype=np.int64)) if row_shape else 1)
+        return _DevView(address, n_el, dtype, self.device, self).tensor.view((int(n_rows),) + tuple(row_shape))
+
+    def check(self):
+        _lib.check(_lib.lib().prk_comm_status(self.handle))
+
+
+class _DevView:
+    """torch tensor over library-owned device memory (the __cuda_array_interface__ route; `owner` keeps it alive)."""
+
+    _TYPESTR = {torch.uint8: '|u1', torch.float32: '<f4', torch.float64: '<f8', torch.int32: '<i4', torch.int64: '<i8'}
+
+    def __init__(self, address, n_el, dtype, device, owner):
+        self.owner = owner
+        self.__cuda_array_interface__ = {'shape': (max(int(n_el), 0),), 'typestr': self._TYPESTR[dtype],
+                                         'data': (int(address or 0), False), 'version': 2}
+        if n_el > 0:
+            with torch.cuda.device(device):
+                self.tensor = torch.as_tensor(self, device=device)
+        else:
+            self.tensor = torch.empty(0, dtype=dtype, device=device)

@@ -31,6 +31,17 @@ def score_euler_records(poses, add_info, which: int, track_of_frame=None, device
     out = torch.zeros((n, 32), dtype=torch.uint8, device=device)
     if n > 0:
         with torch.cuda.device(device):
-            _lib.check(_lib.lib().prk_score_euler(_runtime.ptr(e), _runtime.ptr(info), _runtime.ptr(track), n,
+            _lib.check(_lib.lib().prk_score_euler(_runtime.ptr(e), _runtime.ptr(info), info.shape[0], _runtime.ptr(track), n,
                                                   which, _runtime.ptr(out), _runtime.stream_ptr(device)))
     return _runtime.records_to_numpy(out)
+
+
+def action_band(bands, score):
+    """(level, text) of the band a rounded score falls into; (None, None) below the first band, as the
+    reference's if-ladders leave both unset for scores < 1 (reba.py:83-104, rula.py:100-118)."""
+    score = round(score)
+    if score < 1:
+        return None, None
+    for top, level, text in bands:
+        if top is None or score <= top:
+            return level, text

@@ -25,7 +25,7 @@ def needs_build() -> bool:
     if not os.path.isfile(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = sources() + glob.glob(os.path.join(CSRC, '*.h')) + \
+    deps = sources() + glob.glob(os.path.join(CSRC, '*.h')) + glob.glob(os.path.join(CSRC, '*.cuh')) + \
         [os.path.join(HERE, '..', 'include', 'poserisk_b200.h')]
     return any(os.path.getmtime(d) > t for d in deps)
 

@@ -3,6 +3,7 @@
 #include "prk_internal.h"
 
 #include <atomic>
+#include <mutex>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -23,10 +24,14 @@ struct StageTimer {
     size_t used = 0;                    // pairs in use
 };
 static StageTimer g_timer;
+static std::mutex g_timer_mu;                 // stage timing may be switched on while other threads launch
+static std::atomic<bool> g_timer_on{false};   // the only thing the hot path looks at when timing is off
 struct StageScope {
     cudaStream_t s;
     long idx = -1;
     StageScope(int stage_id, cudaStream_t stream) : s(stream) {
+        if (!g_timer_on.load(std::memory_order_relaxed)) return;
+        std::lock_guard<std::mutex> lk(g_timer_mu);
         if (!g_timer.on || g_timer.used >= 65536) return;
         if (g_timer.used * 2 + 2 > g_timer.pool.size()) {
             cudaEvent_t a, b;
@@ -39,11 +44,17 @@ struct StageScope {
         idx = (long)g_timer.used++;
         cudaEventRecord(g_timer.pool[idx * 2], s);
     }
-    ~StageScope() { if (idx >= 0) cudaEventRecord(g_timer.pool[idx * 2 + 1], s); }
+    ~StageScope() {
+        if (idx < 0) return;
+        std::lock_guard<std::mutex> lk(g_timer_mu);
+        cudaEventRecord(g_timer.pool[idx * 2 + 1], s);
+    }
 };
 
 static thread_local char t_detail[256] = "";
 static void set_detail(const char* what, const char* msg) { snprintf(t_detail, sizeof t_detail, "%s: %s", what, msg); }
+
+void comm_set_detail(const char* what, const char* msg) { set_detail(what, msg); }
 
 static int cuda_fail(cudaError_t e, const char* what) {
     set_detail(what, cudaGetErrorString(e));
@@ -170,27 +181,64 @@ static bool fit_layout(int64_t B, bool mesh, size_t bytes, Layout& L) {
     return true;
 }
 
+// ---- which prk_pipeline_host call last used a workspace ------------------------------------
+// The copy-in of a host call may run ahead of the caller's stream only when the PREVIOUS user of the same workspace
+// was a host call of the same model, batch size and stream: then both calls agree on the staging layout and the
+// model's own events order the two input sets.  Anything else (another batch size => other offsets, another model
+// handle => other events, a device-API call on the same memory) makes the copy-in wait for the caller's stream.
+struct HostChain { const void* ws = nullptr; const Model* m = nullptr; int64_t B = 0; cudaStream_t s = nullptr; };
+static std::mutex g_chain_mu;
+static HostChain g_chain[16];
+static unsigned g_chain_next = 0;
+// true when this call continues such a chain; records the call as the workspace's last user
+static bool chain_continues(const void* ws, const Model* m, int64_t B, cudaStream_t s) {
+    std::lock_guard<std::mutex> lk(g_chain_mu);
+    for (HostChain& c : g_chain)
+        if (c.ws == ws) {
+            const bool same = c.m == m && c.B == B && c.s == s;
+            c.m = m; c.B = B; c.s = s;
+            return same;
+        }
+    g_chain[g_chain_next++ % 16] = HostChain{ws, m, B, s};
+    return false;
+}
+static void chain_break(const void* ws, const Model* m) {   // a device-API call touched `ws` / model `m` goes away
+    std::lock_guard<std::mutex> lk(g_chain_mu);
+    for (HostChain& c : g_chain)
+        if ((ws && c.ws == ws) || (m && c.m == m)) c = HostChain{};
+}
+
 // ev_joints (optional) is recorded on `s` once every frame's joints are final, i.e. after the last
 // pose-chain launch and long before the vertex kernels finish
-static int forward_impl(Model* m, const float* d_pose, const float* d_betas, const float* d_trans, int center_idx,
-                        int64_t B, float* d_verts, float* d_joints, void* ws, size_t ws_bytes, cudaStream_t s,
-                        cudaEvent_t ev_joints = nullptr) {
+// argument / workspace checks of a forward call, done before anything is launched
+static int forward_check(const char* who, const Model* m, const float* d_pose, int center_idx, int64_t B,
+                         const float* d_verts, const float* d_joints, const void* ws, size_t ws_bytes, Layout& L) {
     if (!m || B < 0 || (B > 0 && (!d_pose || !d_joints)) || center_idx >= NJ) {
-        set_detail("prk_smpl_forward", "invalid argument");
+        set_detail(who, "invalid argument");
         return PRK_ERR_INVALID_ARG;
     }
     if (B == 0) return PRK_OK;
     const bool mesh = d_verts != nullptr;
     if (mesh && (reinterpret_cast<uintptr_t>(d_verts) & 7)) {   // frame rows are written in 8- and 16-byte pieces
-        set_detail("prk_smpl_forward", "d_verts must be 8-byte aligned");
+        set_detail(who, "d_verts must be 8-byte aligned");
         return PRK_ERR_INVALID_ARG;
     }
     if (!ws || (reinterpret_cast<uintptr_t>(ws) & 1023)) {
-        set_detail("prk_smpl_forward", "workspace missing or not 1024-byte aligned");
+        set_detail(who, "workspace missing or not 1024-byte aligned");
         return PRK_ERR_WORKSPACE;
     }
+    if (!fit_layout(B, mesh, ws_bytes, L)) { set_detail(who, "workspace too small"); return PRK_ERR_WORKSPACE; }
+    return PRK_OK;
+}
+
+static int forward_impl(Model* m, const float* d_pose, const float* d_betas, const float* d_trans, int center_idx,
+                        int64_t B, float* d_verts, float* d_joints, void* ws, size_t ws_bytes, cudaStream_t s,
+                        cudaEvent_t ev_joints = nullptr) {
     Layout L;
-    if (!fit_layout(B, mesh, ws_bytes, L)) { set_detail("prk_smpl_forward", "workspace too small"); return PRK_ERR_WORKSPACE; }
+    const int rc0 = forward_check("prk_smpl_forward", m, d_pose, center_idx, B, d_verts, d_joints, ws, ws_bytes, L);
+    if (rc0 != PRK_OK) return rc0;
+    if (B == 0) return PRK_OK;
+    const bool mesh = d_verts != nullptr;
     uint8_t* w = static_cast<uint8_t*>(ws);
     BatchFlags* d_flags = reinterpret_cast<BatchFlags*>(w + L.off_flags);
     uint16_t* d_arows = reinterpret_cast<uint16_t*>(w + L.off_arows);
@@ -236,6 +284,7 @@ const char* prk_strerror(int status) {
         case PRK_ERR_WORKSPACE: return "workspace too small or misaligned";
         case PRK_ERR_UNSUPPORTED: return "unsupported configuration";
         case PRK_ERR_DRIVER: return "CUDA driver entry point unavailable or failed";
+        case PRK_ERR_PEER: return "peer-memory exchange failed (a peer did not arrive, or its memory could not be mapped)";
         default: return "unknown status";
     }
 }
@@ -377,6 +426,7 @@ int prk_model_create(prk_model** out, int device, const float* vt, const float* 
     PRK_M(cudaEventCreateWithFlags(&m->ev_h2d, cudaEventDisableTiming));
     PRK_M(cudaEventCreateWithFlags(&m->ev_joints, cudaEventDisableTiming));
     PRK_M(cudaEventCreateWithFlags(&m->ev_out, cudaEventDisableTiming));
+    PRK_M(cudaEventCreateWithFlags(&m->ev_gather, cudaEventDisableTiming));
 #undef PRK_M
     *out = m;
     return PRK_OK;
@@ -385,6 +435,7 @@ int prk_model_create(prk_model** out, int device, const float* vt, const float* 
 void prk_model_destroy(prk_model* model) {
     Model* m = model;
     if (!m) return;
+    chain_break(nullptr, m);
     if (m->device >= 0) cudaSetDevice(m->device);
     cudaFree(m->d_B2); cudaFree(m->d_wpack);
     cudaFree(m->d_Jc);
@@ -396,6 +447,7 @@ void prk_model_destroy(prk_model* model) {
     if (m->ev_h2d) cudaEventDestroy(m->ev_h2d);
     if (m->ev_joints) cudaEventDestroy(m->ev_joints);
     if (m->ev_out) cudaEventDestroy(m->ev_out);
+    if (m->ev_gather) cudaEventDestroy(m->ev_gather);
     for (int i = 0; i < 2; ++i) if (m->ev_set_free[i]) cudaEventDestroy(m->ev_set_free[i]);
     delete m;
 }
@@ -411,50 +463,51 @@ int prk_smpl_forward(prk_model* model, const float* d_pose, const float* d_betas
                      void* stream) {
     Model* m = model;
     if (!m) { set_detail("prk_smpl_forward", "null model"); return PRK_ERR_INVALID_ARG; }
-    m->chained_ws = nullptr;
+    chain_break(ws, nullptr);
     PRK_CUDA(cudaSetDevice(m->device));
     return forward_impl(m, d_pose, d_betas, d_trans, center_idx, B, d_verts, d_joints, ws, ws_bytes,
                         static_cast<cudaStream_t>(stream));
 }
 
-int prk_score_pose(const void* d_pose, int pose_dtype, const prk_addinfo* d_info, const int32_t* d_track, int64_t B,
-                   uint32_t which, prk_score_rec* d_out, double* d_euler_out, const int32_t* h_debug_joint_ids,
+// --debug_joints list -> by-value kernel parameter (no device table, no allocation, no synchronisation)
+static bool make_debug_slots(const int32_t* h_ids, int n_debug, DebugSlots& d) {
+    d.mask = 0;
+    for (int j = 0; j < NJ; ++j) d.slot[j] = -1;
+    for (int k = 0; k < n_debug; ++k) {
+        const int j = h_ids[k];
+        if (j < 0 || j >= NJ || (d.mask & (1u << j))) return false;
+        d.mask |= 1u << j;
+        d.slot[j] = (int8_t)k;
+    }
+    return true;
+}
+
+int prk_score_pose(const void* d_pose, int pose_dtype, const prk_addinfo* d_info, int32_t n_tracks, const int32_t* d_track,
+                   int64_t B, uint32_t which, prk_score_rec* d_out, double* d_euler_out, const int32_t* h_debug_joint_ids,
                    int n_debug, void* stream) {
-    if (B < 0 || (B > 0 && (!d_pose || !d_info || !d_out)) || (pose_dtype != PRK_DTYPE_F32 && pose_dtype != PRK_DTYPE_F64) ||
+    if (B < 0 || (B > 0 && (!d_pose || !d_info || !d_out)) || n_tracks < 1 ||
+        (pose_dtype != PRK_DTYPE_F32 && pose_dtype != PRK_DTYPE_F64) ||
         !(which & 3u) || n_debug < 0 || n_debug > NJ || (n_debug > 0 && (!d_euler_out || !h_debug_joint_ids))) {
         set_detail("prk_score_pose", "invalid argument");
         return PRK_ERR_INVALID_ARG;
     }
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    uint32_t mask = 0;
-    int8_t slot[NJ];
-    for (int j = 0; j < NJ; ++j) slot[j] = -1;
-    for (int k = 0; k < n_debug; ++k) {
-        const int j = h_debug_joint_ids[k];
-        if (j < 0 || j >= NJ || (mask & (1u << j))) { set_detail("prk_score_pose", "bad or duplicate debug joint id"); return PRK_ERR_INVALID_ARG; }
-        mask |= 1u << j;
-        slot[j] = (int8_t)k;
+    DebugSlots dbg;
+    if (!make_debug_slots(h_debug_joint_ids, n_debug, dbg)) {
+        set_detail("prk_score_pose", "bad or duplicate debug joint id");
+        return PRK_ERR_INVALID_ARG;
     }
-    int8_t* d_slot = nullptr;
-    if (n_debug > 0) {   // 24-byte table, stream-ordered allocation (debug path only)
-        PRK_CUDA(cudaMallocAsync(&d_slot, NJ, s));
-        PRK_CUDA(cudaMemcpyAsync(d_slot, slot, NJ, cudaMemcpyHostToDevice, s));
-        PRK_CUDA(cudaStreamSynchronize(s));   // `slot` is a stack buffer
-    }
-    cudaError_t e = launch_score_pose(d_pose, pose_dtype, d_info, d_track, B, which, d_out,
-                                      n_debug > 0 ? d_euler_out : nullptr, mask, d_slot, n_debug, s);
-    if (d_slot) cudaFreeAsync(d_slot, s);
-    if (e != cudaSuccess) return cuda_fail(e, "score_pose_kernel");
+    PRK_CUDA(launch_score_pose(d_pose, pose_dtype, d_info, n_tracks, d_track, B, which, d_out,
+                               n_debug > 0 ? d_euler_out : nullptr, dbg, n_debug, static_cast<cudaStream_t>(stream)));
     return PRK_OK;
 }
 
-int prk_score_euler(const double* d_euler, const prk_addinfo* d_info, const int32_t* d_track, int64_t B,
+int prk_score_euler(const double* d_euler, const prk_addinfo* d_info, int32_t n_tracks, const int32_t* d_track, int64_t B,
                     uint32_t which, prk_score_rec* d_out, void* stream) {
-    if (B < 0 || (B > 0 && (!d_euler || !d_info || !d_out)) || !(which & 3u)) {
+    if (B < 0 || (B > 0 && (!d_euler || !d_info || !d_out)) || n_tracks < 1 || !(which & 3u)) {
         set_detail("prk_score_euler", "invalid argument");
         return PRK_ERR_INVALID_ARG;
     }
-    PRK_CUDA(launch_score_euler(d_euler, d_info, d_track, B, which, d_out, static_cast<cudaStream_t>(stream)));
+    PRK_CUDA(launch_score_euler(d_euler, d_info, n_tracks, d_track, B, which, d_out, static_cast<cudaStream_t>(stream)));
     return PRK_OK;
 }
 
@@ -477,34 +530,63 @@ int prk_rot_to_angle(const void* d_rotmat, int dtype, int64_t n_rot, void* d_rve
 }
 
 int prk_pipeline(prk_model* model, const float* d_pose, const float* d_betas, const float* d_trans, int center_idx,
-                 const prk_addinfo* d_info, const int32_t* d_track, int64_t B, float* d_verts, float* d_joints,
-                 prk_score_rec* d_scores, void* ws, size_t ws_bytes, void* stream) {
+                 const prk_addinfo* d_info, int32_t n_tracks, const int32_t* d_track, int64_t B, float* d_verts,
+                 float* d_joints, prk_score_rec* d_scores, double* d_euler_out, const int32_t* h_debug_joint_ids,
+                 int n_debug, prk_comm* comm_scores, prk_comm* comm_euler, int64_t frame_offset, void* ws, size_t ws_bytes,
+                 void* stream) {
     Model* m = model;
-    if (!m || !d_info || (B > 0 && !d_scores)) { set_detail("prk_pipeline", "invalid argument"); return PRK_ERR_INVALID_ARG; }
-    m->chained_ws = nullptr;
-    PRK_CUDA(cudaSetDevice(m->device));
+    // every check happens before the first launch: a refused call leaves the stream and the outputs untouched
+    if (!m || !d_info || n_tracks < 1 || (B > 0 && !d_scores) || n_debug < 0 || n_debug > NJ ||
+        (n_debug > 0 && (!d_euler_out || !h_debug_joint_ids))) {
+        set_detail("prk_pipeline", "invalid argument");
+        return PRK_ERR_INVALID_ARG;
+    }
+    DebugSlots dbg;
+    if (!make_debug_slots(h_debug_joint_ids, n_debug, dbg)) {
+        set_detail("prk_pipeline", "bad or duplicate debug joint id");
+        return PRK_ERR_INVALID_ARG;
+    }
+    {
+        Layout L;
+        const int rc = forward_check("prk_pipeline", m, d_pose, center_idx, B, d_verts, d_joints, ws, ws_bytes, L);
+        if (rc != PRK_OK) return rc;
+    }
+    if (comm_euler && n_debug == 0) comm_euler = nullptr;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (B == 0) {   // an empty shard still takes part in the exchange
+        int rc = PRK_OK;
+        if (comm_scores) rc = prk_allgather_rows(comm_scores, nullptr, 0, frame_offset, sizeof(prk_score_rec), nullptr, s);
+        if (rc == PRK_OK && comm_euler) rc = prk_allgather_rows(comm_euler, nullptr, 0, frame_offset, n_debug * 24, nullptr, s);
+        return rc;
+    }
+    chain_break(ws, nullptr);
+    PRK_CUDA(cudaSetDevice(m->device));
     // scoring only reads the pose: it runs on the model's scoring stream, beside the mesh path
-    const bool overlap = m->s_score != nullptr && B > 0;
-    cudaStream_t ss = overlap ? m->s_score : s;
-    if (overlap) {
-        PRK_CUDA(cudaEventRecord(m->ev_in, s));
-        PRK_CUDA(cudaStreamWaitEvent(ss, m->ev_in, 0));
+    cudaStream_t ss = m->s_score;
+    PRK_CUDA(cudaEventRecord(m->ev_in, s));
+    PRK_CUDA(cudaStreamWaitEvent(ss, m->ev_in, 0));
+    cudaError_t e;
+    {
         StageScope sc(3, ss);
-        PRK_CUDA(launch_score_pose(d_pose, PRK_DTYPE_F32, d_info, d_track, B, PRK_SCORE_REBA | PRK_SCORE_RULA, d_scores,
-                                   nullptr, 0, nullptr, 0, ss));
+        e = launch_score_pose(d_pose, PRK_DTYPE_F32, d_info, n_tracks, d_track, B, PRK_SCORE_REBA | PRK_SCORE_RULA,
+                              d_scores, n_debug > 0 ? d_euler_out : nullptr, dbg, n_debug, ss);
     }
-    if (overlap) PRK_CUDA(cudaEventRecord(m->ev_score, ss));
-    int rc = forward_impl(m, d_pose, d_betas, d_trans, center_idx, B, d_verts, d_joints, ws, ws_bytes, s);
-    if (rc != PRK_OK) return rc;
-    if (overlap) {
-        PRK_CUDA(cudaStreamWaitEvent(s, m->ev_score, 0));
-    } else {
-        StageScope sc(3, s);
-        PRK_CUDA(launch_score_pose(d_pose, PRK_DTYPE_F32, d_info, d_track, B, PRK_SCORE_REBA | PRK_SCORE_RULA, d_scores,
-                                   nullptr, 0, nullptr, 0, s));
-    }
-    return PRK_OK;
+    // multi-GPU: the records (and debug Euler rows) go to every rank's gather buffer straight from the scoring
+    // stream, i.e. underneath the vertex kernel that is launched on `s` below
+    int rc = PRK_OK;
+    if (e == cudaSuccess && comm_scores)
+        rc = prk_allgather_rows(comm_scores, d_scores, B, frame_offset, sizeof(prk_score_rec), nullptr, ss);
+    if (e == cudaSuccess && rc == PRK_OK && comm_euler)
+        rc = prk_allgather_rows(comm_euler, d_euler_out, B, frame_offset, n_debug * 24, nullptr, ss);
+    // whatever happens next, the caller's stream joins the scoring stream: nothing of this call is still
+    // running once `stream` has passed it, also when the call reports an error
+    cudaError_t e2 = cudaEventRecord(m->ev_score, ss);
+    if (e == cudaSuccess && e2 == cudaSuccess && rc == PRK_OK)
+        rc = forward_impl(m, d_pose, d_betas, d_trans, center_idx, B, d_verts, d_joints, ws, ws_bytes, s);
+    if (e2 == cudaSuccess) e2 = cudaStreamWaitEvent(s, m->ev_score, 0);
+    if (e != cudaSuccess) return cuda_fail(e, "score_pose_kernel");
+    if (e2 != cudaSuccess) return cuda_fail(e2, "join of the scoring stream");
+    return rc;
 }
 
 // host-staging layout in front of the device workspace: two input sets (the copy-in of call i+1
@@ -537,19 +619,28 @@ size_t prk_host_scores_offset(const prk_model*, int64_t B) { return host_stage(B
 
 int prk_pipeline_host(prk_model* model, const float* h_pose, const float* h_betas, const float* h_trans,
                       int center_idx, const prk_addinfo* h_info, int32_t n_tracks, const int32_t* h_track, int64_t B,
-                      float* d_verts, float* h_joints, prk_score_rec* h_scores, void* ws, size_t ws_bytes,
-                      void* stream) {
+                      float* d_verts, float* h_joints, prk_score_rec* h_scores, prk_comm* comm_scores,
+                      int64_t frame_offset, void* ws, size_t ws_bytes, void* stream) {
     Model* m = model;
     if (!m || B < 0 || !h_info || n_tracks < 1 || n_tracks > 4096 || (B > 0 && (!h_pose || !h_scores))) {
         set_detail("prk_pipeline_host", "invalid argument");
         return PRK_ERR_INVALID_ARG;
     }
-    if (B == 0) return PRK_OK;
+    if (B == 0)
+        return comm_scores ? prk_allgather_rows(comm_scores, nullptr, 0, frame_offset, sizeof(prk_score_rec), nullptr, stream) : PRK_OK;
     if (!ws || (reinterpret_cast<uintptr_t>(ws) & 1023)) { set_detail("prk_pipeline_host", "workspace missing or misaligned"); return PRK_ERR_WORKSPACE; }
     PRK_CUDA(cudaSetDevice(m->device));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const HostStage h = host_stage(B, 4096, 0);
     if (ws_bytes <= h.inner) { set_detail("prk_pipeline_host", "workspace too small"); return PRK_ERR_WORKSPACE; }
+    {
+        Layout L;
+        if (center_idx >= NJ || (d_verts && (reinterpret_cast<uintptr_t>(d_verts) & 7))) {
+            set_detail("prk_pipeline_host", "invalid argument");
+            return PRK_ERR_INVALID_ARG;
+        }
+        if (!fit_layout(B, d_verts != nullptr, ws_bytes - h.inner, L)) { set_detail("prk_pipeline_host", "workspace too small"); return PRK_ERR_WORKSPACE; }
+    }
     const int set = (int)(m->host_calls++ & 1);
     uint8_t* w = static_cast<uint8_t*>(ws);
     uint8_t* wi = w + (size_t)set * h.in_set;
@@ -563,12 +654,12 @@ int prk_pipeline_host(prk_model* model, const float* h_pose, const float* h_beta
 
     // ---- copy-in stream: inputs of this call land while the kernels of the previous call run (the
     // host buffers must be ready when the call is made, as for any host argument).  The set was
-    // last read by the call before the previous one (ev_set_free).  Only a chain of host calls on
-    // the same workspace is known to leave the staging area alone: after anything else the copy
-    // waits for the work already queued on the caller's stream.
+    // last read by the call before the previous one (ev_set_free).  Only a chain of host calls of
+    // the same model, batch size and stream on the same workspace shares one staging layout and one
+    // set of events (chain_continues): after anything else the copy waits for the work already
+    // queued on the caller's stream.
     PRK_CUDA(cudaEventRecord(m->ev_in, s));
-    if (m->chained_ws != ws) PRK_CUDA(cudaStreamWaitEvent(m->s_in, m->ev_in, 0));
-    m->chained_ws = ws;
+    if (!chain_continues(ws, m, B, s)) PRK_CUDA(cudaStreamWaitEvent(m->s_in, m->ev_in, 0));
     PRK_CUDA(cudaStreamWaitEvent(m->s_in, m->ev_set_free[set], 0));
     PRK_CUDA(cudaMemcpyAsync(d_pose, h_pose, (size_t)B * 72 * 4, cudaMemcpyHostToDevice, m->s_in));
     if (h_betas) PRK_CUDA(cudaMemcpyAsync(d_betas, h_betas, (size_t)B * NBETA * 4, cudaMemcpyHostToDevice, m->s_in));
@@ -585,15 +676,26 @@ int prk_pipeline_host(prk_model* model, const float* h_pose, const float* h_beta
     PRK_CUDA(cudaStreamWaitEvent(ss, m->ev_in, 0));
     {
         StageScope sc(3, ss);
-        PRK_CUDA(launch_score_pose(d_pose, PRK_DTYPE_F32, d_info, d_track, B, PRK_SCORE_REBA | PRK_SCORE_RULA, d_scores,
-                                   nullptr, 0, nullptr, 0, ss));
+        PRK_CUDA(launch_score_pose(d_pose, PRK_DTYPE_F32, d_info, n_tracks, d_track, B, PRK_SCORE_REBA | PRK_SCORE_RULA,
+                                   d_scores, nullptr, DebugSlots{}, 0, ss));
     }
     PRK_CUDA(cudaEventRecord(m->ev_score, ss));
+    cudaEvent_t ev_gather = nullptr;
+    if (comm_scores) {   // multi-GPU: all-gather of the records underneath the vertex kernel (joined at the end)
+        const int rcg = prk_allgather_rows(comm_scores, d_scores, B, frame_offset, sizeof(prk_score_rec), nullptr, ss);
+        if (rcg != PRK_OK) { cudaStreamWaitEvent(s, m->ev_score, 0); chain_break(ws, nullptr); return rcg; }
+        ev_gather = m->ev_gather;
+        PRK_CUDA(cudaEventRecord(ev_gather, ss));
+    }
     PRK_CUDA(cudaStreamWaitEvent(s, m->ev_h2d, 0));
     PRK_CUDA(cudaStreamWaitEvent(s, m->ev_out, 0));         // d_joints of the previous call has been copied out
     int rc = forward_impl(m, d_pose, d_betas, d_trans, center_idx, B, d_verts, d_joints, w + h.inner, ws_bytes - h.inner, s,
                           m->ev_joints);
-    if (rc != PRK_OK) return rc;
+    if (rc != PRK_OK) {                                     // the caller's stream still joins what was launched
+        cudaStreamWaitEvent(s, m->ev_score, 0);
+        chain_break(ws, nullptr);
+        return rc;
+    }
 
     // ---- copy-out stream: joints and scores leave under the vertex kernel of this call
     PRK_CUDA(cudaStreamWaitEvent(m->s_out, m->ev_joints, 0));
@@ -603,6 +705,7 @@ int prk_pipeline_host(prk_model* model, const float* h_pose, const float* h_beta
     PRK_CUDA(cudaEventRecord(m->ev_out, m->s_out));
     // completion stays ordered on the caller's stream: it joins the copy-out and the scoring stream
     PRK_CUDA(cudaStreamWaitEvent(s, m->ev_out, 0));
+    if (ev_gather) PRK_CUDA(cudaStreamWaitEvent(s, ev_gather, 0));
     PRK_CUDA(cudaEventRecord(m->ev_set_free[set], s));
     return PRK_OK;
 }
@@ -618,12 +721,16 @@ int prk_score_histogram(const prk_score_rec* d_scores, int64_t B, uint32_t which
 }
 
 int prk_profile_begin(void) {
+    std::lock_guard<std::mutex> lk(g_timer_mu);
     g_timer.on = true;
     g_timer.used = 0;
+    g_timer_on.store(true);
     return PRK_OK;
 }
 
 int prk_profile_end(double* ms_out, int64_t* launches_out) {
+    std::lock_guard<std::mutex> lk(g_timer_mu);
+    g_timer_on.store(false);
     g_timer.on = false;
     for (int k = 0; k < 4; ++k) { if (ms_out) ms_out[k] = 0.0; if (launches_out) launches_out[k] = 0; }
     for (size_t i = 0; i < g_timer.used; ++i) {

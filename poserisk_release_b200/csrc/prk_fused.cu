@@ -39,6 +39,7 @@
 #include "prk_internal.h"
 #include "prk_tc.cuh"
 
+#include <atomic>
 #include <cstdlib>
 
 namespace prk {
@@ -724,13 +725,13 @@ cudaError_t launch_fused(const Model& m, const CUtensorMap& tmap_A, int64_t rows
     const int stages = fused_stages(groups);
     const int smem = fused_smem_bytes(stages, groups);
     if (smem > kSmemLimit) return cudaErrorInvalidConfiguration;
-    static int attr_set[64] = {};
-    if (m.device >= 0 && m.device < 64 && attr_set[m.device] < smem) {
+    static std::atomic<int> attr_set[64];       // per device: dynamic shared memory the kernels were opted in for
+    if (m.device >= 0 && m.device < 64 && attr_set[m.device].load(std::memory_order_acquire) < smem) {
         cudaError_t e = cudaFuncSetAttribute(fused_blend_skin_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(fused_blend_skin_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
-        attr_set[m.device] = smem;
+        attr_set[m.device].store(smem, std::memory_order_release);
     }
     int dbg = 0;
 #if defined(PRK_FUSED_DEBUG) || defined(PRK_FUSED_KNOCK)

@@ -90,9 +90,8 @@ struct prk_model {
     cudaEvent_t ev_in = nullptr, ev_score = nullptr;
     // host-buffer pipeline (prk_pipeline_host): copy-in / copy-out streams beside the kernels, two input sets
     cudaStream_t s_in = nullptr, s_out = nullptr;
-    cudaEvent_t ev_h2d = nullptr, ev_joints = nullptr, ev_out = nullptr, ev_set_free[2] = {nullptr, nullptr};
+    cudaEvent_t ev_h2d = nullptr, ev_joints = nullptr, ev_out = nullptr, ev_gather = nullptr, ev_set_free[2] = {nullptr, nullptr};
     uint64_t host_calls = 0;
-    const void* chained_ws = nullptr;   // workspace of the previous call if that was a prk_pipeline_host call
 };
 
 namespace prk {
@@ -125,11 +124,16 @@ cudaError_t launch_blend_simt(const Model& m, const uint16_t* d_Arows, int64_t r
 cudaError_t launch_identity_askin(float* d_AskinT, float* d_off, int64_t rows_pad, cudaStream_t s);
 
 // K3: Euler angles + REBA/RULA
-cudaError_t launch_score_pose(const void* d_pose, int pose_dtype, const prk_addinfo* d_info,
+// --debug_joints list as a by-value kernel parameter: bit j of `mask` = joint j is listed, slot[j] = its position
+struct DebugSlots {
+    uint32_t mask = 0;
+    int8_t slot[NJ] = {};
+};
+cudaError_t launch_score_pose(const void* d_pose, int pose_dtype, const prk_addinfo* d_info, int32_t n_tracks,
                               const int32_t* d_track, int64_t B, uint32_t which,
-                              prk_score_rec* d_out, double* d_euler_out, uint32_t debug_mask,
-                              const int8_t* debug_slot, int n_debug, cudaStream_t s);
-cudaError_t launch_score_euler(const double* d_euler, const prk_addinfo* d_info,
+                              prk_score_rec* d_out, double* d_euler_out, const DebugSlots& dbg, int n_debug,
+                              cudaStream_t s);
+cudaError_t launch_score_euler(const double* d_euler, const prk_addinfo* d_info, int32_t n_tracks,
                                const int32_t* d_track, int64_t B, uint32_t which,
                                prk_score_rec* d_out, cudaStream_t s);
 cudaError_t launch_euler(const void* d_pose, int pose_dtype, int64_t n_rot, double* d_euler,

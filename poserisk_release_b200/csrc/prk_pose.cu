@@ -43,11 +43,12 @@ struct RowWriter {
     uint4* dst;
     uint32_t buf[4];
     int n;
+    bool live;      // false: lanes beyond the batch run the same code and store nothing
     __device__ __forceinline__ void push(uint16_t v) {
         const int w = (n >> 1) & 3;
         if (n & 1) buf[w] |= (uint32_t)v << 16; else buf[w] = v;
         ++n;
-        if ((n & 7) == 0) { *dst = make_uint4(buf[0], buf[1], buf[2], buf[3]); ++dst; }
+        if ((n & 7) == 0) { if (live) *dst = make_uint4(buf[0], buf[1], buf[2], buf[3]); ++dst; }
     }
 };
 
@@ -107,6 +108,8 @@ __device__ __forceinline__ float skin_t(const float* G, int r, float j0, float j
 // so the fused kernel's packed FFMA2 sees (R0c, R1c) register pairs:  R00 R10 R01 R11 R02 R12 t0 t1 | R20 R21 R22 t2
 __host__ __device__ constexpr int askin_col(int r, int c) { return r == 2 ? 8 + c : 2 * c + r; }
 
+constexpr int kChainPitch = 73;    // floats per staged pose / joint row of the thread-per-frame kernel (72 + 1)
+
 // mode bits
 constexpr uint32_t MODE_FRAME_BETAS_ALWAYS = 1u;  // betas given and model betas are zero
 constexpr uint32_t MODE_FRAME_BETAS_FLAG = 2u;    // betas given, honour flags->betas_nonzero
@@ -120,8 +123,29 @@ pose_chain_kernel(const __grid_constant__ PoseConsts pc, const float* __restrict
                   const BatchFlags* __restrict__ flags, uint32_t mode, int center_idx, int64_t B,
                   uint16_t* __restrict__ Arows, float* __restrict__ Askin,
                   float* __restrict__ off, float* __restrict__ joints) {
-    const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= B) return;
+    // Memory path: a frame's pose row is 288 B, so thread-private row accesses would touch 32 different lines per
+    // warp-wide load / store.  Every warp copies the 32 consecutive pose rows of its frames into a shared-memory
+    // tile with fully coalesced loads (odd pitch: conflict-free per-thread row accesses), the joints are written
+    // into the same rows (a joint's pose entries are read before its position is written) and leave the same way.
+    __shared__ float s_tile[4][32 * kChainPitch];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t f0 = (int64_t)blockIdx.x * blockDim.x + warp * 32;     // first frame of this warp
+    if (f0 >= B) return;
+    const int nf = (int)((B - f0) < 32 ? (B - f0) : 32);                 // frames of this warp (warp-uniform)
+    float* tile = s_tile[warp];
+    {
+        const float* src = pose + f0 * 72;
+        const int n = nf * 72;
+        int r = 0, c = lane;
+        for (int q = lane; q < 32 * 72; q += 32) {                       // rows beyond the batch: zeros
+            tile[r * kChainPitch + c] = q < n ? src[q] : 0.0f;
+            c += 32;
+            if (c >= 72) { c -= 72; ++r; }
+        }
+    }
+    __syncwarp();
+    const bool live = lane < nf;
+    const int64_t f = live ? f0 + lane : f0;      // lanes beyond the batch read frame f0's betas / trans and store nothing
 
     bool frame_betas = (mode & MODE_FRAME_BETAS_ALWAYS) != 0;
     bool add_trans = (mode & MODE_TRANS_ALWAYS) != 0;
@@ -140,12 +164,13 @@ pose_chain_kernel(const __grid_constant__ PoseConsts pc, const float* __restrict
     RowWriter rw, rw_lo;
     rw.dst = kMesh ? reinterpret_cast<uint4*>(Arows + f * FUSED_K) : nullptr;
     rw.n = 0;
+    rw.live = live;
     rw.buf[0] = rw.buf[1] = rw.buf[2] = rw.buf[3] = 0;
     rw_lo = rw;
     if (kMesh) rw_lo.dst = reinterpret_cast<uint4*>(Arows + f * FUSED_K + FUSED_COL_LO);
 
-    const float* p = pose + f * 72;
-    float* jout = joints + f * 72;
+    const float* p = tile + lane * kChainPitch;
+    float* jout = tile + lane * kChainPitch;
     float G[NJ][12];     // global transforms, rows [R | t]
     float J[NJ][3];      // rest joints
     float c0 = 0.f, c1 = 0.f, c2 = 0.f;   // centre joint translation
@@ -156,7 +181,7 @@ pose_chain_kernel(const __grid_constant__ PoseConsts pc, const float* __restrict
         const int par = kStd ? smpl_parent(j) : (pos == 0 ? -1 : pc.parents[j]);
 
         float R[9];
-        smpl_rodrigues(p[j * 3 + 0], p[j * 3 + 1], p[j * 3 + 2], R);
+        smpl_rodrigues(p[j * 3 + 0], p[j * 3 + 1], p[j * 3 + 2], R);      // (read before jout[j * 3 ..] is written)
 
         if (kMesh && pos > 0) {   // pose_map = R - I, split hi/lo (tensutils.py:41-48)
             uint16_t hi[9], lo[9];
@@ -190,7 +215,7 @@ pose_chain_kernel(const __grid_constant__ PoseConsts pc, const float* __restrict
         jout[j * 3 + 2] = __fadd_rn(G[j][11], o2);
         if (j == center_idx) { c0 = G[j][3]; c1 = G[j][7]; c2 = G[j][11]; }
 
-        if (kMesh) {   // A_j = G_j - pack(G_j @ [j_rest; 0])  (smpl_layer.py:126-132), TMEM-tile layout
+        if (kMesh && live) {   // A_j = G_j - pack(G_j @ [j_rest; 0])  (smpl_layer.py:126-132), TMEM-tile layout
             float* dst = Askin + ((f >> 5) * FUSED_ASKIN_COLS + j * 12) * 32 + (f & 31);
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
@@ -209,8 +234,20 @@ pose_chain_kernel(const __grid_constant__ PoseConsts pc, const float* __restrict
         }
     }
 
+    {   // coalesced copy of the nf joint rows
+        __syncwarp();
+        float* dst = joints + f0 * 72;
+        const int n = nf * 72;
+        int r = 0, c = lane;
+        for (int q = lane; q < n; q += 32) {
+            dst[q] = tile[r * kChainPitch + c];
+            c += 32;
+            if (c >= 72) { c -= 72; ++r; }
+        }
+    }
+
     if (kMesh) {
-        off[f * 3 + 0] = o0; off[f * 3 + 1] = o1; off[f * 3 + 2] = o2;
+        if (live) { off[f * 3 + 0] = o0; off[f * 3 + 1] = o1; off[f * 3 + 2] = o2; }
         rw.push(0); rw_lo.push(0);                   // columns 207 / 415 close the hi / lo blocks
         rw.dst = reinterpret_cast<uint4*>(Arows + f * FUSED_K + FUSED_COL_BETA);
         uint16_t bs[3][NBETA];                       // 3-way split of every beta

@@ -439,30 +439,81 @@ __device__ __forceinline__ void store_rec(prk_score_rec* dst, const prk_score_re
     d[1] = src[1];
 }
 
-__device__ __forceinline__ void score_and_store(const Angles& A, const prk_addinfo* __restrict__ info,
-                                                const int32_t* __restrict__ track, int64_t i,
-                                                uint32_t which, uint8_t flags, prk_score_rec* out) {
-    const prk_addinfo* ai = info + (track ? track[i] : 0);
-    alignas(16) prk_score_rec r;
+// additional information of frame i's track; an id outside [0, n_tracks) selects track 0 and sets flags bit 1
+// (the reference would raise an IndexError there) instead of reading out of bounds
+__device__ __forceinline__ const prk_addinfo* track_info(const prk_addinfo* __restrict__ info, int32_t n_tracks,
+                                                         const int32_t* __restrict__ track, int64_t i, uint8_t& flags) {
+    int32_t t = track ? track[i] : 0;
+    if ((uint32_t)t >= (uint32_t)n_tracks) { t = 0; flags |= 2; }
+    return info + t;
+}
+
+__device__ __forceinline__ void score_frame(const Angles& A, const prk_addinfo* ai, uint32_t which, uint8_t flags,
+                                            prk_score_rec& r) {
     uint4* z = reinterpret_cast<uint4*>(&r);
     z[0] = make_uint4(0, 0, 0, 0); z[1] = make_uint4(0, 0, 0, 0);
     if (which & PRK_SCORE_REBA) reba_frame(A, ai->reba, r);
     if (which & PRK_SCORE_RULA) rula_frame(A, ai->rula, r);
     r.flags = flags;
+}
+
+__device__ __forceinline__ void score_and_store(const Angles& A, const prk_addinfo* __restrict__ info, int32_t n_tracks,
+                                                const int32_t* __restrict__ track, int64_t i,
+                                                uint32_t which, uint8_t flags, prk_score_rec* out) {
+    const prk_addinfo* ai = track_info(info, n_tracks, track, i, flags);
+    alignas(16) prk_score_rec r;
+    score_frame(A, ai, which, flags, r);
     store_rec(out + i, r);
 }
 
-// pose (axis-angle) -> Euler -> scores.  debug_mask: bit j set = also emit joint j's Euler
-// angles to euler_out[i][debug_slot[j]][3].
+// pose (axis-angle) -> Euler -> scores, one thread per frame (large batches, and every call with debug joints).
+// debug: bit j of `mask` set = also emit joint j's Euler angles to euler_out[i][slot[j]][3].
+//
+// Memory path: a frame's pose row is 288 B (576 B for float64), so thread-private row reads would touch 32
+// different lines per warp-wide load.  Each warp instead copies the 32 consecutive rows of its frames into a
+// shared-memory tile with fully coalesced loads (odd pitch: conflict-free per-thread row reads), the debug Euler
+// sequences leave through a second tile the same way, and the 32-byte records are exchanged between lane pairs so
+// that every store instruction writes 512 contiguous bytes.
+constexpr int kScoreWarps = 2;
+constexpr int kPosePitch = 73;            // elements per staged pose row (72 + 1)
+constexpr int kDebugStageJoints = 6;      // debug joint lists up to this length are staged (longer lists: direct stores)
+constexpr int kDebugPitch = kDebugStageJoints * 3 + 1;
+
 template <typename T>
-__global__ void __launch_bounds__(128)
-score_pose_kernel(const T* __restrict__ pose, const prk_addinfo* __restrict__ info,
+__global__ void __launch_bounds__(kScoreWarps * 32)
+score_pose_kernel(const T* __restrict__ pose, const prk_addinfo* __restrict__ info, int32_t n_tracks,
                   const int32_t* __restrict__ track, int64_t B, uint32_t which,
                   prk_score_rec* __restrict__ out, double* __restrict__ euler_out,
-                  uint32_t debug_mask, const int8_t* __restrict__ debug_slot, int n_debug) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= B) return;
-    const T* p = pose + i * 72;
+                  const DebugSlots dbg, int n_debug) {
+    __shared__ T s_pose[kScoreWarps][32 * kPosePitch];
+    __shared__ double s_dbg[kScoreWarps][32 * kDebugPitch];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t f0 = ((int64_t)blockIdx.x * kScoreWarps + warp) * 32;     // first frame of this warp
+    if (f0 >= B) return;
+    const int nf = (int)((B - f0) < 32 ? (B - f0) : 32);                   // frames of this warp (warp-uniform)
+    T* tile = s_pose[warp];
+    {   // coalesced copy of nf consecutive pose rows: flat element q -> row q / 72, column q % 72
+        const T* src = pose + f0 * 72;
+        const int n = nf * 72;
+        int r = 0, c = lane;
+        for (int q = lane; q < n; q += 32) {
+            tile[r * kPosePitch + c] = src[q];
+            c += 32;
+            if (c >= 72) { c -= 72; ++r; }
+        }
+    }
+    __syncwarp();
+    const bool live = lane < nf;
+    const int64_t i = f0 + lane;
+    const T* p = tile + lane * kPosePitch;
+    const uint32_t debug_mask = dbg.mask;
+    const bool stage_dbg = n_debug <= kDebugStageJoints;
+    double* dtile = s_dbg[warp];
+    auto emit = [&](int j, double ex, double ey, double ez) {
+        const int slot = dbg.slot[j];
+        double* e = stage_dbg ? dtile + lane * kDebugPitch + slot * 3 : euler_out + (i * n_debug + slot) * 3;
+        if (stage_dbg || live) { e[0] = ex; e[1] = ey; e[2] = ez; }
+    };
     Angles A;
     bool bad = false;
 #pragma unroll
@@ -472,10 +523,7 @@ score_pose_kernel(const T* __restrict__ pose, const prk_addinfo* __restrict__ in
         bad |= euler_from_axis_angle<sizeof(T) == 4>((double)p[j * 3 + 0], (double)p[j * 3 + 1],
                                                     (double)p[j * 3 + 2], ex, ey, ez);
         A.a[s][0] = ex; A.a[s][1] = ey; A.a[s][2] = ez;
-        if (debug_mask & (1u << j)) {
-            double* e = euler_out + (i * n_debug + debug_slot[j]) * 3;
-            e[0] = ex; e[1] = ey; e[2] = ez;
-        }
+        if (debug_mask & (1u << j)) emit(j, ex, ey, ez);
     }
     // debug joints that are not scored
     uint32_t rest = debug_mask & ~0x3F7038u;   // bits of joints 3,4,5,12,13,14,16..21 cleared
@@ -485,14 +533,45 @@ score_pose_kernel(const T* __restrict__ pose, const prk_addinfo* __restrict__ in
         double ex, ey, ez;
         euler_from_axis_angle<sizeof(T) == 4>((double)p[j * 3 + 0], (double)p[j * 3 + 1],
                                               (double)p[j * 3 + 2], ex, ey, ez);
-        double* e = euler_out + (i * n_debug + debug_slot[j]) * 3;
-        e[0] = ex; e[1] = ey; e[2] = ez;
+        emit(j, ex, ey, ez);
     }
-    score_and_store(A, info, track, i, which, bad ? 1 : 0, out);
+    alignas(16) prk_score_rec r;
+    {
+        uint8_t flags = bad ? 1 : 0;
+        const prk_addinfo* ai = track_info(info, n_tracks, track, live ? i : f0, flags);
+        score_frame(A, ai, which, flags, r);
+    }
+    {   // records: lane l holds the two 16-byte halves of frame f0 + l; store k writes the 512 contiguous bytes of
+        // frames f0 + 16k .. f0 + 16k + 15 (lane l: frame 16k + l/2, half l & 1)
+        const uint4* h = reinterpret_cast<const uint4*>(&r);
+        uint4* dst = reinterpret_cast<uint4*>(out + f0);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int src_lane = 16 * k + (lane >> 1);
+            uint4 a, b;
+            a.x = __shfl_sync(0xffffffffu, h[0].x, src_lane); a.y = __shfl_sync(0xffffffffu, h[0].y, src_lane);
+            a.z = __shfl_sync(0xffffffffu, h[0].z, src_lane); a.w = __shfl_sync(0xffffffffu, h[0].w, src_lane);
+            b.x = __shfl_sync(0xffffffffu, h[1].x, src_lane); b.y = __shfl_sync(0xffffffffu, h[1].y, src_lane);
+            b.z = __shfl_sync(0xffffffffu, h[1].z, src_lane); b.w = __shfl_sync(0xffffffffu, h[1].w, src_lane);
+            if (src_lane < nf) dst[32 * k + lane] = (lane & 1) ? b : a;
+        }
+    }
+    if (n_debug > 0 && stage_dbg) {   // coalesced copy of the staged Euler sequences: nf rows of n_debug * 3 doubles
+        __syncwarp();
+        const int w = n_debug * 3, n = nf * w;
+        double* dst = euler_out + f0 * w;
+        int rr = 0, c = lane;
+        while (c >= w) { c -= w; ++rr; }
+        for (int q = lane; q < n; q += 32) {
+            dst[q] = dtile[rr * kDebugPitch + c];
+            c += 32;
+            while (c >= w) { c -= w; ++rr; }
+        }
+    }
 }
 
 __global__ void __launch_bounds__(128)
-score_euler_kernel(const double* __restrict__ euler, const prk_addinfo* __restrict__ info,
+score_euler_kernel(const double* __restrict__ euler, const prk_addinfo* __restrict__ info, int32_t n_tracks,
                    const int32_t* __restrict__ track, int64_t B, uint32_t which,
                    prk_score_rec* __restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -504,7 +583,7 @@ score_euler_kernel(const double* __restrict__ euler, const prk_addinfo* __restri
         const int j = slot_joint(s);
         A.a[s][0] = e[j * 3 + 0]; A.a[s][1] = e[j * 3 + 1]; A.a[s][2] = e[j * 3 + 2];
     }
-    score_and_store(A, info, track, i, which, 0, out);
+    score_and_store(A, info, n_tracks, track, i, which, 0, out);
 }
 
 template <typename T>
@@ -548,12 +627,12 @@ score_hist_kernel(const prk_score_rec* __restrict__ recs, int64_t B, uint32_t wh
 constexpr int kFramesPerBlockLanes = 8;
 template <typename T>
 __global__ void __launch_bounds__(kFramesPerBlockLanes * 16)
-score_pose_lanes_kernel(const T* __restrict__ pose, const prk_addinfo* __restrict__ info,
+score_pose_lanes_kernel(const T* __restrict__ pose, const prk_addinfo* __restrict__ info, int32_t n_tracks,
                         const int32_t* __restrict__ track, int64_t B, uint32_t which,
                         prk_score_rec* __restrict__ out) {
     __shared__ double s_e[kFramesPerBlockLanes][N_SLOTS][3];
     __shared__ __align__(16) prk_score_rec s_rec[kFramesPerBlockLanes];
-    __shared__ int s_bad[kFramesPerBlockLanes];
+    __shared__ int s_bad[kFramesPerBlockLanes];      // flags of the frame: bit 0 non-finite rotation, bit 1 track id out of range
     const int fl = threadIdx.x >> 4, slot = threadIdx.x & 15;
     const int64_t i = (int64_t)blockIdx.x * kFramesPerBlockLanes + fl;
     const bool live = i < B;
@@ -576,50 +655,51 @@ score_pose_lanes_kernel(const T* __restrict__ pose, const prk_addinfo* __restric
         Angles A;
 #pragma unroll
         for (int s = 0; s < N_SLOTS; ++s) { A.a[s][0] = s_e[fl][s][0]; A.a[s][1] = s_e[fl][s][1]; A.a[s][2] = s_e[fl][s][2]; }
-        const prk_addinfo* ai = info + (track ? track[i] : 0);
+        uint8_t oob = 0;
+        const prk_addinfo* ai = track_info(info, n_tracks, track, i, oob);
+        if (oob && slot == 0) atomicOr(&s_bad[fl], 2);
         if (slot == 0 && (which & PRK_SCORE_REBA)) reba_frame(A, ai->reba, s_rec[fl]);
         if (slot == 1 && (which & PRK_SCORE_RULA)) rula_frame(A, ai->rula, s_rec[fl]);
     }
     __syncwarp();
     if (live && slot == 0) {
-        s_rec[fl].flags = (uint8_t)(s_bad[fl] ? 1 : 0);
+        s_rec[fl].flags = (uint8_t)s_bad[fl];
         store_rec(out + i, s_rec[fl]);
     }
 }
 
 static inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
 
-cudaError_t launch_score_pose(const void* d_pose, int pose_dtype, const prk_addinfo* d_info,
+cudaError_t launch_score_pose(const void* d_pose, int pose_dtype, const prk_addinfo* d_info, int32_t n_tracks,
                               const int32_t* d_track, int64_t B, uint32_t which,
-                              prk_score_rec* d_out, double* d_euler_out, uint32_t debug_mask,
-                              const int8_t* debug_slot, int n_debug, cudaStream_t s) {
+                              prk_score_rec* d_out, double* d_euler_out, const DebugSlots& dbg, int n_debug,
+                              cudaStream_t s) {
     if (B == 0) return cudaSuccess;
     if (n_debug == 0 && B <= 131072) {   // latency-bound regime: spread each frame over 16 lanes
         const unsigned g = grid_for(B, kFramesPerBlockLanes);
         if (pose_dtype == PRK_DTYPE_F32)
-            score_pose_lanes_kernel<float><<<g, kFramesPerBlockLanes * 16, 0, s>>>((const float*)d_pose, d_info, d_track, B, which, d_out);
+            score_pose_lanes_kernel<float><<<g, kFramesPerBlockLanes * 16, 0, s>>>((const float*)d_pose, d_info, n_tracks, d_track, B, which, d_out);
         else
-            score_pose_lanes_kernel<double><<<g, kFramesPerBlockLanes * 16, 0, s>>>((const double*)d_pose, d_info, d_track, B, which, d_out);
+            score_pose_lanes_kernel<double><<<g, kFramesPerBlockLanes * 16, 0, s>>>((const double*)d_pose, d_info, n_tracks, d_track, B, which, d_out);
         count_launch();
         return cudaGetLastError();
     }
+    const unsigned g = grid_for(B, kScoreWarps * 32);
     if (pose_dtype == PRK_DTYPE_F32)
-        score_pose_kernel<float><<<grid_for(B, 128), 128, 0, s>>>(
-            (const float*)d_pose, d_info, d_track, B, which, d_out, d_euler_out, debug_mask,
-            debug_slot, n_debug);
+        score_pose_kernel<float><<<g, kScoreWarps * 32, 0, s>>>(
+            (const float*)d_pose, d_info, n_tracks, d_track, B, which, d_out, d_euler_out, dbg, n_debug);
     else
-        score_pose_kernel<double><<<grid_for(B, 128), 128, 0, s>>>(
-            (const double*)d_pose, d_info, d_track, B, which, d_out, d_euler_out, debug_mask,
-            debug_slot, n_debug);
+        score_pose_kernel<double><<<g, kScoreWarps * 32, 0, s>>>(
+            (const double*)d_pose, d_info, n_tracks, d_track, B, which, d_out, d_euler_out, dbg, n_debug);
     count_launch();
     return cudaGetLastError();
 }
 
-cudaError_t launch_score_euler(const double* d_euler, const prk_addinfo* d_info,
+cudaError_t launch_score_euler(const double* d_euler, const prk_addinfo* d_info, int32_t n_tracks,
                                const int32_t* d_track, int64_t B, uint32_t which,
                                prk_score_rec* d_out, cudaStream_t s) {
     if (B == 0) return cudaSuccess;
-    score_euler_kernel<<<grid_for(B, 128), 128, 0, s>>>(d_euler, d_info, d_track, B, which, d_out);
+    score_euler_kernel<<<grid_for(B, 128), 128, 0, s>>>(d_euler, d_info, n_tracks, d_track, B, which, d_out);
     count_launch();
     return cudaGetLastError();
 }

@@ -135,12 +135,33 @@ def load_smpl_pkl(path: str, gender: str = 'neutral') -> SMPLModelData:
         gender=gender, synthetic=False)
 
 
-def get_model_data(gender: str = 'neutral', model_root: str | None = None) -> SMPLModelData:
-    """Real model if ``model_root/SMPL_<GENDER>.pkl`` exists, else synthetic."""
+def synthetic_allowed() -> bool:
+    return os.environ.get('PRK_SYNTHETIC_SMPL', '') not in ('', '0')
+
+
+def get_model_data(gender: str = 'neutral', model_root: str | None = None,
+                   allow_synthetic: bool | None = None) -> SMPLModelData:
+    """``model_root/SMPL_<GENDER>.pkl`` (read without chumpy).
+
+    A missing file raises ``FileNotFoundError`` exactly like the reference's ``open()``
+    (serialization.py:10).  The synthetic SMPL-shaped model is only handed out on request:
+    ``allow_synthetic=True`` or the environment variable ``PRK_SYNTHETIC_SMPL=1`` (tests, bench) --
+    and says so with a warning, because its vertices and joints mean nothing anatomically."""
     if gender not in GENDER_FILE:
         raise KeyError(gender)
+    path = None
     if model_root is not None:
-        p = os.path.join(model_root, GENDER_FILE[gender])
-        if os.path.isfile(p):
-            return load_smpl_pkl(p, gender)
+        path = os.path.join(model_root, GENDER_FILE[gender])
+        if os.path.isfile(path):
+            return load_smpl_pkl(path, gender)
+    if allow_synthetic is None:
+        allow_synthetic = synthetic_allowed()
+    if not allow_synthetic:
+        raise FileNotFoundError(
+            f'SMPL model file {path or GENDER_FILE[gender]!r} not found (the licensed .pkl files are not shipped); '
+            'pass model_data=synthetic_smpl(...) / allow_synthetic=True or set PRK_SYNTHETIC_SMPL=1 to run on the '
+            'synthetic SMPL-shaped model instead')
+    import warnings
+    warnings.warn(f'poserisk_release_b200: using the SYNTHETIC SMPL-shaped {gender} model '
+                  f'({path or "no model_root"} not found); vertices and joints are not anatomical', stacklevel=2)
     return synthetic_smpl(gender)

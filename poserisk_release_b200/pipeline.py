@@ -21,11 +21,14 @@ GENDERS = ('neutral', 'female', 'male')
 
 
 class PoseRiskEngine:
-    def __init__(self, device=None, genders=('neutral',), model_root=None):
+    def __init__(self, device=None, genders=('neutral',), model_root=None, allow_synthetic=None, model_data=None):
+        """model_data: optional {gender: SMPLModelData}; otherwise ``model_root/SMPL_<GENDER>.pkl`` is read
+        (FileNotFoundError when missing, unless allow_synthetic / PRK_SYNTHETIC_SMPL=1: model_provider.get_model_data)."""
         self.device = _runtime.require_cuda(device)
         self.models = {}
         for g in genders:
-            self.models[g] = _runtime.ModelHandle(get_model_data(g, model_root), self.device)
+            data = (model_data or {}).get(g) or get_model_data(g, model_root, allow_synthetic)
+            self.models[g] = _runtime.ModelHandle(data, self.device)
         self._host_ws = None
 
     # ------------------------------------------------------------------ device path
@@ -38,10 +41,15 @@ class PoseRiskEngine:
         return t.reshape(B, n)
 
     def run(self, pose, betas=None, trans=None, add_info=None, track_of_frame=None, gender='neutral',
-            want_verts=True, center_idx=None, verts_out=None, joints_out=None, scores_out=None):
-        """pose (B,72) float32 CUDA tensor.  Returns dict(verts|None, joints, scores) where
+            want_verts=True, center_idx=None, verts_out=None, joints_out=None, scores_out=None,
+            debug_joints=None, euler_out=None, exchange=None, frame_offset=0):
+        """pose (B,72) float32 CUDA tensor.  Returns dict(verts|None, joints, scores[, euler]) where
         scores is a (B,32) uint8 tensor of prk_score_rec.  The *_out tensors, when given, receive
-        the results (no allocation in the call)."""
+        the results (no allocation in the call).
+        debug_joints: joint ids whose Euler sequences (B,k,3) float64 are emitted as well (the
+        --debug_joints output, base.py:144-146).
+        exchange: a distributed.ScoreExchange -- the records (and Euler rows) of this rank are all-gathered
+        into every rank's buffer at frame `frame_offset`, underneath the body-model kernels."""
         dev = self.device
         B = pose.shape[0]
         pose = self._dev_f32(pose, B, 72)
@@ -49,48 +57,71 @@ class PoseRiskEngine:
         trans = self._dev_f32(trans, B, 3)
         info = add_info if isinstance(add_info, torch.Tensor) else _runtime.addinfo_tensor(add_info, dev)
         track = None if track_of_frame is None else torch.as_tensor(track_of_frame, dtype=torch.int32).to(dev).contiguous()
+        ids = None if debug_joints is None else np.ascontiguousarray(debug_joints, np.int32)
+        n_debug = 0 if ids is None else len(ids)
         h = self.models[gender]
+        comm_s = comm_e = None
+        if exchange is not None:
+            comm_s, comm_e = exchange.native_handles(n_debug)
         with torch.cuda.device(dev):
             verts = None
             if want_verts:
                 verts = verts_out if verts_out is not None else torch.empty((B, 6890, 3), dtype=torch.float32, device=dev)
             joints = joints_out if joints_out is not None else torch.empty((B, 24, 3), dtype=torch.float32, device=dev)
             scores = scores_out if scores_out is not None else torch.empty((B, 32), dtype=torch.uint8, device=dev)
-            if B > 0:
+            euler = None
+            if n_debug:
+                euler = euler_out if euler_out is not None else torch.empty((B, n_debug, 3), dtype=torch.float64, device=dev)
+            if B > 0 or comm_s is not None:
                 key = (B, want_verts, gender)
                 if getattr(self, '_ws_key', None) != key:      # workspace size per (batch, mode): queried once
-                    self._ws_key, self._ws_bytes = key, h.workspace_bytes(B, not want_verts)
+                    self._ws_key, self._ws_bytes = key, h.workspace_bytes(max(B, 1), not want_verts)
                 ws, ws_bytes, _keep = _runtime.workspace.get(dev, self._ws_bytes)
                 _lib.check(_lib.lib().prk_pipeline(
                     h.handle, _runtime.ptr(pose), _runtime.ptr(betas), _runtime.ptr(trans),
-                    -1 if center_idx is None else int(center_idx), _runtime.ptr(info), _runtime.ptr(track), B,
-                    _runtime.ptr(verts), _runtime.ptr(joints), _runtime.ptr(scores), ws, ws_bytes,
-                    _runtime.stream_ptr(dev)))
-        return {'verts': verts, 'joints': joints, 'scores': scores}
+                    -1 if center_idx is None else int(center_idx), _runtime.ptr(info), info.shape[0], _runtime.ptr(track), B,
+                    _runtime.ptr(verts), _runtime.ptr(joints), _runtime.ptr(scores), _runtime.ptr(euler),
+                    None if ids is None else ids.ctypes.data_as(C.c_void_p), n_debug, comm_s, comm_e, int(frame_offset),
+                    ws, ws_bytes, _runtime.stream_ptr(dev)))
+        out = {'verts': verts, 'joints': joints, 'scores': scores}
+        if n_debug:
+            out['euler'] = euler
+        return out
 
-    def run_tracks(self, pose, betas, trans, add_infos, track_of_frame, gender_of_track, want_verts=True):
-        """Mixed-gender multi-person batch: frames are grouped by their track's gender, each
-        group goes through its own model; outputs are scattered back to frame order."""
+    def run_tracks(self, pose, betas, trans, add_infos, track_of_frame, gender_of_track, want_verts=True,
+                   verts_out=None, joints_out=None, scores_out=None):
+        """Mixed-gender multi-person batch (BASELINE.json config 4).  Frames of one track are contiguous
+        (a track is one person's clip), so the batch is a sequence of RUNS of equal gender: every run goes
+        through its gender's model as a slice of the caller's tensors and writes straight into slices of the
+        outputs -- no index gather, no scatter, no device synchronisation.  `track_of_frame` must be a HOST
+        array (it is metadata the caller built; base.py:72-73 picks tracks on the host too)."""
         dev = self.device
-        track = torch.as_tensor(track_of_frame, dtype=torch.int64).to(dev)
         B = pose.shape[0]
-        info = _runtime.addinfo_tensor(add_infos, dev)
-        g_of_t = torch.tensor([GENDERS.index(g) for g in gender_of_track], device=dev)
-        g_of_f = g_of_t[track]
-        joints = torch.empty((B, 24, 3), dtype=torch.float32, device=dev)
-        scores = torch.empty((B, 32), dtype=torch.uint8, device=dev)
-        verts = torch.empty((B, 6890, 3), dtype=torch.float32, device=dev) if want_verts else None
-        for gi, g in enumerate(GENDERS):
-            idx = torch.nonzero(g_of_f == gi).squeeze(1)
-            if idx.numel() == 0:
-                continue
-            r = self.run(pose[idx], None if betas is None else betas[idx], None if trans is None else trans[idx],
-                         info, track[idx].to(torch.int32), gender=g, want_verts=want_verts)
-            joints[idx] = r['joints']
-            scores[idx] = r['scores']
-            if want_verts:
-                verts[idx] = r['verts']
-        return {'verts': verts, 'joints': joints, 'scores': scores}
+        track_h = np.ascontiguousarray(track_of_frame.cpu().numpy() if isinstance(track_of_frame, torch.Tensor)
+                                       else track_of_frame, dtype=np.int32).reshape(B)
+        n_tracks = len(gender_of_track)
+        if B and (track_h.min() < 0 or track_h.max() >= n_tracks):
+            raise IndexError('track_of_frame holds an id outside gender_of_track')    # list index in the reference
+        g_of_t = np.array([GENDERS.index(g) for g in gender_of_track], np.int32)
+        g_of_f = g_of_t[track_h] if B else np.zeros(0, np.int32)
+        cuts = np.flatnonzero(np.diff(g_of_f)) + 1                   # run boundaries
+        starts = np.concatenate(([0], cuts)) if B else np.zeros(0, np.int64)
+        ends = np.concatenate((cuts, [B])) if B else np.zeros(0, np.int64)
+        pose = self._dev_f32(pose, B, 72)
+        betas = self._dev_f32(betas, B, 10)
+        trans = self._dev_f32(trans, B, 3)
+        info = add_infos if isinstance(add_infos, torch.Tensor) else _runtime.addinfo_tensor(add_infos, dev)
+        track_d = torch.from_numpy(track_h).to(dev)
+        joints = joints_out if joints_out is not None else torch.empty((B, 24, 3), dtype=torch.float32, device=dev)
+        scores = scores_out if scores_out is not None else torch.empty((B, 32), dtype=torch.uint8, device=dev)
+        verts = None
+        if want_verts:
+            verts = verts_out if verts_out is not None else torch.empty((B, 6890, 3), dtype=torch.float32, device=dev)
+        for lo, hi in zip(starts.tolist(), ends.tolist()):
+            self.run(pose[lo:hi], None if betas is None else betas[lo:hi], None if trans is None else trans[lo:hi],
+                     info, track_d[lo:hi], gender=GENDERS[int(g_of_f[lo])], want_verts=want_verts,
+                     verts_out=None if verts is None else verts[lo:hi], joints_out=joints[lo:hi], scores_out=scores[lo:hi])
+        return {'verts': verts, 'joints': joints, 'scores': scores, 'runs': len(starts)}
 
     def euler_debug(self, pose, joint_ids, add_info, track_of_frame=None):
         """Scores + Euler sequences of the listed joints (the --debug_joints output,
@@ -106,14 +137,14 @@ class PoseRiskEngine:
         eul = torch.empty((B, len(ids), 3), dtype=torch.float64, device=dev)
         with torch.cuda.device(dev):
             _lib.check(_lib.lib().prk_score_pose(
-                _runtime.ptr(pose), _lib.PRK_DTYPE_F64 if is64 else _lib.PRK_DTYPE_F32, _runtime.ptr(info),
+                _runtime.ptr(pose), _lib.PRK_DTYPE_F64 if is64 else _lib.PRK_DTYPE_F32, _runtime.ptr(info), info.shape[0],
                 _runtime.ptr(track), B, _lib.PRK_SCORE_REBA | _lib.PRK_SCORE_RULA, _runtime.ptr(scores),
                 _runtime.ptr(eul), ids.ctypes.data_as(C.c_void_p), len(ids), _runtime.stream_ptr(dev)))
         return scores, eul
 
     # ------------------------------------------------------------------ host path
     def run_host(self, pose, betas, trans, add_infos, track_of_frame, joints_out, scores_out, gender='neutral',
-                 verts_out=None, center_idx=None):
+                 verts_out=None, center_idx=None, exchange=None, frame_offset=0):
         """Host buffers in, host buffers out (torch CPU tensors, ideally pinned):
         pose (B,72) f32, betas (B,10)|None, trans (B,3)|None, joints_out (B,24,3) f32,
         scores_out (B,32) uint8; verts_out is an optional CUDA tensor.  Asynchronous on the
@@ -130,7 +161,9 @@ class PoseRiskEngine:
                 h.handle, _runtime.ptr(pose), _runtime.ptr(betas), _runtime.ptr(trans),
                 -1 if center_idx is None else int(center_idx), info.ctypes.data_as(C.c_void_p), info.shape[0],
                 None if track is None else track.ctypes.data_as(C.c_void_p), B, _runtime.ptr(verts_out),
-                _runtime.ptr(joints_out), _runtime.ptr(scores_out), ws, ws_bytes, _runtime.stream_ptr(dev)))
+                _runtime.ptr(joints_out), _runtime.ptr(scores_out),
+                None if exchange is None else exchange.native_handles(0)[0], int(frame_offset),
+                ws, ws_bytes, _runtime.stream_ptr(dev)))
         self._keep = (info, track)   # pageable host arrays must outlive the async copies
         # device copy of the score records inside the workspace (what a multi-GPU caller all-gathers)
         base = ws.value - _keep.data_ptr()

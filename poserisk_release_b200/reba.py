@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from . import _lib
+from . import _lib, _scorer
 from ._scorer import JOINT_NAME, score_euler_records
 
 
@@ -84,23 +84,12 @@ class REBA:
                                                 f"R {P('R_Wrist', 1):.1f},{P('R_Wrist', 0):.1f}")
         return log
 
+    # (highest score of the band, level, text): reba.py:83-104; the last band is open-ended
+    ACTION_BANDS = ((1, 1, "Negligible risk"),
+                    (3, 2, "Low risk. Change may be needed."),
+                    (7, 3, "Medium risk. Further Investigate. Change Soon."),
+                    (10, 4, "High risk. Investigate and implement change"),
+                    (None, 5, "Very high risk. Implement change"))
+
     def action_level(self, score):
-        score = round(score)
-        action_level = None
-        action_name = None
-        if score in [1]:
-            action_level = 1
-            action_name = "Negligible risk"
-        elif score in [2, 3]:
-            action_level = 2
-            action_name = "Low risk. Change may be needed."
-        elif score in [4, 5, 6, 7]:
-            action_level = 3
-            action_name = "Medium risk. Further Investigate. Change Soon."
-        elif score in [8, 9, 10]:
-            action_level = 4
-            action_name = "High risk. Investigate and implement change"
-        elif score >= 11:
-            action_level = 5
-            action_name = "Very high risk. Implement change"
-        return action_level, action_name
+        return _scorer.action_band(self.ACTION_BANDS, score)

@@ -8,6 +8,8 @@ from per-frame Python lists.
   save_csv_pose_log      lib/core/base.py:329-350           debug/pose_log.csv
   save_csv               lib/core/base.py:352-397           debug/<TITLE>_score_log.csv, <TITLE>_eval_pose_log.csv
   write_result_txt       lib/core/base.py:158-165,176-183   reba_result.txt / rula_result.txt
+  save_obj               lib/utils/vis_utils.py:238-245     Wavefront .obj of one frame's mesh (the debug
+                                                            smpl_model.obj of base.py:273-282)
 
 ``timestamp`` is the reference's ``(0, frames, img_num)`` tuple (base.py:112): the CSVs get one row per
 frame index in ``range(timestamp[0], timestamp[-1])`` and only the frames listed in ``timestamp[1]`` carry
@@ -92,3 +94,30 @@ def result_text(final_score, action_level, action_name, title='REBA'):
 def write_result_txt(final_score, action_level, action_name, output_path, title='REBA'):
     with open(osp.join(output_path, title.lower() + '_result.txt'), 'w') as f:
         f.write(result_text(final_score, action_level, action_name, title))
+
+
+def save_obj(v, f=None, file_name=''):
+    """Wavefront .obj of one mesh: a `v x y z` line per vertex with Python's shortest-repr number text (what
+    ``str()`` of the element gives, so float32 input prints as float32), then -- when faces are given --
+    one `f a/a b/b c/c` line per triangle with 1-based indices.  Accepts numpy arrays or torch tensors (a CUDA
+    vertex tensor is copied to the host once)."""
+    if hasattr(v, 'detach'):
+        v = v.detach().cpu().numpy()
+    if f is not None and hasattr(f, 'detach'):
+        f = f.detach().cpu().numpy()
+    lines = ['v %s %s %s\n' % (str(p[0]), str(p[1]), str(p[2])) for p in v]
+    if f is not None:
+        for tri in f:
+            a, b, c = tri[0] + 1, tri[1] + 1, tri[2] + 1
+            lines.append('f %s/%s %s/%s %s/%s\n' % (a, a, b, b, c, c))
+    with open(file_name, 'w') as out:
+        out.writelines(lines)
+
+
+def save_debug_mesh(verts_m, faces, output_path):
+    """The debug mesh of base.py:273-282: one frame's vertices (metres, (6890, 3)) scaled to millimetres as
+    float32 and written to ``output_path/smpl_model.obj``."""
+    if hasattr(verts_m, 'detach'):
+        verts_m = verts_m.detach().cpu().numpy()
+    v = np.asarray(verts_m).astype(np.float32).reshape(-1, 3) * 1000
+    save_obj(v, faces, osp.join(output_path, 'smpl_model.obj'))

@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from . import _lib
+from . import _lib, _scorer
 from ._scorer import JOINT_NAME, score_euler_records
 
 
@@ -84,20 +84,11 @@ class RULA:
         log['trunk_side_bending'] = f"{P('Torso', 2):.1f}"
         return log
 
+    # (highest score of the band, level, text): rula.py:100-118; the last band is open-ended
+    ACTION_BANDS = ((2, 1, "Acceptable posture"),
+                    (4, 2, "Further investigation, change may be needed"),
+                    (6, 3, "Further investigation, change soon"),
+                    (None, 4, "Investigate and implement change"))
+
     def action_level(self, score):
-        score = round(score)
-        action_level = None
-        action_name = None
-        if score in [1, 2]:
-            action_level = 1
-            action_name = "Acceptable posture"
-        elif score in [3, 4]:
-            action_level = 2
-            action_name = "Further investigation, change may be needed"
-        elif score in [5, 6]:
-            action_level = 3
-            action_name = "Further investigation, change soon"
-        elif score >= 7:
-            action_level = 4
-            action_name = "Investigate and implement change"
-        return action_level, action_name
+        return _scorer.action_band(self.ACTION_BANDS, score)

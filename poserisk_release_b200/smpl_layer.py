@@ -18,43 +18,38 @@ from . import _lib, _runtime
 from .model_provider import GENDER_FILE, SMPLModelData, get_model_data
 
 
+# (buffer name, field of SMPLModelData, leading batch axis): the seven tensors the reference layer registers
+# (smpl_layer.py:40-56) -- their names are API, main/run.py and lib/utils/smpl.py read th_faces / th_J_regressor.
+_BUFFERS = (('th_betas', 'betas', True), ('th_shapedirs', 'shapedirs', False), ('th_posedirs', 'posedirs', False),
+            ('th_v_template', 'v_template', True), ('th_J_regressor', 'J_regressor', False),
+            ('th_weights', 'weights', False))
+
+
 class SMPL_Layer(Module):
     __constants__ = ['kintree_parents', 'gender', 'center_idx', 'num_joints']
 
     def __init__(self, center_idx=None, gender='neutral', model_root='smpl/native/models',
-                 model_data: SMPLModelData | None = None):
-        """
-        Args:
-            center_idx: index of center joint in our computations,
-            model_root: path to pkl files for the model
-            gender: 'neutral' (default) or 'female' or 'male'
-            model_data: (extension) pre-loaded constants; default loads
-                ``model_root/SMPL_<GENDER>.pkl`` or, when that licensed file is absent,
-                the synthetic SMPL-shaped model.
-        """
+                 model_data: SMPLModelData | None = None, allow_synthetic: bool | None = None):
+        """center_idx: joint whose position is subtracted from vertices and joints when no translation is
+        given (None: nothing is subtracted); gender: 'neutral' | 'female' | 'male', selects
+        ``model_root/SMPL_<GENDER>.pkl``.  Extensions: ``model_data`` hands the constants over directly,
+        ``allow_synthetic`` (or PRK_SYNTHETIC_SMPL=1) permits the synthetic stand-in when the licensed file
+        is missing -- otherwise that is a FileNotFoundError, as in the reference."""
         super().__init__()
-        self.center_idx = center_idx
-        self.gender = gender
-        if gender in GENDER_FILE:                      # smpl_layer.py:30-35
+        self.center_idx, self.gender = center_idx, gender
+        if gender in GENDER_FILE:
             self.model_path = os.path.join(model_root, GENDER_FILE[gender])
-        data = model_data if model_data is not None else get_model_data(gender, model_root)
-        self.smpl_data = data
-
-        self.register_buffer('th_betas', torch.Tensor(data.betas).unsqueeze(0))
-        self.register_buffer('th_shapedirs', torch.Tensor(data.shapedirs))
-        self.register_buffer('th_posedirs', torch.Tensor(data.posedirs))
-        self.register_buffer('th_v_template', torch.Tensor(data.v_template).unsqueeze(0))
-        self.register_buffer('th_J_regressor', torch.Tensor(np.array(data.J_regressor)))
-        self.register_buffer('th_weights', torch.Tensor(data.weights))
-        self.register_buffer('th_faces', torch.Tensor(data.faces.astype(np.int32)).long())
-
-        self.vertice_segmentation = torch.argmax(self.th_weights, dim=1)
-
-        # Kinematic chain params
-        self.kintree_table = data.kintree_table
-        parents = list(self.kintree_table[0].tolist())
-        self.kintree_parents = parents
-        self.num_joints = len(parents)  # 24
+        if model_data is None:
+            model_data = get_model_data(gender, model_root, allow_synthetic)
+        self.smpl_data = model_data
+        for name, field, batched in _BUFFERS:
+            t = torch.tensor(np.asarray(getattr(model_data, field), dtype=np.float32))
+            self.register_buffer(name, t.unsqueeze(0) if batched else t)
+        self.register_buffer('th_faces', torch.from_numpy(np.asarray(model_data.faces).astype(np.int64)))
+        self.vertice_segmentation = self.th_weights.argmax(dim=1)     # dominant joint per vertex
+        self.kintree_table = model_data.kintree_table
+        self.kintree_parents = [int(p) for p in self.kintree_table[0]]
+        self.num_joints = len(self.kintree_parents)
         self._handles = {}
 
     # -- device-side model ---------------------------------------------------
@@ -79,13 +74,11 @@ class SMPL_Layer(Module):
         return t.to(device=device, dtype=torch.float32).reshape(B, width).contiguous()
 
     def forward(self, th_pose_axisang, th_betas=torch.zeros(1), th_trans=torch.zeros(1), want_verts=True):
-        """
-        Args:
-        th_pose_axisang (Tensor (batch_size x 72)): pose parameters in axis-angle representation
-        th_betas (Tensor (batch_size x 10)): if provided, uses given shape parameters
-        th_trans (Tensor (batch_size x 3)): if provided, applies trans to joints and vertices
-        want_verts (extension): False selects the joints-only fast path and returns (None, joints)
-        """
+        """th_pose_axisang (B, 72): axis-angle pose, root first.  th_betas (B, 10): per-frame shape; the
+        default / an all-zero batch selects the model's own betas.  th_trans (B, 3): added to vertices and
+        joints; the default / an all-zero batch means no translation (then ``center_idx`` applies).
+        want_verts=False (extension) skips the mesh and returns (None, joints).
+        Returns (vertices (B, 6890, 3), joints (B, 24, 3)) in metres on the input's device."""
         out_device = th_pose_axisang.device
         device = _runtime.require_cuda(out_device)
         batch_size = th_pose_axisang.shape[0]
@@ -107,5 +100,4 @@ class SMPL_Layer(Module):
         if out_device != device:
             joints = joints.to(out_device)
             verts = verts.to(out_device) if verts is not None else None
-        # Vertices and joints in meters
         return verts, joints

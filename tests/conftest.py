@@ -3,6 +3,9 @@ import sys
 
 import pytest
 
+# the licensed SMPL .pkl files are not in the repo: tests opt in to the synthetic SMPL-shaped model
+os.environ.setdefault('PRK_SYNTHETIC_SMPL', '1')
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, 'tests')):
     if p not in sys.path:

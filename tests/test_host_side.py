@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     from poserisk_release_b200 import _lib
     assert set(_lib.EXPORTS) == declared
     L.prk_abi_version.restype = ctypes.c_int
-    assert L.prk_abi_version() == 1
+    assert L.prk_abi_version() == _lib.ABI_VERSION == 2
     L.prk_strerror.restype = ctypes.c_char_p
     assert L.prk_strerror(0) == b'ok' and b'workspace' in L.prk_strerror(3)
     # struct sizes the Python side relies on
@@ -188,7 +188,7 @@ _GLOO_WORKER = r'''
 import os, sys
 sys.path.insert(0, {root!r})
 import torch, torch.distributed as dist
-from poserisk_release_b200.distributed import shard_range, all_gather_rows
+from poserisk_release_b200.distributed import shard_range, all_gather_rows, ScoreExchange, run_sharded, shard_tracks
 dist.init_process_group('gloo', rank=int(os.environ['RANK']), world_size=int(os.environ['WORLD_SIZE']))
 rank, world = dist.get_rank(), dist.get_world_size()
 for n in (10, 11, 4096):
@@ -196,6 +196,33 @@ for n in (10, 11, 4096):
     lo, hi = shard_range(n, rank, world)
     got = all_gather_rows(full[lo:hi].clone(), n)
     assert got.shape == full.shape and torch.equal(got, full), (n, rank)
+
+# run_sharded with a stand-in engine: scores AND debug Euler sequences are gathered into frame order
+class FakeEngine:
+    device = None
+    def run(self, pose, betas, trans, add_info=None, track_of_frame=None, want_verts=False, debug_joints=None,
+            exchange=None, frame_offset=0):
+        n = pose.shape[0]
+        assert exchange is not None and exchange.native_handles(len(debug_joints)) == (None, None)   # CPU: collective
+        scores = (pose[:, :32] * 7).to(torch.uint8)
+        euler = pose[:, :len(debug_joints) * 3].double().reshape(n, len(debug_joints), 3) + 0.5
+        return {'scores': scores, 'euler': euler, 'joints': pose[:, :72].reshape(n, 24, 3), 'verts': None}
+n = 1001
+pose = torch.arange(n * 72, dtype=torch.float32).reshape(n, 72) % 13
+out = run_sharded(FakeEngine(), pose, None, None, add_info=None, debug_joints=[12, 16, 17, 3])
+assert out['transport'] == 'nccl' and out['range'] == shard_range(n, rank, world)
+assert torch.equal(out['scores'], (pose[:, :32] * 7).to(torch.uint8))
+assert torch.equal(out['euler'], pose[:, :12].double().reshape(n, 4, 3) + 0.5)
+
+# config 4: whole tracks per rank, ragged shards gathered with explicit sizes
+lengths = [5, 7, 3, 9, 4]
+sh = shard_tracks(lengths, world)
+assert sh[0][0] == 0 and sh[-1][1] == len(lengths) and sh[-1][3] == sum(lengths)
+t0, t1, f0, f1 = sh[rank]
+full = torch.arange(sum(lengths) * 32, dtype=torch.int64).reshape(-1, 32).to(torch.uint8)
+ex = ScoreExchange(sum(lengths), None, 0, None, 'nccl')
+got, _ = ex.gather(full[f0:f1].clone(), f0, None, sizes=[s[3] - s[2] for s in sh])
+assert torch.equal(got, full)
 dist.barrier()
 dist.destroy_process_group()
 print('ok', rank)
@@ -205,7 +232,7 @@ print('ok', rank)
 def test_all_gather_rows_gloo_world2(tmp_path):
     """N>1 path on CPU: two ranks, ragged and equal shards, gathered rows in frame order."""
     script = tmp_path / 'worker.py'
-    script.write_text(_GLOO_WORKER.format(root=ROOT))
+    script.write_text(_GLOO_WORKER.replace('{root!r}', repr(ROOT)))
     env = dict(os.environ, MASTER_ADDR='127.0.0.1', MASTER_PORT='29571', WORLD_SIZE='2')
     procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)),
                               stdout=subprocess.PIPE, stderr=subprocess.STDOUT) for r in range(2)]
@@ -247,3 +274,70 @@ def test_report_writers_known_answers(tmp_path):
     assert rows[0] == ['Frame', 'Joint Pose', 'Neck'] and rows[2] == ['1', '', 'p1']
     txt = report.result_text((5.5, 7.0, float('nan'), 7, 4), 3, 'Medium risk.', 'RULA')
     assert txt.startswith('AVG Score: 5.5 \n%50 Score: 7.0 \n%10 Score: nan ') and txt.endswith('Action: Medium risk.')
+
+
+_COMPAT_PROBE = r'''
+import os, sys, json
+sys.path.insert(0, {root!r})
+import poserisk_release_b200
+sys.path.insert(0, os.path.join(os.path.dirname(poserisk_release_b200.__file__), 'compat'))   # INTEGRATION.md section 1
+# exactly the bare imports of lib/core/base.py:24-31 and lib/utils/smpl.py:5
+from smpl import SMPL
+from coord_utils import axis_angle_to_euler_angle, rot_to_angle, get_joint_cam
+from reba import REBA
+from rula import RULA
+from smplpytorch.pytorch.smpl_layer import SMPL_Layer
+mods = {{c.__name__: c.__module__ for c in (SMPL, REBA, RULA, SMPL_Layer, axis_angle_to_euler_angle, rot_to_angle, get_joint_cam)}}
+m = SMPL()
+assert isinstance(m.layer['female'], SMPL_Layer)
+print(json.dumps({{'mods': mods, 'model_path': m.model_path, 'layers': sorted(m.layer), 'jr': list(m.joint_regressor.shape)}}))
+'''
+
+
+def test_compat_shims_resolve_the_reference_imports(tmp_path):
+    """The drop-in mechanism itself: with compat/ first on sys.path the bare module names that base.py:24-31 and
+    smpl.py:5 import resolve to this package, and SMPL() builds its three layers through them."""
+    script = tmp_path / 'probe.py'
+    script.write_text(_COMPAT_PROBE.format(root=ROOT))
+    out = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=300,
+                         env=dict(os.environ, PRK_SYNTHETIC_SMPL='1'), cwd=str(tmp_path))
+    assert out.returncode == 0, out.stderr
+    got = json.loads(out.stdout.strip().splitlines()[-1])
+    assert all(v.startswith('poserisk_release_b200.') for v in got['mods'].values()), got['mods']
+    assert got['layers'] == ['female', 'male', 'neutral'] and got['jr'] == [29, 6890]
+    assert got['model_path'] == os.path.join('data', 'base_data', 'human_models')
+
+
+def test_missing_model_file_raises_unless_synthetic_is_requested(monkeypatch):
+    """serialization.py:10 open()s the .pkl: a wrong model_root must not silently give a random model."""
+    from poserisk_release_b200 import SMPL_Layer, model_provider
+    monkeypatch.delenv('PRK_SYNTHETIC_SMPL', raising=False)
+    with pytest.raises(FileNotFoundError, match='SMPL_NEUTRAL.pkl'):
+        SMPL_Layer(model_root='no/such/dir')
+    with pytest.raises(FileNotFoundError):
+        model_provider.get_model_data('male', None)
+    with pytest.warns(UserWarning, match='SYNTHETIC'):
+        lay = SMPL_Layer(model_root='no/such/dir', allow_synthetic=True)
+    assert lay.smpl_data.synthetic
+    lay = SMPL_Layer(model_data=model_provider.synthetic_smpl('female'), gender='female')      # explicit data: no warning needed
+    assert lay.smpl_data.gender == 'female'
+
+
+def test_action_levels_known_answers():
+    from poserisk_release_b200 import REBA, RULA
+    r, u = REBA(), RULA()
+    assert [r.action_level(s)[0] for s in (1, 2, 3, 4, 7, 8, 10, 11, 15)] == [1, 2, 2, 3, 3, 4, 4, 5, 5]
+    assert [u.action_level(s)[0] for s in (1, 2, 3, 4, 5, 6, 7, 9)] == [1, 1, 2, 2, 3, 3, 4, 4]
+    assert r.action_level(0) == (None, None) and u.action_level(-3) == (None, None)
+    assert r.action_level(7.4) == (3, "Medium risk. Further Investigate. Change Soon.")
+    assert u.action_level(6.5)[0] == 3 and u.action_level(6.51)[0] == 4        # round-half-even, like the reference
+
+
+def test_save_obj_known_answer(tmp_path):
+    from poserisk_release_b200 import report
+    v = np.array([[0.5, -1.25, 3.0], [1e-7, 2.0, 1234.5678]], np.float32)
+    f = np.array([[0, 1, 1]], np.uint32)
+    report.save_obj(v, f, str(tmp_path / 'm.obj'))
+    assert (tmp_path / 'm.obj').read_text() == 'v 0.5 -1.25 3.0\nv 1e-07 2.0 1234.5677\nf 1/1 2/2 2/2\n'
+    report.save_obj(v[:1].astype(np.float64), None, str(tmp_path / 'n.obj'))
+    assert (tmp_path / 'n.obj').read_text() == 'v 0.5 -1.25 3.0\n'

@@ -5,6 +5,7 @@ import os
 import types
 
 import numpy as np
+import torch
 import pytest
 
 from ref_harness import reference_available, load_reference, ref_log_to_parts
@@ -143,3 +144,62 @@ def test_report_writers_match_reference_text(tmp_path):
         final = (4.123, 5.5, 7.0, 9, 4)
         ns = {f'final_score_{var}': final, f'{var}_action_level': 3, f'{var}_action_name': 'Medium risk.'}
         assert report.result_text(final, 3, 'Medium risk.', title) == eval(expr, ns)
+
+
+def test_save_obj_matches_reference_bytes(tmp_path):
+    """report.save_obj against the reference's own function (lib/utils/vis_utils.py:238-245), compiled from its
+    source (vis_utils imports matplotlib/cv2 plotting helpers that are out of scope): float32 millimetre vertices as
+    base.py:279-281 passes them, with and without faces."""
+    import ast, filecmp, os.path as osp
+    from ref_harness import REF_ROOT
+    from poserisk_release_b200 import report
+    path = osp.join(REF_ROOT, 'lib', 'utils', 'vis_utils.py')
+    tree = ast.parse(open(path).read())
+    fn = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == 'save_obj']
+    ns = {}
+    exec(compile(ast.Module(body=fn, type_ignores=[]), path, 'exec'), ns)
+    m = synthetic_smpl('neutral')
+    rng = np.random.default_rng(9)
+    v = (rng.normal(0, 0.4, (6890, 3)).astype(np.float32) * 1000)
+    v[0] = [0.0, -0.0, 1e-5]
+    v[1] = [123456.789, 1e9, -3.4e-12]
+    faces = m.faces.astype(np.uint32)
+    ns['save_obj'](v, faces, str(tmp_path / 'ref.obj'))
+    report.save_obj(v, faces, str(tmp_path / 'new.obj'))
+    assert filecmp.cmp(tmp_path / 'ref.obj', tmp_path / 'new.obj', shallow=False)
+    ns['save_obj'](v[:50], None, str(tmp_path / 'ref2.obj'))
+    report.save_obj(torch.from_numpy(v[:50]), None, str(tmp_path / 'new2.obj'))
+    assert filecmp.cmp(tmp_path / 'ref2.obj', tmp_path / 'new2.obj', shallow=False)
+    # the int64 faces th_faces.numpy() gives (smpl.py:11) print the same text
+    ns['save_obj'](v[:50], m.faces[:20].astype(np.int64), str(tmp_path / 'ref3.obj'))
+    report.save_obj(v[:50], torch.from_numpy(m.faces[:20].astype(np.int64)), str(tmp_path / 'new3.obj'))
+    assert filecmp.cmp(tmp_path / 'ref3.obj', tmp_path / 'new3.obj', shallow=False)
+
+
+def test_smpl_wrapper_attributes_match_the_live_reference():
+    """SMPL() of lib/utils/smpl.py:7-45 against ours: every public attribute the reference sets, same values and
+    types (the three layers are compared through their buffers)."""
+    import importlib, sys
+    ref = load_reference()                       # puts lib/utils + lib/smplpytorch on sys.path, stubs ready_arguments
+    ref_smpl = importlib.import_module('smpl')   # the reference's lib/utils/smpl.py
+    assert ref_smpl.__file__.startswith(ref.root)
+    r = ref_smpl.SMPL()
+    from poserisk_release_b200.smpl import SMPL
+    o = SMPL()
+    public = [k for k in vars(r) if not k.startswith('_')]
+    assert sorted(public) == sorted(k for k in vars(o) if not k.startswith('_'))
+    for k in public:
+        a, b = getattr(r, k), getattr(o, k)
+        if k == 'layer':
+            assert sorted(a) == sorted(b)
+            for g in a:
+                for name in ('th_betas', 'th_shapedirs', 'th_posedirs', 'th_v_template', 'th_J_regressor', 'th_weights', 'th_faces'):
+                    ta, tb = getattr(a[g], name), getattr(b[g], name)
+                    assert ta.dtype == tb.dtype and ta.shape == tb.shape and torch.equal(ta, tb), (g, name)
+                assert a[g].kintree_parents == b[g].kintree_parents and a[g].num_joints == b[g].num_joints
+                assert a[g].model_path == b[g].model_path and a[g].gender == b[g].gender and a[g].center_idx == b[g].center_idx
+                assert torch.equal(a[g].vertice_segmentation, b[g].vertice_segmentation)
+        elif isinstance(a, np.ndarray):
+            assert a.dtype == b.dtype and a.shape == b.shape and np.array_equal(a, b), k
+        else:
+            assert type(a) is type(b) and a == b, k

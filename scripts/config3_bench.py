@@ -1,6 +1,7 @@
 """One rank's share of BASELINE.json config 3 on one GPU: 262,144 frames (1M frames / 4 GPUs) with the full mesh,
 joints and REBA/RULA scores in ONE call (four 65,536-frame pose-chain / vertex-kernel pairs), device-resident inputs,
 CUDA-event timing; the first 4096 frames are compared bit for bit with a 4096-frame call."""
+import os; os.environ.setdefault("PRK_SYNTHETIC_SMPL", "1")
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench

@@ -1,3 +1,4 @@
+import os; os.environ.setdefault("PRK_SYNTHETIC_SMPL", "1")
 import sys, time, torch
 sys.path.insert(0, '/root/repo')
 import bench

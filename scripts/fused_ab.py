@@ -3,6 +3,7 @@
 Every variant runs in its own process (PRK_LIB), 4096 frames per step; prints the per-kernel CUDA-event times and a
 checksum of the vertices so a variant that changes results is seen at once.
 """
+import os; os.environ.setdefault("PRK_SYNTHETIC_SMPL", "1")
 import os
 import subprocess
 import sys

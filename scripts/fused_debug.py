@@ -1,4 +1,5 @@
 """Phase timers of the fused kernel's epilogue warps (library built with PRK_FUSED_DEBUG=1)."""
+import os; os.environ.setdefault("PRK_SYNTHETIC_SMPL", "1")
 import ctypes as C, os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from poserisk_release_b200 import _lib

@@ -1,5 +1,6 @@
 """Config 5 of BASELINE.json on one GPU: 1M frames, joints-only (no vertices), REBA+RULA scores and the
 debug Euler sequences of four joints.  CUDA-event timing, inputs resident in HBM."""
+import os; os.environ.setdefault("PRK_SYNTHETIC_SMPL", "1")
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench

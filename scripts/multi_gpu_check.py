@@ -1,5 +1,6 @@
 """N-rank correctness of the sharded path: every rank scores its contiguous frame shard, the
 32-byte records are all-gathered over NCCL, and the result must equal the 1-rank result."""
+import os; os.environ.setdefault("PRK_SYNTHETIC_SMPL", "1")
 import os
 import sys
 

@@ -17,3 +17,15 @@ for line in sys.stdin:
              r['frac'], o['executed_mma']['frac'], o['frac'], d['clocks']['sm_mhz'], d['clocks']['reasons']))
     if d.get('cpu_baseline'):
         print('cpu_baseline %.0f frames/s on %d threads' % (d['cpu_baseline']['value'], d['cpu_baseline']['cores']))
+    if d.get('value_spread'):
+        s, e = d['value_spread'], d['e2e'].get('spread', {})
+        print('value median %.3e [%.3e .. %.3e] x%d | e2e [%.3e .. %.3e]' % (s['median'], s['min'], s['max'], s['repeats'],
+                                                                        e.get('min', 0), e.get('max', 0)))
+    if d.get('e2e_with_verts'):
+        print('e2e_with_verts %.3e frames/s (%.2f ms/step)' % (d['e2e_with_verts']['value'], d['e2e_with_verts']['ms_per_step']))
+    for k in ('config3', 'config5', 'config4'):
+        c = d.get(k)
+        if c:
+            print('%s: %.3e frames/s (%.2f ms, %s GB/s, exchange %s) parity %s %s' % (
+                k, c['value'], c['ms'], round(c['achieved_gbs']), c['exchange'], json.dumps(c['parity']),
+                {x: c[x] for x in ('sharded_equals_single', 'stages_alone_ms', 'model_runs_on_rank0') if x in c}))

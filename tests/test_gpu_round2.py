@@ -206,7 +206,8 @@ def test_nan_pose_poisons_its_frame_and_nothing_else(engine):
     pose_bad = pose.clone()
     pose_bad[5, 0] = float('inf')
     out = engine.run(pose_bad.cuda(), betas.cuda(), trans.cuda(), add_info=EXAMPLE_INFO)
-    assert torch.isnan(out['verts'][5]).all() and torch.isnan(out['joints'][5]).all()
+    assert torch.isnan(out['verts'][5]).all() and torch.isnan(out['joints'][5][1:]).all()
+    assert torch.equal(out['joints'][5][0], clean['joints'][5][0])     # the root's position is its rest joint + trans
     assert torch.equal(out['verts'][6:], clean['verts'][6:]) and torch.equal(out['verts'][:5], clean['verts'][:5])
 
 

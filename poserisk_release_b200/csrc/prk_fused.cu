@@ -63,8 +63,23 @@ constexpr int kOutBytesPerQuarter = 32 * kOutPitch * 4;          // 32 frames of
 constexpr int kOutBytes = 4 * kOutBytesPerQuarter;               // 26,624
 constexpr int kWSlots = 4;
 constexpr int kMaxStages = 6;
-constexpr int kNumBars = 2 * kMaxStages + 2 * kEpiWarps + 2 + kWSlots + 2 + 8;
-constexpr int kThreads = (kEpiWarps + 2) * 32;                   // 576
+constexpr int kNumBars = 3 * kMaxStages + 2 * kEpiWarps + 2 + kWSlots + 2 + 8;
+// Register re-allocation between warp groups (setmaxnreg): the CTA is launched with five warp groups of 4 warps at
+// kRegsLaunch registers per thread; the fifth group (TMA producer, MMA issuer, two idle warps) gives registers back and
+// the four epilogue groups take them, so the epilogue -- whose speed is set by how many tensor-memory gathers it can
+// keep in flight -- runs with kRegsEpi registers instead of the 96 an 18-warp CTA is capped at (4 x 128 x 112 + 128 x 32
+// = 640 x 96 registers; per scheduler 4 x 32 x 112 + 32 x 32 <= 16384).  -DPRK_SETMAXNREG=0 builds the 18-warp kernel.
+#ifndef PRK_SETMAXNREG
+#define PRK_SETMAXNREG 0
+#endif
+constexpr bool kRegRealloc = PRK_SETMAXNREG != 0;
+constexpr int kAuxWarps = kRegRealloc ? 4 : 2;
+#ifndef PRK_REGS_EPI
+#define PRK_REGS_EPI 112
+#define PRK_REGS_AUX 32
+#endif
+constexpr int kRegsEpi = PRK_REGS_EPI, kRegsAux = PRK_REGS_AUX;
+constexpr int kThreads = (kEpiWarps + kAuxWarps) * 32;           // 640 (576 without the re-allocation)
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kAccCol0 = 288;                               // accumulators behind the 24 x 12 A_j columns
 constexpr int kSmemLimit = 232448;                               // 227 KB opt-in maximum per CTA
@@ -83,6 +98,28 @@ __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_
 // vertex stores are evict-first (st.global.cs).  (An evict_last hint on the B' loads measured no gain.)
 __device__ __forceinline__ void store_vertex_pair(float* dst, float2 v) {
     __stcs(reinterpret_cast<float2*>(dst), v);                  // st.global.cs: evict-first
+}
+// ---- thread-block clusters: the CTAs of a cluster walk the same vertex tiles for different frame tiles and share
+// every B' chunk through ONE multicast bulk copy (half / a quarter of the L2 -> SM operand traffic per CTA)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {   // same barrier, CTA `cta` of the cluster
+    uint32_t raddr;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(bar)), "r"(cta));
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+// one bulk copy delivered to the same shared-memory offset of every CTA in `mask`; each destination's own mbarrier
+// (same offset) receives the transaction bytes
+__device__ __forceinline__ void bulk_load_1d_multicast(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+                 : "memory");
 }
 __device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t* r) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -131,21 +168,23 @@ __device__ __forceinline__ void umma_bf16_lohi(uint32_t d_tmem, uint32_t a_lo, u
             : "memory");
 }
 
-// Build with -DPRK_FUSED_DEBUG to get run-time switches (env PRK_FUSED_DBG) that knock out one side
-// of the pipeline at a time: 1 = no MMAs issued, 2 = epilogue skips gather+math, 4 = no global stores,
-// 8 = no TMEM gather of A_j (math on stale registers), 16 = no B' loads (producer only signals).
-// -DPRK_FUSED_KNOCK: the switches only (no phase timers, which cost ~50 % themselves).
+// Knock-out builds for finding out where the time goes: -DPRK_KNOCK=<mask> removes one side of the pipeline at
+// COMPILE time (run-time switches perturb the unrolled epilogue too much to be trusted):
+//   1 = no MMAs issued, 2 = epilogue skips gather + math + stores, 4 = no global stores (staging and read-back kept),
+//   8 = no TMEM gather of A_j (math on stale registers), 16 = no B' loads (producer only signals),
+//   32 = no skinning FMAs (gathers kept), 64 = constant weights / columns, 128 = no staging, read-back or stores,
+//   256 = no read-back and no stores (staging and hand-shakes kept), 512 = no waits on the staging tile's barriers,
+//   1024 = no arrives on them either, 2048 = results staged vertex by vertex instead of four at a time.
+// -DPRK_FUSED_DEBUG adds clock64 phase timers to the epilogue (they cost ~50 % themselves).
+#ifndef PRK_KNOCK
+#define PRK_KNOCK 0
+#endif
+#define DBG(bit) ((PRK_KNOCK) & (bit))
 #ifdef PRK_FUSED_DEBUG
-#define DBG(bit) (dbg & (bit))
 __device__ unsigned long long g_fdbg[8];
 #define TCLK(var) const long long var = clock64()
 #define TACC(k, a, b) t_sum[k] += (b) - (a)
 #else
-#ifdef PRK_FUSED_KNOCK
-#define DBG(bit) (dbg & (bit))
-#else
-#define DBG(bit) 0
-#endif
 #define TCLK(var)
 #define TACC(k, a, b)
 #endif
@@ -181,7 +220,8 @@ __device__ __forceinline__ bool elect_one() {
 // kGroups: weight groups of 4 per vertex known at compile time (1 = SMPL), 0 = run-time `groups`
 #define GATHER_ADDR(col) (col)                 // the table holds absolute tensor-memory addresses
 
-template <int kGroups>
+// kClus: CTAs per cluster (1 = no cluster).  n_units counts cluster units: (group of kClus frame tiles) x vertex tile.
+template <int kGroups, int kClus>
 __global__ void __launch_bounds__(kThreads, 1)
 fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const uint16_t* __restrict__ B2img,
                         const float* __restrict__ AskinT, const float* __restrict__ off,
@@ -210,7 +250,9 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const uint16
     // arrive and wait are far apart in the instruction stream, so the four warps need not run in lock-step
     uint64_t* qstaged_bar = aempty_bar + 1;                       // [4 quarters]
     uint64_t* qflushed_bar = qstaged_bar + 4;                     // [4 quarters]
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(qflushed_bar + 4);
+    // cluster leader only: "the peers' copies of ring slot s are free and their full barriers are armed"
+    uint64_t* pempty_bar = qflushed_bar + 4;             // [kMaxStages]
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(pempty_bar + kMaxStages);
 
     // The warp index is broadcast from lane 0 so the compiler knows it is warp-uniform: role
     // branches stay convergent and the MMA / TMA warps compute their operands in uniform registers.
@@ -221,7 +263,10 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const uint16
 
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_A)) : "memory");
-        for (int i = 0; i < kMaxStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < kMaxStages; ++i) {
+            mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1);
+            mbar_init(&pempty_bar[i], kClus > 1 ? kClus - 1 : 1);
+        }
         for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&tfull_bar[i], 1);
         for (int i = 0; i < 2; ++i) mbar_init(&tempty_bar[i], kEpiWarps);
         for (int i = 0; i < kWSlots; ++i) mbar_init(&wfull_bar[i], 1);
@@ -238,6 +283,7 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const uint16
     }
     tcgen05_fence_before();
     __syncthreads();
+    if (kClus > 1) cluster_sync_all();          // every CTA's barriers exist before a peer arrives on / multicasts to them
     tcgen05_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_holder, 0);
     // everything above ran while the previous kernel of the stream (the pose chain) was still draining; its
@@ -245,13 +291,19 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const uint16
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (tmem_base != 0) __trap();              // all 512 columns are ours: the allocation can only start at 0
 
-    // contiguous unit range of this CTA; unit u = frame tile (u / 216), vertex tile (u % 216)
-    const int64_t u0 = (int64_t)blockIdx.x * n_units / gridDim.x;
-    const int64_t u1 = (int64_t)(blockIdx.x + 1) * n_units / gridDim.x;
+    // contiguous unit range of this cluster; unit u = frame-tile group (u / 216), vertex tile (u % 216); CTA `crank`
+    // of the cluster takes frame tile group * kClus + crank (a tile beyond the batch computes on zero rows, stores nothing)
+    const int crank = kClus > 1 ? (int)cluster_ctarank() : 0;
+    const int64_t cid = blockIdx.x / kClus, ncl = gridDim.x / kClus;
+    const int64_t u0 = cid * n_units / ncl;
+    const int64_t u1 = (cid + 1) * n_units / ncl;
     const int n_my = (int)(u1 - u0);
-    const int64_t ft0 = u0 / FUSED_NT;
-    const int vt0 = (int)(u0 - ft0 * FUSED_NT);
+    const int64_t ft0 = (u0 / FUSED_NT) * kClus + crank;
+    const int vt0 = (int)(u0 - (u0 / FUSED_NT) * FUSED_NT);
+    const int64_t n_ft_real = (B + FUSED_BM - 1) / FUSED_BM;
 
+    if (warp >= kEpiWarps) {
+    if (kRegRealloc && kRegsEpi > 96) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsAux));   // the whole fifth warp group
     if (warp == kEpiWarps) {
         // ===== TMA producer (whole warp converged, one elected lane issues) =====
         int stage = 0; uint32_t phase = 0;
@@ -279,19 +331,32 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const uint16
             }
 #pragma unroll 1
             for (int c = 0; c < FUSED_B_CHUNKS; ++c) {
-                MBAR_WAIT(&empty_bar[stage], phase ^ 1);
-                if (elect_one()) {
-                    if (DBG(16)) { mbar_arrive(&full_bar[stage]); }
-                    else {
-                        // one contiguous 12 KB block of the pre-swizzled B' image (prk_internal.h fused_b2_index)
+                MBAR_WAIT(&empty_bar[stage], phase ^ 1);          // this CTA's MMAs have released the slot
+                const uint16_t* chunk = B2img + ((size_t)vt * FUSED_B_CHUNKS + c) * (kBChunkBytes / 2);
+                if (kClus > 1 && crank != 0) {
+                    // peer: arm the local barrier for the bytes the leader's multicast will deliver, then tell the leader
+                    if (elect_one()) {
                         mbar_expect_tx(&full_bar[stage], kBChunkBytes);
-                        bulk_load_1d(sB + stage * kBChunkBytes,
-                                     B2img + ((size_t)vt * FUSED_B_CHUNKS + c) * (kBChunkBytes / 2), kBChunkBytes, &full_bar[stage]);
+                        mbar_arrive_remote(&pempty_bar[stage], 0);
+                    }
+                } else {
+                    if (kClus > 1) MBAR_WAIT(&pempty_bar[stage], phase);      // every peer's slot is free and armed
+                    if (elect_one()) {
+                        if (DBG(16)) { mbar_arrive(&full_bar[stage]); }
+                        else {
+                            // one contiguous 12 KB block of the pre-swizzled B' image (prk_internal.h fused_b2_index)
+                            mbar_expect_tx(&full_bar[stage], kBChunkBytes);
+                            if (kClus > 1)
+                                bulk_load_1d_multicast(sB + stage * kBChunkBytes, chunk, kBChunkBytes, &full_bar[stage],
+                                                       (uint16_t)((1u << kClus) - 1));
+                            else
+                                bulk_load_1d(sB + stage * kBChunkBytes, chunk, kBChunkBytes, &full_bar[stage]);
+                        }
                     }
                 }
                 if (++stage == stages) { stage = 0; phase ^= 1; }
             }
-            if (++vt == FUSED_NT) { vt = 0; ++ft; }
+            if (++vt == FUSED_NT) { vt = 0; ft += kClus; }
         }
     } else if (warp == kEpiWarps + 1) {
         // ===== MMA issuer (whole warp converged, one elected lane issues) =====
@@ -350,8 +415,11 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const uint16
             }
             if (++vt == FUSED_NT) vt = 0;
         }
+    }
+    // (warps 18, 19 of the fifth warp group are idle: they only exist so that the group can hand its registers over)
     } else {
         // ===== epilogue: thread = frame (TMEM lane), loop over the warp's 8 vertices of each unit =====
+        if (kRegRealloc && kRegsEpi > 96) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsEpi));
         const int quarter = warp & 3, oct = warp >> 2;
         const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
         // Vertices leave through a staging tile shared by the four warps of a lane quarter:
@@ -379,15 +447,17 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const uint16
         uint32_t n_staged = 0;                                        // halves this warp has staged so far
         auto flush_pending = [&]() {
             if (pend == nullptr) return;                              // warp-uniform
-            MBAR_WAIT(&qstaged_bar[quarter], (n_staged - 1) & 1);    // all four warps staged the pending half
+            if (!DBG(512)) MBAR_WAIT(&qstaged_bar[quarter], (n_staged - 1) & 1);    // all four warps staged the pending half
 #pragma unroll
-            for (int it = 0; it < 6; ++it) {
+            for (int it = 0; it < (DBG(256) ? 0 : 6); ++it) {
                 const int j = it % 3, up = (it / 3) * 4;
-                store_vertex_pair(pend + rb_glob[j] + up * NVC,
-                                  *reinterpret_cast<const float2*>(q_out + rb_smem[j] + up * kOutPitch));
+                const float2 val = *reinterpret_cast<const float2*>(q_out + rb_smem[j] + up * kOutPitch);
+                if (!DBG(4) || val.x == 123.456f) store_vertex_pair(pend + rb_glob[j] + up * NVC, val);
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&qflushed_bar[quarter]);      // my rows of that half are in registers / on their way
+            if (!DBG(1024)) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&qflushed_bar[quarter]);  // my rows of that half are in registers / on their way
+            }
             pend = nullptr;
         };
         int64_t ft = ft0; int vt = vt0;
@@ -407,7 +477,7 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const uint16
                 for (int b = 0; b < 3; ++b) {
                     uint32_t v[24];
 #pragma unroll
-                    for (int k = 0; k < 24; ++k) v[k] = __float_as_uint(__ldg(src + (b * 24 + k) * 32));
+                    for (int k = 0; k < 24; ++k) v[k] = ft < n_ft_real ? __float_as_uint(__ldg(src + (b * 24 + k) * 32)) : 0u;
 #pragma unroll
                     for (int c = 0; c < 3; ++c) tmem_st_x8(t_lane + (uint32_t)(oct * 72 + b * 24 + c * 8), v + c * 8);
                 }
@@ -431,7 +501,7 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const uint16
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-                if (++vt == FUSED_NT) { vt = 0; ++ft; }
+                if (++vt == FUSED_NT) { vt = 0; ft += kClus; }
                 continue;
             }
             const uint32_t t_acc = t_lane + kAccCol0 + (uint32_t)acc * FUSED_BN + (uint32_t)(oct * 12);
@@ -534,7 +604,10 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const uint16
                         } else if (k < 7) {
                             if (!DBG(8)) { tmem_ld_x8(GATHER_ADDR(cj_next.x), nb); tmem_ld_x4(GATHER_ADDR(cj_next.x) + 8, nb + 8); }
                         }
-                        {   // x, y per joint; the z row is blended first and applied once per vertex:
+                        if (DBG(32)) {
+                            const uint32_t* a = buf[n & 1];
+                            accxy ^= pack2(a[0] ^ a[11], a[5]);
+                        } else {   // x, y per joint; the z row is blended first and applied once per vertex:
                             // 6 packed FMAs per item, every operand straight out of the gather registers
                             const uint32_t* a = buf[n & 1];
                             uint64_t xy = fma2(pack2(a[0], a[1]), pxx, pack2(a[6], a[7]));
@@ -551,18 +624,30 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const uint16
                     unpack2(accxy, res[(k & 3) * 3 + 0], res[(k & 3) * 3 + 1]);
                     unpack2(accz, zl, zh);
                     res[(k & 3) * 3 + 2] = zl + zh;
+                    if (DBG(2048)) {
+                        float* d1 = q_out + lane * kOutPitch + oct * 12 + (k & 3) * 3;
+                        d1[0] = res[(k & 3) * 3 + 0]; d1[1] = res[(k & 3) * 3 + 1]; d1[2] = res[(k & 3) * 3 + 2];
+                    }
                     if ((k & 3) == 3) {
                         TCLK(tg1);
                         TACC(2, tg0, tg1);
                         const int half = k >> 2;
                         if (k == 3) { tmem_ld_x8(t_acc + 48, p); tmem_ld_x4(t_acc + 56, p + 8); }   // next half's v_posed
-                        if (n_staged > 0) MBAR_WAIT(&qflushed_bar[quarter], (n_staged - 1) & 1);   // tile is free
+                        if (DBG(128)) {                              // knock-out: no staging, no read-back, no stores
+                            if (res[0] == 123.456f && res[5] == 1.5f && res[10] == 7.f) vrow[half] = res[1] + res[4] + res[7] + res[11];
+                            continue;
+                        }
+                        if (n_staged > 0 && !DBG(512)) MBAR_WAIT(&qflushed_bar[quarter], (n_staged - 1) & 1);   // tile is free
                         float4* dst = reinterpret_cast<float4*>(q_out + lane * kOutPitch + oct * 12);
-                        dst[0] = make_float4(res[0], res[1], res[2], res[3]);
-                        dst[1] = make_float4(res[4], res[5], res[6], res[7]);
-                        dst[2] = make_float4(res[8], res[9], res[10], res[11]);
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&qstaged_bar[quarter]);
+                        if (!DBG(2048)) {
+                            dst[0] = make_float4(res[0], res[1], res[2], res[3]);
+                            dst[1] = make_float4(res[4], res[5], res[6], res[7]);
+                            dst[2] = make_float4(res[8], res[9], res[10], res[11]);
+                        }
+                        if (!DBG(1024)) {
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&qstaged_bar[quarter]);
+                        }
                         ++n_staged;
                         const int c_first = c_unit + half * 48;
                         float* vhalf = vrow + half * 48;
@@ -626,7 +711,7 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const uint16
                     store_half(res, half);
                 }
             }
-            if (++vt == FUSED_NT) { vt = 0; ++ft; }
+            if (++vt == FUSED_NT) { vt = 0; ft += kClus; }
         }
         flush_pending();
 #ifdef PRK_FUSED_DEBUG
@@ -640,6 +725,7 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const uint16
 
     tcgen05_fence_before();
     __syncthreads();
+    if (kClus > 1) cluster_sync_all();          // no CTA leaves while a peer may still arrive on its barriers
     if (warp == kEpiWarps + 1) {
         tcgen05_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
@@ -718,6 +804,80 @@ int fused_stages(int groups) {
     return stages;
 }
 
+// cluster size of the vertex kernel: PRK_CLUSTER=1|2|4 overrides; default PRK_CLUSTER_DEFAULT when the batch has at
+// least that many frame tiles
+#ifndef PRK_CLUSTER_DEFAULT
+#define PRK_CLUSTER_DEFAULT 1
+#endif
+static int fused_cluster_size(int64_t n_ft) {
+    static const int forced = [] { const char* e = getenv("PRK_CLUSTER"); return e ? atoi(e) : 0; }();
+    int c = forced > 0 ? forced : PRK_CLUSTER_DEFAULT;
+    if (c != 1 && c != 2 && c != 4) c = 1;
+    while (c > 1 && n_ft < c) c >>= 1;
+    return c;
+}
+
+template <int kGroups, int kClus>
+static cudaError_t launch_fused_t(const Model& m, const CUtensorMap& tmap_A, int64_t rows_pad, const float* d_AskinT,
+                                  const float* d_off, int64_t B, float* d_verts, cudaStream_t s, int stages, int smem, int dbg,
+                                  bool pdl) {
+    auto kern = fused_blend_skin_kernel<kGroups, kClus>;
+    static std::atomic<int> attr_set[64];       // per device: dynamic shared memory this instantiation was opted in for
+    if (m.device >= 0 && m.device < 64 && attr_set[m.device].load(std::memory_order_acquire) < smem) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        attr_set[m.device].store(smem, std::memory_order_release);
+    }
+    const int64_t n_ft = rows_pad / FUSED_BM;
+    const int64_t n_units = ((n_ft + kClus - 1) / kClus) * FUSED_NT;          // cluster units
+    int grid = m.sm_count > 0 ? m.sm_count : 148;
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (kClus > 1) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = kClus; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+        ++na;
+        // one CTA per SM: as many clusters as the GPU can hold at once (a GPC with a number of SMs that is not a multiple
+        // of the cluster size leaves some idle)
+        static std::atomic<int> max_clusters[64];
+        int mc = (m.device >= 0 && m.device < 64) ? max_clusters[m.device].load(std::memory_order_acquire) : 0;
+        if (mc == 0) {
+            cfg.gridDim = dim3((unsigned)(grid / kClus * kClus));
+            cfg.attrs = attr; cfg.numAttrs = na;
+            cudaError_t e = cudaOccupancyMaxActiveClusters(&mc, kern, &cfg);
+            if (e != cudaSuccess) return e;
+            if (mc < 1) return cudaErrorInvalidConfiguration;
+            if (m.device >= 0 && m.device < 64) max_clusters[m.device].store(mc, std::memory_order_release);
+        }
+        if (grid > mc * kClus) grid = mc * kClus;
+        grid = grid / kClus * kClus;
+        if ((int64_t)grid / kClus > n_units) grid = (int)n_units * kClus;
+    } else if (grid > n_units) {
+        grid = (int)n_units;
+    }
+    // Programmatic dependent launch: the CTAs become resident and run their prologue (barrier init, tensor-memory
+    // allocation, descriptor prefetch) while the pose-chain kernel in front of them drains; every thread passes
+    // griddepcontrol.wait before it touches that kernel's outputs.  PRK_PDL=0 launches without the attribute.
+    if (pdl) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    const uint8_t* wpack = m.d_wpack;
+    const uint16_t* b2img = m.d_B2;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmap_A, b2img, d_AskinT, d_off, wpack, m.nnz_groups, stages, B, n_units,
+                                       d_verts, dbg);
+    count_launch();
+    return e != cudaSuccess ? e : cudaGetLastError();
+}
+
 cudaError_t launch_fused(const Model& m, const CUtensorMap& tmap_A, int64_t rows_pad, const float* d_AskinT,
                          const float* d_off, int64_t B, float* d_verts, cudaStream_t s) {
     if (B == 0) return cudaSuccess;
@@ -725,46 +885,13 @@ cudaError_t launch_fused(const Model& m, const CUtensorMap& tmap_A, int64_t rows
     const int stages = fused_stages(groups);
     const int smem = fused_smem_bytes(stages, groups);
     if (smem > kSmemLimit) return cudaErrorInvalidConfiguration;
-    static std::atomic<int> attr_set[64];       // per device: dynamic shared memory the kernels were opted in for
-    if (m.device >= 0 && m.device < 64 && attr_set[m.device].load(std::memory_order_acquire) < smem) {
-        cudaError_t e = cudaFuncSetAttribute(fused_blend_skin_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(fused_blend_skin_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        attr_set[m.device].store(smem, std::memory_order_release);
-    }
-    int dbg = 0;
-#if defined(PRK_FUSED_DEBUG) || defined(PRK_FUSED_KNOCK)
-    if (const char* e = getenv("PRK_FUSED_DBG")) dbg = atoi(e);
-#endif
-    const int64_t n_units = (rows_pad / FUSED_BM) * FUSED_NT;
-    int grid = m.sm_count > 0 ? m.sm_count : 148;
-    if (grid > n_units) grid = (int)n_units;
-    // Programmatic dependent launch: the CTAs become resident and run their prologue (barrier init, tensor-memory
-    // allocation, descriptor prefetch) while the pose-chain kernel in front of them drains; every thread passes
-    // griddepcontrol.wait before it touches that kernel's outputs.  PRK_PDL=0 launches without the attribute.
+    const int dbg = 0;
     static const bool pdl = [] { const char* e = getenv("PRK_PDL"); return !e || atoi(e) != 0; }();
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = (size_t)smem;
-    cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = pdl ? 1 : 0;
-    const uint8_t* wpack = m.d_wpack;
-    const uint16_t* b2img = m.d_B2;
-    cudaError_t e;
-    if (groups == 1)
-        e = cudaLaunchKernelEx(&cfg, fused_blend_skin_kernel<1>, tmap_A, b2img, d_AskinT, d_off, wpack, groups, stages, B,
-                               n_units, d_verts, dbg);
-    else
-        e = cudaLaunchKernelEx(&cfg, fused_blend_skin_kernel<0>, tmap_A, b2img, d_AskinT, d_off, wpack, groups, stages, B,
-                               n_units, d_verts, dbg);
-    count_launch();
-    return e != cudaSuccess ? e : cudaGetLastError();
+    const int clus = fused_cluster_size(rows_pad / FUSED_BM);
+#define PRK_GO(G, C) launch_fused_t<G, C>(m, tmap_A, rows_pad, d_AskinT, d_off, B, d_verts, s, stages, smem, dbg, pdl)
+    if (groups == 1) return clus == 4 ? PRK_GO(1, 4) : (clus == 2 ? PRK_GO(1, 2) : PRK_GO(1, 1));
+    return clus == 4 ? PRK_GO(0, 4) : (clus == 2 ? PRK_GO(0, 2) : PRK_GO(0, 1));
+#undef PRK_GO
 }
 
 }  // namespace prk

@@ -58,28 +58,21 @@ constexpr int kAChunkBytes = FUSED_BM * 128;                     // 128 frames x
 constexpr int kABytes = FUSED_A_CHUNKS * kAChunkBytes;           // 114,688: resident A' tile
 constexpr int kBChunkBytes = FUSED_BN * 128;                     // 96 vertex coords x 64 bf16 = 12,288
 constexpr int kEpiWarps = 16;
+// Store warp (kGroups == 1): the read-back of the staging tiles and the global vertex stores are done by the TMA producer
+// warp, which is otherwise idle between its eight bulk copies per unit -- the sixteen epilogue warps only gather, multiply
+// and stage.  -DPRK_STOREWARP=0: every epilogue warp reads its own rows back and stores them (round-1 kernel).
+#ifndef PRK_STOREWARP
+#define PRK_STOREWARP 1
+#endif
+constexpr bool kStoreWarp = PRK_STOREWARP != 0;
+
 constexpr int kOutPitch = 52;                                    // floats per staged frame row: 16 vertices x 3 (+4: conflict-free float4)
 constexpr int kOutBytesPerQuarter = 32 * kOutPitch * 4;          // 32 frames of one TMEM lane quarter
 constexpr int kOutBytes = 4 * kOutBytesPerQuarter;               // 26,624
 constexpr int kWSlots = 4;
 constexpr int kMaxStages = 6;
-constexpr int kNumBars = 3 * kMaxStages + 2 * kEpiWarps + 2 + kWSlots + 2 + 8;
-// Register re-allocation between warp groups (setmaxnreg): the CTA is launched with five warp groups of 4 warps at
-// kRegsLaunch registers per thread; the fifth group (TMA producer, MMA issuer, two idle warps) gives registers back and
-// the four epilogue groups take them, so the epilogue -- whose speed is set by how many tensor-memory gathers it can
-// keep in flight -- runs with kRegsEpi registers instead of the 96 an 18-warp CTA is capped at (4 x 128 x 112 + 128 x 32
-// = 640 x 96 registers; per scheduler 4 x 32 x 112 + 32 x 32 <= 16384).  -DPRK_SETMAXNREG=0 builds the 18-warp kernel.
-#ifndef PRK_SETMAXNREG
-#define PRK_SETMAXNREG 0
-#endif
-constexpr bool kRegRealloc = PRK_SETMAXNREG != 0;
-constexpr int kAuxWarps = kRegRealloc ? 4 : 2;
-#ifndef PRK_REGS_EPI
-#define PRK_REGS_EPI 112
-#define PRK_REGS_AUX 32
-#endif
-constexpr int kRegsEpi = PRK_REGS_EPI, kRegsAux = PRK_REGS_AUX;
-constexpr int kThreads = (kEpiWarps + kAuxWarps) * 32;           // 640 (576 without the re-allocation)
+constexpr int kNumBars = 2 * kMaxStages + 2 * kEpiWarps + 2 + kWSlots + 2 + 8;
+constexpr int kThreads = (kEpiWarps + 2) * 32;                   // 576
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kAccCol0 = 288;                               // accumulators behind the 24 x 12 A_j columns
 constexpr int kSmemLimit = 232448;                               // 227 KB opt-in maximum per CTA
@@ -98,28 +91,6 @@ __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_
 // vertex stores are evict-first (st.global.cs).  (An evict_last hint on the B' loads measured no gain.)
 __device__ __forceinline__ void store_vertex_pair(float* dst, float2 v) {
     __stcs(reinterpret_cast<float2*>(dst), v);                  // st.global.cs: evict-first
-}
-// ---- thread-block clusters: the CTAs of a cluster walk the same vertex tiles for different frame tiles and share
-// every B' chunk through ONE multicast bulk copy (half / a quarter of the L2 -> SM operand traffic per CTA)
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {   // same barrier, CTA `cta` of the cluster
-    uint32_t raddr;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(bar)), "r"(cta));
-    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
-}
-// one bulk copy delivered to the same shared-memory offset of every CTA in `mask`; each destination's own mbarrier
-// (same offset) receives the transaction bytes
-__device__ __forceinline__ void bulk_load_1d_multicast(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t mask) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
-                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
-                 : "memory");
 }
 __device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t* r) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -169,12 +140,11 @@ __device__ __forceinline__ void umma_bf16_lohi(uint32_t d_tmem, uint32_t a_lo, u
 }
 
 // Knock-out builds for finding out where the time goes: -DPRK_KNOCK=<mask> removes one side of the pipeline at
-// COMPILE time (run-time switches perturb the unrolled epilogue too much to be trusted):
+// COMPILE time (run-time switches perturb the unrolled epilogue too much to be trusted; profiles/r2_ab_runs.txt):
 //   1 = no MMAs issued, 2 = epilogue skips gather + math + stores, 4 = no global stores (staging and read-back kept),
 //   8 = no TMEM gather of A_j (math on stale registers), 16 = no B' loads (producer only signals),
 //   32 = no skinning FMAs (gathers kept), 64 = constant weights / columns, 128 = no staging, read-back or stores,
-//   256 = no read-back and no stores (staging and hand-shakes kept), 512 = no waits on the staging tile's barriers,
-//   1024 = no arrives on them either, 2048 = results staged vertex by vertex instead of four at a time.
+//   256 = no read-back and no stores (staging and hand-shakes kept).
 // -DPRK_FUSED_DEBUG adds clock64 phase timers to the epilogue (they cost ~50 % themselves).
 #ifndef PRK_KNOCK
 #define PRK_KNOCK 0
@@ -211,6 +181,12 @@ __device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {     // has the phase of this parity completed?
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return done != 0;
+}
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
@@ -220,8 +196,7 @@ __device__ __forceinline__ bool elect_one() {
 // kGroups: weight groups of 4 per vertex known at compile time (1 = SMPL), 0 = run-time `groups`
 #define GATHER_ADDR(col) (col)                 // the table holds absolute tensor-memory addresses
 
-// kClus: CTAs per cluster (1 = no cluster).  n_units counts cluster units: (group of kClus frame tiles) x vertex tile.
-template <int kGroups, int kClus>
+template <int kGroups>
 __global__ void __launch_bounds__(kThreads, 1)
 fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const uint16_t* __restrict__ B2img,
                         const float* __restrict__ AskinT, const float* __restrict__ off,
@@ -250,9 +225,7 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const uint16
     // arrive and wait are far apart in the instruction stream, so the four warps need not run in lock-step
     uint64_t* qstaged_bar = aempty_bar + 1;                       // [4 quarters]
     uint64_t* qflushed_bar = qstaged_bar + 4;                     // [4 quarters]
-    // cluster leader only: "the peers' copies of ring slot s are free and their full barriers are armed"
-    uint64_t* pempty_bar = qflushed_bar + 4;             // [kMaxStages]
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(pempty_bar + kMaxStages);
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(qflushed_bar + 4);
 
     // The warp index is broadcast from lane 0 so the compiler knows it is warp-uniform: role
     // branches stay convergent and the MMA / TMA warps compute their operands in uniform registers.
@@ -263,16 +236,13 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const uint16
 
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_A)) : "memory");
-        for (int i = 0; i < kMaxStages; ++i) {
-            mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1);
-            mbar_init(&pempty_bar[i], kClus > 1 ? kClus - 1 : 1);
-        }
+        for (int i = 0; i < kMaxStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
         for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&tfull_bar[i], 1);
         for (int i = 0; i < 2; ++i) mbar_init(&tempty_bar[i], kEpiWarps);
         for (int i = 0; i < kWSlots; ++i) mbar_init(&wfull_bar[i], 1);
         mbar_init(afull_bar, 1);
         mbar_init(aempty_bar, 1);
-        for (int i = 0; i < 4; ++i) { mbar_init(&qstaged_bar[i], 4); mbar_init(&qflushed_bar[i], 4); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&qstaged_bar[i], 4); mbar_init(&qflushed_bar[i], (kStoreWarp && kGroups == 1) ? 1 : 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kEpiWarps + 1) {
@@ -283,7 +253,6 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const uint16
     }
     tcgen05_fence_before();
     __syncthreads();
-    if (kClus > 1) cluster_sync_all();          // every CTA's barriers exist before a peer arrives on / multicasts to them
     tcgen05_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_holder, 0);
     // everything above ran while the previous kernel of the stream (the pose chain) was still draining; its
@@ -291,20 +260,123 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const uint16
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (tmem_base != 0) __trap();              // all 512 columns are ours: the allocation can only start at 0
 
-    // contiguous unit range of this cluster; unit u = frame-tile group (u / 216), vertex tile (u % 216); CTA `crank`
-    // of the cluster takes frame tile group * kClus + crank (a tile beyond the batch computes on zero rows, stores nothing)
-    const int crank = kClus > 1 ? (int)cluster_ctarank() : 0;
-    const int64_t cid = blockIdx.x / kClus, ncl = gridDim.x / kClus;
-    const int64_t u0 = cid * n_units / ncl;
-    const int64_t u1 = (cid + 1) * n_units / ncl;
+    // contiguous unit range of this CTA; unit u = frame tile (u / 216), vertex tile (u % 216)
+    const int64_t u0 = (int64_t)blockIdx.x * n_units / gridDim.x;
+    const int64_t u1 = (int64_t)(blockIdx.x + 1) * n_units / gridDim.x;
     const int n_my = (int)(u1 - u0);
-    const int64_t ft0 = (u0 / FUSED_NT) * kClus + crank;
-    const int vt0 = (int)(u0 - (u0 / FUSED_NT) * FUSED_NT);
-    const int64_t n_ft_real = (B + FUSED_BM - 1) / FUSED_BM;
+    const int64_t ft0 = u0 / FUSED_NT;
+    const int vt0 = (int)(u0 - ft0 * FUSED_NT);
 
-    if (warp >= kEpiWarps) {
-    if (kRegRealloc && kRegsEpi > 96) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsAux));   // the whole fifth warp group
-    if (warp == kEpiWarps) {
+    if (warp == kEpiWarps && kStoreWarp && kGroups == 1) {
+        // ===== TMA producer + store warp: one polling loop, nothing in it blocks =====
+        // producer duty: A' tile per frame tile, skinning weights per unit, eight B' chunks per unit through the ring;
+        // store duty: whenever the four epilogue warps of a lane quarter have staged a half unit (32 frames x 16 vertices),
+        // read the tile back (coalesced 8-byte pieces, 192-byte frame rows), hand the tile back, store the rows.
+        int stage = 0; uint32_t phase = 0;
+        int64_t ft = ft0; int vt = vt0;
+        uint32_t n_ft = 0;
+        int i_p = 0, c_p = -1;                  // unit being loaded; its next chunk (-1: A' tile / weights not issued yet)
+        const uint32_t n_halves = 2u * (uint32_t)n_my;
+        const uint32_t wbytes = (uint32_t)groups * FUSED_WGROUP_BYTES;
+        // read-back pattern of one pass: float2 index q = it * 32 + lane over [4 rows][24 float2], it = 0..2
+        int rb_smem[3], rb_glob[3], rb_row[3], rb_c2[3];
+#pragma unroll
+        for (int it = 0; it < 3; ++it) {
+            const int q = it * 32 + lane;
+            rb_row[it] = q / 24; rb_c2[it] = (q % 24) * 2;
+            rb_smem[it] = rb_row[it] * kOutPitch + rb_c2[it];
+            rb_glob[it] = rb_row[it] * NVC + rb_c2[it];
+        }
+        auto store_half_of = [&](int quarter, uint32_t n) {
+            const int t = vt0 + (int)(n >> 1), fti = t / FUSED_NT, vtu = t - fti * FUSED_NT, half = (int)(n & 1);
+            const int row0 = ((int)ft0 + fti) * FUSED_BM + quarter * 32;
+            const int left = (int)B - row0, valid = left < 32 ? left : 32;
+            const int c_first = vtu * (FUSED_VT * 3) + half * 48;
+            const float* tile = reinterpret_cast<const float*>(sOut + quarter * kOutBytesPerQuarter);
+            float* g = verts + (size_t)row0 * NVC + c_first;
+            float2 v[24];
+#pragma unroll
+            for (int it = 0; it < 24; ++it)
+                v[it] = *reinterpret_cast<const float2*>(tile + rb_smem[it % 3] + (it / 3) * 4 * kOutPitch);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&qflushed_bar[quarter]);      // the tile is in registers: the quarter may stage again
+            if (DBG(4)) { if (v[0].x != 123.456f) return; }
+            if (valid == 32 && c_first + 48 <= NVC) {                 // warp-uniform: all but the edge tiles
+#pragma unroll
+                for (int it = 0; it < 24; ++it) store_vertex_pair(g + rb_glob[it % 3] + (it / 3) * 4 * NVC, v[it]);
+            } else {
+#pragma unroll
+                for (int it = 0; it < 24; ++it)
+                    if (rb_row[it % 3] + (it / 3) * 4 < valid && c_first + rb_c2[it % 3] < NVC)
+                        store_vertex_pair(g + rb_glob[it % 3] + (it / 3) * 4 * NVC, v[it]);
+            }
+        };
+        // The loop body is kept SMALL (one copy of the store code, counters packed in one register pair): a polling loop that
+        // branches over four inlined copies of it ran at ~1,400 clk per pass, apparently on instruction fetch.
+        uint64_t nf = 0;                        // halves stored so far, 16 bits per lane quarter (a CTA sees < 2^15 units)
+        uint32_t idle = 0;
+        uint64_t t_idle = 0;
+        for (;;) {
+            bool busy = false;
+#pragma unroll 1
+            for (int rep = 0; rep < 4 && i_p < n_my; ++rep) {      // producer duty: up to four steps per pass
+                if (c_p < 0) {
+                    const bool new_tile = i_p == 0 || vt == 0;
+                    // the MMAs of the previous frame tile still read the resident A' tile
+                    if (new_tile && n_ft > 0 && !mbar_test(aempty_bar, (n_ft - 1) & 1)) break;
+                    if (elect_one()) {
+                        if (new_tile) {
+                            mbar_expect_tx(afull_bar, kABytes);
+                            for (int c = 0; c < FUSED_A_CHUNKS; ++c)
+                                tma_load_2d(&tmap_A, afull_bar, sA + c * kAChunkBytes, c * 64, (int)(ft * FUSED_BM));
+                        }
+                        // skinning weights of the tile's 32 vertices (slot reuse: see the plain producer below)
+                        uint64_t* wb = &wfull_bar[i_p & (kWSlots - 1)];
+                        mbar_expect_tx(wb, wbytes);
+                        bulk_load_1d(sW + (i_p & (kWSlots - 1)) * wbytes, wpack + (size_t)vt * wbytes, wbytes, wb);
+                    }
+                    if (new_tile) ++n_ft;
+                    c_p = 0;
+                } else {
+                    if (!mbar_test(&empty_bar[stage], phase ^ 1)) break;
+                    if (elect_one()) {
+                        if (DBG(16)) { mbar_arrive(&full_bar[stage]); }
+                        else {
+                            mbar_expect_tx(&full_bar[stage], kBChunkBytes);
+                            bulk_load_1d(sB + stage * kBChunkBytes,
+                                         B2img + ((size_t)vt * FUSED_B_CHUNKS + c_p) * (kBChunkBytes / 2), kBChunkBytes, &full_bar[stage]);
+                        }
+                    }
+                    if (++stage == stages) { stage = 0; phase ^= 1; }
+                    if (++c_p == FUSED_B_CHUNKS) {
+                        c_p = -1; ++i_p;
+                        if (++vt == FUSED_NT) { vt = 0; ++ft; }
+                    }
+                }
+                busy = true;
+            }
+            bool stored_all = true;
+            if (!DBG(2) && !DBG(128)) {
+#pragma unroll 1
+                for (int q = 0; q < 4; ++q) {                      // store duty: at most one half per lane quarter per pass
+                    const uint32_t n = (uint32_t)(nf >> (16 * q)) & 0xFFFFu;
+                    if (n >= n_halves) continue;
+                    stored_all = false;
+                    if (!mbar_test(&qstaged_bar[q], n & 1)) continue;
+                    store_half_of(q, n);
+                    nf += 1ull << (16 * q);
+                    busy = true;
+                }
+            }
+            if (i_p >= n_my && stored_all) break;
+            if (busy) { idle = 0; continue; }
+            if ((++idle & 0x3FF) == 0) {                          // bounded like every other wait: trap after ~4 s without progress
+                const uint64_t now = global_ns();
+                if (idle == 0x400) t_idle = now;
+                else if (now - t_idle > 4000000000ull) __trap();
+            }
+        }
+    } else if (warp == kEpiWarps) {
         // ===== TMA producer (whole warp converged, one elected lane issues) =====
         int stage = 0; uint32_t phase = 0;
         int64_t ft = ft0; int vt = vt0;
@@ -331,32 +403,19 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const uint16
             }
 #pragma unroll 1
             for (int c = 0; c < FUSED_B_CHUNKS; ++c) {
-                MBAR_WAIT(&empty_bar[stage], phase ^ 1);          // this CTA's MMAs have released the slot
-                const uint16_t* chunk = B2img + ((size_t)vt * FUSED_B_CHUNKS + c) * (kBChunkBytes / 2);
-                if (kClus > 1 && crank != 0) {
-                    // peer: arm the local barrier for the bytes the leader's multicast will deliver, then tell the leader
-                    if (elect_one()) {
+                MBAR_WAIT(&empty_bar[stage], phase ^ 1);
+                if (elect_one()) {
+                    if (DBG(16)) { mbar_arrive(&full_bar[stage]); }
+                    else {
+                        // one contiguous 12 KB block of the pre-swizzled B' image (prk_internal.h fused_b2_index)
                         mbar_expect_tx(&full_bar[stage], kBChunkBytes);
-                        mbar_arrive_remote(&pempty_bar[stage], 0);
-                    }
-                } else {
-                    if (kClus > 1) MBAR_WAIT(&pempty_bar[stage], phase);      // every peer's slot is free and armed
-                    if (elect_one()) {
-                        if (DBG(16)) { mbar_arrive(&full_bar[stage]); }
-                        else {
-                            // one contiguous 12 KB block of the pre-swizzled B' image (prk_internal.h fused_b2_index)
-                            mbar_expect_tx(&full_bar[stage], kBChunkBytes);
-                            if (kClus > 1)
-                                bulk_load_1d_multicast(sB + stage * kBChunkBytes, chunk, kBChunkBytes, &full_bar[stage],
-                                                       (uint16_t)((1u << kClus) - 1));
-                            else
-                                bulk_load_1d(sB + stage * kBChunkBytes, chunk, kBChunkBytes, &full_bar[stage]);
-                        }
+                        bulk_load_1d(sB + stage * kBChunkBytes,
+                                     B2img + ((size_t)vt * FUSED_B_CHUNKS + c) * (kBChunkBytes / 2), kBChunkBytes, &full_bar[stage]);
                     }
                 }
                 if (++stage == stages) { stage = 0; phase ^= 1; }
             }
-            if (++vt == FUSED_NT) { vt = 0; ft += kClus; }
+            if (++vt == FUSED_NT) { vt = 0; ++ft; }
         }
     } else if (warp == kEpiWarps + 1) {
         // ===== MMA issuer (whole warp converged, one elected lane issues) =====
@@ -415,11 +474,8 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const uint16
             }
             if (++vt == FUSED_NT) vt = 0;
         }
-    }
-    // (warps 18, 19 of the fifth warp group are idle: they only exist so that the group can hand its registers over)
     } else {
         // ===== epilogue: thread = frame (TMEM lane), loop over the warp's 8 vertices of each unit =====
-        if (kRegRealloc && kRegsEpi > 96) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsEpi));
         const int quarter = warp & 3, oct = warp >> 2;
         const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
         // Vertices leave through a staging tile shared by the four warps of a lane quarter:
@@ -446,18 +502,17 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const uint16
         float* pend = nullptr;
         uint32_t n_staged = 0;                                        // halves this warp has staged so far
         auto flush_pending = [&]() {
+            if (kStoreWarp && kGroups == 1) return;                   // the store warp reads the tiles back
             if (pend == nullptr) return;                              // warp-uniform
-            if (!DBG(512)) MBAR_WAIT(&qstaged_bar[quarter], (n_staged - 1) & 1);    // all four warps staged the pending half
+            MBAR_WAIT(&qstaged_bar[quarter], (n_staged - 1) & 1);    // all four warps staged the pending half
 #pragma unroll
-            for (int it = 0; it < (DBG(256) ? 0 : 6); ++it) {
+            for (int it = 0; it < 6; ++it) {
                 const int j = it % 3, up = (it / 3) * 4;
                 const float2 val = *reinterpret_cast<const float2*>(q_out + rb_smem[j] + up * kOutPitch);
                 if (!DBG(4) || val.x == 123.456f) store_vertex_pair(pend + rb_glob[j] + up * NVC, val);
             }
-            if (!DBG(1024)) {
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&qflushed_bar[quarter]);  // my rows of that half are in registers / on their way
-            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&qflushed_bar[quarter]);      // my rows of that half are in registers / on their way
             pend = nullptr;
         };
         int64_t ft = ft0; int vt = vt0;
@@ -477,7 +532,7 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const uint16
                 for (int b = 0; b < 3; ++b) {
                     uint32_t v[24];
 #pragma unroll
-                    for (int k = 0; k < 24; ++k) v[k] = ft < n_ft_real ? __float_as_uint(__ldg(src + (b * 24 + k) * 32)) : 0u;
+                    for (int k = 0; k < 24; ++k) v[k] = __float_as_uint(__ldg(src + (b * 24 + k) * 32));
 #pragma unroll
                     for (int c = 0; c < 3; ++c) tmem_st_x8(t_lane + (uint32_t)(oct * 72 + b * 24 + c * 8), v + c * 8);
                 }
@@ -501,7 +556,7 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const uint16
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-                if (++vt == FUSED_NT) { vt = 0; ft += kClus; }
+                if (++vt == FUSED_NT) { vt = 0; ++ft; }
                 continue;
             }
             const uint32_t t_acc = t_lane + kAccCol0 + (uint32_t)acc * FUSED_BN + (uint32_t)(oct * 12);
@@ -624,10 +679,6 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const uint16
                     unpack2(accxy, res[(k & 3) * 3 + 0], res[(k & 3) * 3 + 1]);
                     unpack2(accz, zl, zh);
                     res[(k & 3) * 3 + 2] = zl + zh;
-                    if (DBG(2048)) {
-                        float* d1 = q_out + lane * kOutPitch + oct * 12 + (k & 3) * 3;
-                        d1[0] = res[(k & 3) * 3 + 0]; d1[1] = res[(k & 3) * 3 + 1]; d1[2] = res[(k & 3) * 3 + 2];
-                    }
                     if ((k & 3) == 3) {
                         TCLK(tg1);
                         TACC(2, tg0, tg1);
@@ -637,33 +688,31 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const uint16
                             if (res[0] == 123.456f && res[5] == 1.5f && res[10] == 7.f) vrow[half] = res[1] + res[4] + res[7] + res[11];
                             continue;
                         }
-                        if (n_staged > 0 && !DBG(512)) MBAR_WAIT(&qflushed_bar[quarter], (n_staged - 1) & 1);   // tile is free
+                        if (n_staged > 0) MBAR_WAIT(&qflushed_bar[quarter], (n_staged - 1) & 1);   // tile is free
                         float4* dst = reinterpret_cast<float4*>(q_out + lane * kOutPitch + oct * 12);
-                        if (!DBG(2048)) {
-                            dst[0] = make_float4(res[0], res[1], res[2], res[3]);
-                            dst[1] = make_float4(res[4], res[5], res[6], res[7]);
-                            dst[2] = make_float4(res[8], res[9], res[10], res[11]);
-                        }
-                        if (!DBG(1024)) {
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(&qstaged_bar[quarter]);
-                        }
+                        dst[0] = make_float4(res[0], res[1], res[2], res[3]);
+                        dst[1] = make_float4(res[4], res[5], res[6], res[7]);
+                        dst[2] = make_float4(res[8], res[9], res[10], res[11]);
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&qstaged_bar[quarter]);
                         ++n_staged;
-                        const int c_first = c_unit + half * 48;
-                        float* vhalf = vrow + half * 48;
-                        if (rows_valid() == 32 && c_first + 48 <= NVC) {
-                            pend = vhalf;                           // interior tile: stored during the next half
-                        } else {                                    // edge tile: predicated stores right away
-                            MBAR_WAIT(&qstaged_bar[quarter], (n_staged - 1) & 1);
+                        if (!(kStoreWarp && kGroups == 1)) {
+                            const int c_first = c_unit + half * 48;
+                            float* vhalf = vrow + half * 48;
+                            if (rows_valid() == 32 && c_first + 48 <= NVC) {
+                                pend = vhalf;                           // interior tile: stored during the next half
+                            } else {                                    // edge tile: predicated stores right away
+                                MBAR_WAIT(&qstaged_bar[quarter], (n_staged - 1) & 1);
 #pragma unroll
-                            for (int it = 0; it < 6; ++it) {
-                                const int j = it % 3, up = (it / 3) * 4;
-                                const float2 val = *reinterpret_cast<const float2*>(q_out + rb_smem[j] + up * kOutPitch);
-                                if (rb_row[j] + up < rows_valid() && c_first + rb_c2[j] < NVC)
-                                    store_vertex_pair(vhalf + rb_glob[j] + up * NVC, val);
+                                for (int it = 0; it < 6; ++it) {
+                                    const int j = it % 3, up = (it / 3) * 4;
+                                    const float2 val = *reinterpret_cast<const float2*>(q_out + rb_smem[j] + up * kOutPitch);
+                                    if (rb_row[j] + up < rows_valid() && c_first + rb_c2[j] < NVC)
+                                        store_vertex_pair(vhalf + rb_glob[j] + up * NVC, val);
+                                }
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive(&qflushed_bar[quarter]);
                             }
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(&qflushed_bar[quarter]);
                         }
                     }
                 }
@@ -711,7 +760,7 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const uint16
                     store_half(res, half);
                 }
             }
-            if (++vt == FUSED_NT) { vt = 0; ft += kClus; }
+            if (++vt == FUSED_NT) { vt = 0; ++ft; }
         }
         flush_pending();
 #ifdef PRK_FUSED_DEBUG
@@ -725,7 +774,6 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const uint16
 
     tcgen05_fence_before();
     __syncthreads();
-    if (kClus > 1) cluster_sync_all();          // no CTA leaves while a peer may still arrive on its barriers
     if (warp == kEpiWarps + 1) {
         tcgen05_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
@@ -804,80 +852,6 @@ int fused_stages(int groups) {
     return stages;
 }
 
-// cluster size of the vertex kernel: PRK_CLUSTER=1|2|4 overrides; default PRK_CLUSTER_DEFAULT when the batch has at
-// least that many frame tiles
-#ifndef PRK_CLUSTER_DEFAULT
-#define PRK_CLUSTER_DEFAULT 1
-#endif
-static int fused_cluster_size(int64_t n_ft) {
-    static const int forced = [] { const char* e = getenv("PRK_CLUSTER"); return e ? atoi(e) : 0; }();
-    int c = forced > 0 ? forced : PRK_CLUSTER_DEFAULT;
-    if (c != 1 && c != 2 && c != 4) c = 1;
-    while (c > 1 && n_ft < c) c >>= 1;
-    return c;
-}
-
-template <int kGroups, int kClus>
-static cudaError_t launch_fused_t(const Model& m, const CUtensorMap& tmap_A, int64_t rows_pad, const float* d_AskinT,
-                                  const float* d_off, int64_t B, float* d_verts, cudaStream_t s, int stages, int smem, int dbg,
-                                  bool pdl) {
-    auto kern = fused_blend_skin_kernel<kGroups, kClus>;
-    static std::atomic<int> attr_set[64];       // per device: dynamic shared memory this instantiation was opted in for
-    if (m.device >= 0 && m.device < 64 && attr_set[m.device].load(std::memory_order_acquire) < smem) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        attr_set[m.device].store(smem, std::memory_order_release);
-    }
-    const int64_t n_ft = rows_pad / FUSED_BM;
-    const int64_t n_units = ((n_ft + kClus - 1) / kClus) * FUSED_NT;          // cluster units
-    int grid = m.sm_count > 0 ? m.sm_count : 148;
-    cudaLaunchConfig_t cfg = {};
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = (size_t)smem;
-    cfg.stream = s;
-    cudaLaunchAttribute attr[2];
-    int na = 0;
-    if (kClus > 1) {
-        attr[na].id = cudaLaunchAttributeClusterDimension;
-        attr[na].val.clusterDim.x = kClus; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
-        ++na;
-        // one CTA per SM: as many clusters as the GPU can hold at once (a GPC with a number of SMs that is not a multiple
-        // of the cluster size leaves some idle)
-        static std::atomic<int> max_clusters[64];
-        int mc = (m.device >= 0 && m.device < 64) ? max_clusters[m.device].load(std::memory_order_acquire) : 0;
-        if (mc == 0) {
-            cfg.gridDim = dim3((unsigned)(grid / kClus * kClus));
-            cfg.attrs = attr; cfg.numAttrs = na;
-            cudaError_t e = cudaOccupancyMaxActiveClusters(&mc, kern, &cfg);
-            if (e != cudaSuccess) return e;
-            if (mc < 1) return cudaErrorInvalidConfiguration;
-            if (m.device >= 0 && m.device < 64) max_clusters[m.device].store(mc, std::memory_order_release);
-        }
-        if (grid > mc * kClus) grid = mc * kClus;
-        grid = grid / kClus * kClus;
-        if ((int64_t)grid / kClus > n_units) grid = (int)n_units * kClus;
-    } else if (grid > n_units) {
-        grid = (int)n_units;
-    }
-    // Programmatic dependent launch: the CTAs become resident and run their prologue (barrier init, tensor-memory
-    // allocation, descriptor prefetch) while the pose-chain kernel in front of them drains; every thread passes
-    // griddepcontrol.wait before it touches that kernel's outputs.  PRK_PDL=0 launches without the attribute.
-    if (pdl) {
-        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[na].val.programmaticStreamSerializationAllowed = 1;
-        ++na;
-    }
-    cfg.gridDim = dim3((unsigned)grid);
-    cfg.attrs = attr;
-    cfg.numAttrs = na;
-    const uint8_t* wpack = m.d_wpack;
-    const uint16_t* b2img = m.d_B2;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmap_A, b2img, d_AskinT, d_off, wpack, m.nnz_groups, stages, B, n_units,
-                                       d_verts, dbg);
-    count_launch();
-    return e != cudaSuccess ? e : cudaGetLastError();
-}
-
 cudaError_t launch_fused(const Model& m, const CUtensorMap& tmap_A, int64_t rows_pad, const float* d_AskinT,
                          const float* d_off, int64_t B, float* d_verts, cudaStream_t s) {
     if (B == 0) return cudaSuccess;
@@ -885,13 +859,43 @@ cudaError_t launch_fused(const Model& m, const CUtensorMap& tmap_A, int64_t rows
     const int stages = fused_stages(groups);
     const int smem = fused_smem_bytes(stages, groups);
     if (smem > kSmemLimit) return cudaErrorInvalidConfiguration;
+    static std::atomic<int> attr_set[64];       // per device: dynamic shared memory the kernels were opted in for
+    if (m.device >= 0 && m.device < 64 && attr_set[m.device].load(std::memory_order_acquire) < smem) {
+        cudaError_t e = cudaFuncSetAttribute(fused_blend_skin_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(fused_blend_skin_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        attr_set[m.device].store(smem, std::memory_order_release);
+    }
     const int dbg = 0;
+    const int64_t n_units = (rows_pad / FUSED_BM) * FUSED_NT;
+    int grid = m.sm_count > 0 ? m.sm_count : 148;
+    if (grid > n_units) grid = (int)n_units;
+    // Programmatic dependent launch: the CTAs become resident and run their prologue (barrier init, tensor-memory
+    // allocation, descriptor prefetch) while the pose-chain kernel in front of them drains; every thread passes
+    // griddepcontrol.wait before it touches that kernel's outputs.  PRK_PDL=0 launches without the attribute.
     static const bool pdl = [] { const char* e = getenv("PRK_PDL"); return !e || atoi(e) != 0; }();
-    const int clus = fused_cluster_size(rows_pad / FUSED_BM);
-#define PRK_GO(G, C) launch_fused_t<G, C>(m, tmap_A, rows_pad, d_AskinT, d_off, B, d_verts, s, stages, smem, dbg, pdl)
-    if (groups == 1) return clus == 4 ? PRK_GO(1, 4) : (clus == 2 ? PRK_GO(1, 2) : PRK_GO(1, 1));
-    return clus == 4 ? PRK_GO(0, 4) : (clus == 2 ? PRK_GO(0, 2) : PRK_GO(0, 1));
-#undef PRK_GO
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    const uint8_t* wpack = m.d_wpack;
+    const uint16_t* b2img = m.d_B2;
+    cudaError_t e;
+    if (groups == 1)
+        e = cudaLaunchKernelEx(&cfg, fused_blend_skin_kernel<1>, tmap_A, b2img, d_AskinT, d_off, wpack, groups, stages, B,
+                               n_units, d_verts, dbg);
+    else
+        e = cudaLaunchKernelEx(&cfg, fused_blend_skin_kernel<0>, tmap_A, b2img, d_AskinT, d_off, wpack, groups, stages, B,
+                               n_units, d_verts, dbg);
+    count_launch();
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 }  // namespace prk

@@ -58,14 +58,6 @@ constexpr int kAChunkBytes = FUSED_BM * 128;                     // 128 frames x
 constexpr int kABytes = FUSED_A_CHUNKS * kAChunkBytes;           // 114,688: resident A' tile
 constexpr int kBChunkBytes = FUSED_BN * 128;                     // 96 vertex coords x 64 bf16 = 12,288
 constexpr int kEpiWarps = 16;
-// Store warp (kGroups == 1): the read-back of the staging tiles and the global vertex stores are done by the TMA producer
-// warp, which is otherwise idle between its eight bulk copies per unit -- the sixteen epilogue warps only gather, multiply
-// and stage.  -DPRK_STOREWARP=0: every epilogue warp reads its own rows back and stores them (round-1 kernel).
-#ifndef PRK_STOREWARP
-#define PRK_STOREWARP 1
-#endif
-constexpr bool kStoreWarp = PRK_STOREWARP != 0;
-
 constexpr int kOutPitch = 52;                                    // floats per staged frame row: 16 vertices x 3 (+4: conflict-free float4)
 constexpr int kOutBytesPerQuarter = 32 * kOutPitch * 4;          // 32 frames of one TMEM lane quarter
 constexpr int kOutBytes = 4 * kOutBytesPerQuarter;               // 26,624
@@ -181,12 +173,6 @@ __device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
-__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {     // has the phase of this parity completed?
-    uint32_t done;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    return done != 0;
-}
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
@@ -242,7 +228,7 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const uint16
         for (int i = 0; i < kWSlots; ++i) mbar_init(&wfull_bar[i], 1);
         mbar_init(afull_bar, 1);
         mbar_init(aempty_bar, 1);
-        for (int i = 0; i < 4; ++i) { mbar_init(&qstaged_bar[i], 4); mbar_init(&qflushed_bar[i], (kStoreWarp && kGroups == 1) ? 1 : 4); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&qstaged_bar[i], 4); mbar_init(&qflushed_bar[i], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kEpiWarps + 1) {
@@ -267,116 +253,7 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const uint16
     const int64_t ft0 = u0 / FUSED_NT;
     const int vt0 = (int)(u0 - ft0 * FUSED_NT);
 
-    if (warp == kEpiWarps && kStoreWarp && kGroups == 1) {
-        // ===== TMA producer + store warp: one polling loop, nothing in it blocks =====
-        // producer duty: A' tile per frame tile, skinning weights per unit, eight B' chunks per unit through the ring;
-        // store duty: whenever the four epilogue warps of a lane quarter have staged a half unit (32 frames x 16 vertices),
-        // read the tile back (coalesced 8-byte pieces, 192-byte frame rows), hand the tile back, store the rows.
-        int stage = 0; uint32_t phase = 0;
-        int64_t ft = ft0; int vt = vt0;
-        uint32_t n_ft = 0;
-        int i_p = 0, c_p = -1;                  // unit being loaded; its next chunk (-1: A' tile / weights not issued yet)
-        const uint32_t n_halves = 2u * (uint32_t)n_my;
-        const uint32_t wbytes = (uint32_t)groups * FUSED_WGROUP_BYTES;
-        // read-back pattern of one pass: float2 index q = it * 32 + lane over [4 rows][24 float2], it = 0..2
-        int rb_smem[3], rb_glob[3], rb_row[3], rb_c2[3];
-#pragma unroll
-        for (int it = 0; it < 3; ++it) {
-            const int q = it * 32 + lane;
-            rb_row[it] = q / 24; rb_c2[it] = (q % 24) * 2;
-            rb_smem[it] = rb_row[it] * kOutPitch + rb_c2[it];
-            rb_glob[it] = rb_row[it] * NVC + rb_c2[it];
-        }
-        auto store_half_of = [&](int quarter, uint32_t n) {
-            const int t = vt0 + (int)(n >> 1), fti = t / FUSED_NT, vtu = t - fti * FUSED_NT, half = (int)(n & 1);
-            const int row0 = ((int)ft0 + fti) * FUSED_BM + quarter * 32;
-            const int left = (int)B - row0, valid = left < 32 ? left : 32;
-            const int c_first = vtu * (FUSED_VT * 3) + half * 48;
-            const float* tile = reinterpret_cast<const float*>(sOut + quarter * kOutBytesPerQuarter);
-            float* g = verts + (size_t)row0 * NVC + c_first;
-            float2 v[24];
-#pragma unroll
-            for (int it = 0; it < 24; ++it)
-                v[it] = *reinterpret_cast<const float2*>(tile + rb_smem[it % 3] + (it / 3) * 4 * kOutPitch);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&qflushed_bar[quarter]);      // the tile is in registers: the quarter may stage again
-            if (DBG(4)) { if (v[0].x != 123.456f) return; }
-            if (valid == 32 && c_first + 48 <= NVC) {                 // warp-uniform: all but the edge tiles
-#pragma unroll
-                for (int it = 0; it < 24; ++it) store_vertex_pair(g + rb_glob[it % 3] + (it / 3) * 4 * NVC, v[it]);
-            } else {
-#pragma unroll
-                for (int it = 0; it < 24; ++it)
-                    if (rb_row[it % 3] + (it / 3) * 4 < valid && c_first + rb_c2[it % 3] < NVC)
-                        store_vertex_pair(g + rb_glob[it % 3] + (it / 3) * 4 * NVC, v[it]);
-            }
-        };
-        // The loop body is kept SMALL (one copy of the store code, counters packed in one register pair): a polling loop that
-        // branches over four inlined copies of it ran at ~1,400 clk per pass, apparently on instruction fetch.
-        uint64_t nf = 0;                        // halves stored so far, 16 bits per lane quarter (a CTA sees < 2^15 units)
-        uint32_t idle = 0;
-        uint64_t t_idle = 0;
-        for (;;) {
-            bool busy = false;
-#pragma unroll 1
-            for (int rep = 0; rep < 4 && i_p < n_my; ++rep) {      // producer duty: up to four steps per pass
-                if (c_p < 0) {
-                    const bool new_tile = i_p == 0 || vt == 0;
-                    // the MMAs of the previous frame tile still read the resident A' tile
-                    if (new_tile && n_ft > 0 && !mbar_test(aempty_bar, (n_ft - 1) & 1)) break;
-                    if (elect_one()) {
-                        if (new_tile) {
-                            mbar_expect_tx(afull_bar, kABytes);
-                            for (int c = 0; c < FUSED_A_CHUNKS; ++c)
-                                tma_load_2d(&tmap_A, afull_bar, sA + c * kAChunkBytes, c * 64, (int)(ft * FUSED_BM));
-                        }
-                        // skinning weights of the tile's 32 vertices (slot reuse: see the plain producer below)
-                        uint64_t* wb = &wfull_bar[i_p & (kWSlots - 1)];
-                        mbar_expect_tx(wb, wbytes);
-                        bulk_load_1d(sW + (i_p & (kWSlots - 1)) * wbytes, wpack + (size_t)vt * wbytes, wbytes, wb);
-                    }
-                    if (new_tile) ++n_ft;
-                    c_p = 0;
-                } else {
-                    if (!mbar_test(&empty_bar[stage], phase ^ 1)) break;
-                    if (elect_one()) {
-                        if (DBG(16)) { mbar_arrive(&full_bar[stage]); }
-                        else {
-                            mbar_expect_tx(&full_bar[stage], kBChunkBytes);
-                            bulk_load_1d(sB + stage * kBChunkBytes,
-                                         B2img + ((size_t)vt * FUSED_B_CHUNKS + c_p) * (kBChunkBytes / 2), kBChunkBytes, &full_bar[stage]);
-                        }
-                    }
-                    if (++stage == stages) { stage = 0; phase ^= 1; }
-                    if (++c_p == FUSED_B_CHUNKS) {
-                        c_p = -1; ++i_p;
-                        if (++vt == FUSED_NT) { vt = 0; ++ft; }
-                    }
-                }
-                busy = true;
-            }
-            bool stored_all = true;
-            if (!DBG(2) && !DBG(128)) {
-#pragma unroll 1
-                for (int q = 0; q < 4; ++q) {                      // store duty: at most one half per lane quarter per pass
-                    const uint32_t n = (uint32_t)(nf >> (16 * q)) & 0xFFFFu;
-                    if (n >= n_halves) continue;
-                    stored_all = false;
-                    if (!mbar_test(&qstaged_bar[q], n & 1)) continue;
-                    store_half_of(q, n);
-                    nf += 1ull << (16 * q);
-                    busy = true;
-                }
-            }
-            if (i_p >= n_my && stored_all) break;
-            if (busy) { idle = 0; continue; }
-            if ((++idle & 0x3FF) == 0) {                          // bounded like every other wait: trap after ~4 s without progress
-                const uint64_t now = global_ns();
-                if (idle == 0x400) t_idle = now;
-                else if (now - t_idle > 4000000000ull) __trap();
-            }
-        }
-    } else if (warp == kEpiWarps) {
+    if (warp == kEpiWarps) {
         // ===== TMA producer (whole warp converged, one elected lane issues) =====
         int stage = 0; uint32_t phase = 0;
         int64_t ft = ft0; int vt = vt0;
@@ -502,11 +379,10 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const uint16
         float* pend = nullptr;
         uint32_t n_staged = 0;                                        // halves this warp has staged so far
         auto flush_pending = [&]() {
-            if (kStoreWarp && kGroups == 1) return;                   // the store warp reads the tiles back
             if (pend == nullptr) return;                              // warp-uniform
             MBAR_WAIT(&qstaged_bar[quarter], (n_staged - 1) & 1);    // all four warps staged the pending half
 #pragma unroll
-            for (int it = 0; it < 6; ++it) {
+            for (int it = 0; it < (DBG(256) ? 0 : 6); ++it) {
                 const int j = it % 3, up = (it / 3) * 4;
                 const float2 val = *reinterpret_cast<const float2*>(q_out + rb_smem[j] + up * kOutPitch);
                 if (!DBG(4) || val.x == 123.456f) store_vertex_pair(pend + rb_glob[j] + up * NVC, val);
@@ -696,23 +572,21 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const uint16
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&qstaged_bar[quarter]);
                         ++n_staged;
-                        if (!(kStoreWarp && kGroups == 1)) {
-                            const int c_first = c_unit + half * 48;
-                            float* vhalf = vrow + half * 48;
-                            if (rows_valid() == 32 && c_first + 48 <= NVC) {
-                                pend = vhalf;                           // interior tile: stored during the next half
-                            } else {                                    // edge tile: predicated stores right away
-                                MBAR_WAIT(&qstaged_bar[quarter], (n_staged - 1) & 1);
+                        const int c_first = c_unit + half * 48;
+                        float* vhalf = vrow + half * 48;
+                        if (rows_valid() == 32 && c_first + 48 <= NVC) {
+                            pend = vhalf;                           // interior tile: stored during the next half
+                        } else {                                    // edge tile: predicated stores right away
+                            MBAR_WAIT(&qstaged_bar[quarter], (n_staged - 1) & 1);
 #pragma unroll
-                                for (int it = 0; it < 6; ++it) {
-                                    const int j = it % 3, up = (it / 3) * 4;
-                                    const float2 val = *reinterpret_cast<const float2*>(q_out + rb_smem[j] + up * kOutPitch);
-                                    if (rb_row[j] + up < rows_valid() && c_first + rb_c2[j] < NVC)
-                                        store_vertex_pair(vhalf + rb_glob[j] + up * NVC, val);
-                                }
-                                __syncwarp();
-                                if (lane == 0) mbar_arrive(&qflushed_bar[quarter]);
+                            for (int it = 0; it < 6; ++it) {
+                                const int j = it % 3, up = (it / 3) * 4;
+                                const float2 val = *reinterpret_cast<const float2*>(q_out + rb_smem[j] + up * kOutPitch);
+                                if (rb_row[j] + up < rows_valid() && c_first + rb_c2[j] < NVC)
+                                    store_vertex_pair(vhalf + rb_glob[j] + up * NVC, val);
                             }
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&qflushed_bar[quarter]);
                         }
                     }
                 }

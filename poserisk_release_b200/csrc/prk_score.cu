@@ -55,15 +55,23 @@ enum Slot { S_TORSO = 0, S_LKNEE, S_RKNEE, S_NECK, S_LTHORAX, S_RTHORAX, S_LSHOU
 __host__ __device__ constexpr int slot_joint(int s) { return s < 3 ? 3 + s : (s < 6 ? 9 + s : 10 + s); }
 
 struct Angles { double a[N_SLOTS][3]; };   // Euler degrees [slot][x,y,z]
+// components of a scored joint's Euler triple that some REBA / RULA rule reads (the P(slot, c)
+// uses below): knees x only, thorax x and z, elbows y and z, everything else all three
+__host__ __device__ constexpr int slot_need(int s) {
+    return (s == S_LKNEE || s == S_RKNEE) ? 1 : ((s == S_LTHORAX || s == S_RTHORAX) ? 5 : ((s == S_LELBOW || s == S_RELBOW) ? 6 : 7));
+}
 
 __device__ __forceinline__ int iclip(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 // cv2.Rodrigues(rvec)[0] followed by rotationMatrixToEulerAngles and *180/pi
 // (coord_utils.py:86,69-81,93).  Returns true when R is not finite, i.e. the reference's
 // assert(isRotationMatrix(R)) (coord_utils.py:70) fires.
+// kNeed (a constant after inlining / unrolling): bit c set = component c (x, y, z) is wanted; the others come back as 0
+// and their atan2 is not evaluated
+// (the ladders never read 8 of the 36 angles: knees y/z, thorax y, elbows x -- slot_need below).
 template <bool kF32>
 __device__ __forceinline__ bool euler_from_axis_angle(double x, double y, double z, double& ex,
-                                                      double& ey, double& ez) {
+                                                      double& ey, double& ez, const int kNeed = 7) {
     const double th2 = __dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z));
     const double theta = sqrt(th2);
     double R00, R10, R20, R21, R22, R11, R12;
@@ -95,19 +103,19 @@ __device__ __forceinline__ bool euler_from_axis_angle(double x, double y, double
     } else {
         sy = sqrt(__dadd_rn(__dmul_rn(R00, R00), __dmul_rn(R10, R10)));
     }
+    ex = ey = ez = 0.0;
     if (!(sy < 1e-6)) {
-        ex = atan2(R21, R22);
-        ey = atan2(-R20, sy);
-        ez = atan2(R10, R00);
+        if (kNeed & 1) ex = atan2(R21, R22);
+        if (kNeed & 2) ey = atan2(-R20, sy);
+        if (kNeed & 4) ez = atan2(R10, R00);
     } else {
-        ex = atan2(-R12, R11);
-        ey = atan2(-R20, sy);
-        ez = 0.0;
+        if (kNeed & 1) ex = atan2(-R12, R11);
+        if (kNeed & 2) ey = atan2(-R20, sy);
     }
     const double kPi = 3.141592653589793;
-    ex = __ddiv_rn(__dmul_rn(ex, 180.0), kPi);
-    ey = __ddiv_rn(__dmul_rn(ey, 180.0), kPi);
-    ez = __ddiv_rn(__dmul_rn(ez, 180.0), kPi);
+    if (kNeed & 1) ex = __ddiv_rn(__dmul_rn(ex, 180.0), kPi);
+    if (kNeed & 2) ey = __ddiv_rn(__dmul_rn(ey, 180.0), kPi);
+    if (kNeed & 4) ez = __ddiv_rn(__dmul_rn(ez, 180.0), kPi);
     return !isfinite(theta);
 }
 
@@ -479,8 +487,11 @@ constexpr int kPosePitch = 73;            // elements per staged pose row (72 + 
 constexpr int kDebugStageJoints = 6;      // debug joint lists up to this length are staged (longer lists: direct stores)
 constexpr int kDebugPitch = kDebugStageJoints * 3 + 1;
 
+#ifndef PRK_SCORE_MINBLOCKS
+#define PRK_SCORE_MINBLOCKS 1
+#endif
 template <typename T>
-__global__ void __launch_bounds__(kScoreWarps * 32)
+__global__ void __launch_bounds__(kScoreWarps * 32, PRK_SCORE_MINBLOCKS)
 score_pose_kernel(const T* __restrict__ pose, const prk_addinfo* __restrict__ info, int32_t n_tracks,
                   const int32_t* __restrict__ track, int64_t B, uint32_t which,
                   prk_score_rec* __restrict__ out, double* __restrict__ euler_out,
@@ -520,8 +531,12 @@ score_pose_kernel(const T* __restrict__ pose, const prk_addinfo* __restrict__ in
     for (int s = 0; s < N_SLOTS; ++s) {
         const int j = slot_joint(s);
         double ex, ey, ez;
-        bad |= euler_from_axis_angle<sizeof(T) == 4>((double)p[j * 3 + 0], (double)p[j * 3 + 1],
-                                                    (double)p[j * 3 + 2], ex, ey, ez);
+        if (slot_need(s) != 7 && (debug_mask & (1u << j)))    // warp-uniform: a debug joint needs the whole triple
+            bad |= euler_from_axis_angle<sizeof(T) == 4>((double)p[j * 3 + 0], (double)p[j * 3 + 1],
+                                                        (double)p[j * 3 + 2], ex, ey, ez);
+        else
+            bad |= euler_from_axis_angle<sizeof(T) == 4>((double)p[j * 3 + 0], (double)p[j * 3 + 1],
+                                                        (double)p[j * 3 + 2], ex, ey, ez, slot_need(s));
         A.a[s][0] = ex; A.a[s][1] = ey; A.a[s][2] = ez;
         if (debug_mask & (1u << j)) emit(j, ex, ey, ez);
     }

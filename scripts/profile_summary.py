@@ -24,7 +24,7 @@ for r in rows:
     tot[name][1] += float(r[-1].replace(',', '')) / 1e3
 total = sum(v[1] for v in tot.values())
 with open(os.path.join(out, f'{tag}_launch_summary.txt'), 'w') as f:
-    f.write('ncu --metrics gpu__time_duration.sum --clock-control none, python bench.py --steps 3 --warmup 3 (PRK_BENCH_PRELOAD_S=0)\n')
+    f.write('ncu --metrics gpu__time_duration.sum --clock-control none, python bench.py --steps 3 --warmup 3 --repeats 1 --skip-extra (PRK_BENCH_PRELOAD_S=0)\n')
     for name, (n, us) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
         f.write('%-60s launches %3d  total %8.1f us  share %5.1f%%  avg %6.1f us\n' % (name, n, us, 100 * us / total, us / n))
 print(open(os.path.join(out, f'{tag}_launch_summary.txt')).read())

@@ -378,12 +378,14 @@ def run_gpu_arm(args):
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
+        local_ms.append(ms)
         if world > 1:
             t = torch.tensor([ms], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         return ms
 
+    local_ms = []            # this rank's own event times, in call order (diagnostic: how far apart the ranks are)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -405,6 +407,12 @@ def run_gpu_arm(args):
     ms_runs = [timed(step_device, K) for _ in range(R)]
     launches = (_lib.launch_count() - launches0) // R
     ms = float(np.median(ms_runs))
+    per_rank = None
+    if world > 1:            # every rank's own median step time of the timed regions
+        t = torch.tensor([float(np.median(local_ms[-R:])) / K], device=dev, dtype=torch.float64)
+        allt = torch.empty(world, device=dev, dtype=torch.float64)
+        dist.all_gather_into_tensor(allt, t)
+        per_rank = [float(x) for x in allt.cpu()]
     # one more pass of K steps with a CUDA-event pair around every kernel (on the stream it is launched on):
     # per-kernel durations for the roofline.  Kept out of the timed region: the event records cost ~5 %.
     _lib.check(L.prk_profile_begin())
@@ -506,7 +514,7 @@ def run_gpu_arm(args):
                                 "tensors on the input's device and the reference reads vertices only for a debug .obj) -- "
                                 "see e2e_with_verts for the host-to-host full-mesh rate, which is PCIe bound"},
                 "e2e_with_verts": e2e_verts,
-                "gpu_launches": int(launches),
+                "gpu_launches": int(launches), "per_rank_ms_per_step": per_rank,
                 "roofline": dominant, "roofline_other": other, "stages": per_stage,
                 "cpu_baseline": cpu_baseline, "parity": parity}
         line.update(extra)

@@ -230,21 +230,27 @@ int prk_score_histogram(const prk_score_rec* d_scores, int64_t B, uint32_t which
  *   prk_allgather_rows     d_local: n_local rows of row_bytes that belong at row
  *                          `row_offset` of the gathered array (row_bytes: a multiple of 8); every rank must call it the same number of
  *                          times.  On return (stream order) *d_gathered_out = the device pointer of the
- *                          slot holding all ranks' rows; it stays valid until this rank's next-but-one call.
+ *                          slot holding all ranks' rows; readers must be queued before this rank issues its next
+ *                          exchange on the communicator (two slots alternate).
  *                          A peer that does not arrive within ~20 s makes a later prk_comm_status()
  *                          return PRK_ERR_PEER.
  *   prk_allgather_scores   the same for prk_score_rec rows (row_bytes = 32)
+ *   prk_comm_wait          makes `stream` wait for the most recent exchange (needed after prk_pipeline /
+ *                          prk_pipeline_host, which run the exchange on a side stream and do not join it)
  *   prk_comm_gathered      device pointer of the slot written by the most recent exchange
  *   prk_comm_status        PRK_OK, or PRK_ERR_PEER once a wait has timed out (reads a host-mapped flag)
  * prk_pipeline / prk_pipeline_host take the communicators directly (comm_scores, comm_euler, frame_offset): the
  * exchange then runs on the handle's scoring stream right behind the scoring kernel, i.e. underneath the vertex
- * kernel, and is joined into the caller's stream with the rest of the call. */
+ * kernel.  It waits for the peers, so the call does NOT join it into the caller's stream (a fast rank may run one call
+ * ahead of a slow one): call prk_comm_wait(comm, stream) where the gathered rows are read.  d_scores / d_euler_out must
+ * not be modified by other work until then. */
 typedef struct prk_comm prk_comm;
 int prk_comm_create(prk_comm** out, int rank, int world, int device, size_t slot_bytes);
 void prk_comm_destroy(prk_comm* comm);
 size_t prk_comm_handle_bytes(void);
 int prk_comm_get_handle(prk_comm* comm, void* h_handle_out);
 int prk_comm_open_peers(prk_comm* comm, const void* h_all_handles);
+int prk_comm_wait(prk_comm* comm, void* stream);
 void* prk_comm_gathered(prk_comm* comm);
 int prk_allgather_rows(prk_comm* comm, const void* d_local, int64_t n_local, int64_t row_offset,
                        int64_t row_bytes, void** d_gathered_out, void* stream);

@@ -40,7 +40,7 @@ EXPORTS = (
     'prk_rot_to_angle', 'prk_host_workspace_bytes', 'prk_host_scores_offset', 'prk_pipeline_host', 'prk_score_histogram', 'prk_debug_blend',
     'prk_vposed_pitch', 'prk_launch_count', 'prk_profile_begin', 'prk_profile_end',
     'prk_comm_create', 'prk_comm_destroy', 'prk_comm_handle_bytes', 'prk_comm_get_handle', 'prk_comm_open_peers',
-    'prk_comm_gathered', 'prk_allgather_rows', 'prk_allgather_scores', 'prk_comm_status')
+    'prk_comm_gathered', 'prk_comm_wait', 'prk_allgather_rows', 'prk_allgather_scores', 'prk_comm_status')
 
 
 class PoseRiskError(RuntimeError):
@@ -110,6 +110,8 @@ def lib():
     L.prk_comm_get_handle.argtypes = [vp, vp]
     L.prk_comm_open_peers.restype = i32
     L.prk_comm_open_peers.argtypes = [vp, vp]
+    L.prk_comm_wait.restype = i32
+    L.prk_comm_wait.argtypes = [vp, vp]
     L.prk_comm_gathered.restype = vp
     L.prk_comm_gathered.argtypes = [vp]
     L.prk_allgather_rows.restype = i32

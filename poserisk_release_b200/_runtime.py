@@ -139,7 +139,10 @@ class PeerComm:
         return self.view(n_total_rows, row_shape, local.dtype, out.value)
 
     def gathered(self, n_rows: int, row_shape, dtype) -> torch.Tensor:
-        """View of the slot written by the most recent exchange (e.g. one issued inside prk_pipeline)."""
+        """View of the slot written by the most recent exchange (e.g. one issued inside prk_pipeline, which runs it
+        on a side stream): the current stream is made to wait for that exchange first."""
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().prk_comm_wait(self.handle, stream_ptr(self.device)))
         return self.view(n_rows, tuple(row_shape), dtype, _lib.lib().prk_comm_gathered(self.handle))
 
     def view(self, n_rows, row_shape, dtype, address):

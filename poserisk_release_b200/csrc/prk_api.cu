@@ -426,7 +426,6 @@ int prk_model_create(prk_model** out, int device, const float* vt, const float* 
     PRK_M(cudaEventCreateWithFlags(&m->ev_h2d, cudaEventDisableTiming));
     PRK_M(cudaEventCreateWithFlags(&m->ev_joints, cudaEventDisableTiming));
     PRK_M(cudaEventCreateWithFlags(&m->ev_out, cudaEventDisableTiming));
-    PRK_M(cudaEventCreateWithFlags(&m->ev_gather, cudaEventDisableTiming));
 #undef PRK_M
     *out = m;
     return PRK_OK;
@@ -447,7 +446,6 @@ void prk_model_destroy(prk_model* model) {
     if (m->ev_h2d) cudaEventDestroy(m->ev_h2d);
     if (m->ev_joints) cudaEventDestroy(m->ev_joints);
     if (m->ev_out) cudaEventDestroy(m->ev_out);
-    if (m->ev_gather) cudaEventDestroy(m->ev_gather);
     for (int i = 0; i < 2; ++i) if (m->ev_set_free[i]) cudaEventDestroy(m->ev_set_free[i]);
     delete m;
 }
@@ -571,16 +569,17 @@ int prk_pipeline(prk_model* model, const float* d_pose, const float* d_betas, co
         e = launch_score_pose(d_pose, PRK_DTYPE_F32, d_info, n_tracks, d_track, B, PRK_SCORE_REBA | PRK_SCORE_RULA,
                               d_scores, n_debug > 0 ? d_euler_out : nullptr, dbg, n_debug, ss);
     }
-    // multi-GPU: the records (and debug Euler rows) go to every rank's gather buffer straight from the scoring
-    // stream, i.e. underneath the vertex kernel that is launched on `s` below
+    // the caller's stream joins the scoring stream where the RECORDS are final, whatever happens next: nothing of this
+    // call's own outputs is still being written once `stream` has passed it, also when the call reports an error
+    cudaError_t e2 = cudaEventRecord(m->ev_score, ss);
+    // multi-GPU: the records (and debug Euler rows) go to every rank's gather buffer straight from the scoring stream,
+    // i.e. underneath the vertex kernel launched on `s` below.  The exchange waits for the peers, so it is NOT joined
+    // into `stream`: prk_comm_wait does that where the gathered rows are needed (a rank may run one call ahead).
     int rc = PRK_OK;
     if (e == cudaSuccess && comm_scores)
         rc = prk_allgather_rows(comm_scores, d_scores, B, frame_offset, sizeof(prk_score_rec), nullptr, ss);
     if (e == cudaSuccess && rc == PRK_OK && comm_euler)
         rc = prk_allgather_rows(comm_euler, d_euler_out, B, frame_offset, n_debug * 24, nullptr, ss);
-    // whatever happens next, the caller's stream joins the scoring stream: nothing of this call is still
-    // running once `stream` has passed it, also when the call reports an error
-    cudaError_t e2 = cudaEventRecord(m->ev_score, ss);
     if (e == cudaSuccess && e2 == cudaSuccess && rc == PRK_OK)
         rc = forward_impl(m, d_pose, d_betas, d_trans, center_idx, B, d_verts, d_joints, ws, ws_bytes, s);
     if (e2 == cudaSuccess) e2 = cudaStreamWaitEvent(s, m->ev_score, 0);
@@ -680,12 +679,9 @@ int prk_pipeline_host(prk_model* model, const float* h_pose, const float* h_beta
                                    d_scores, nullptr, DebugSlots{}, 0, ss));
     }
     PRK_CUDA(cudaEventRecord(m->ev_score, ss));
-    cudaEvent_t ev_gather = nullptr;
-    if (comm_scores) {   // multi-GPU: all-gather of the records underneath the vertex kernel (joined at the end)
+    if (comm_scores) {   // multi-GPU: all-gather of the records underneath the vertex kernel; joined by prk_comm_wait
         const int rcg = prk_allgather_rows(comm_scores, d_scores, B, frame_offset, sizeof(prk_score_rec), nullptr, ss);
         if (rcg != PRK_OK) { cudaStreamWaitEvent(s, m->ev_score, 0); chain_break(ws, nullptr); return rcg; }
-        ev_gather = m->ev_gather;
-        PRK_CUDA(cudaEventRecord(ev_gather, ss));
     }
     PRK_CUDA(cudaStreamWaitEvent(s, m->ev_h2d, 0));
     PRK_CUDA(cudaStreamWaitEvent(s, m->ev_out, 0));         // d_joints of the previous call has been copied out
@@ -705,7 +701,6 @@ int prk_pipeline_host(prk_model* model, const float* h_pose, const float* h_beta
     PRK_CUDA(cudaEventRecord(m->ev_out, m->s_out));
     // completion stays ordered on the caller's stream: it joins the copy-out and the scoring stream
     PRK_CUDA(cudaStreamWaitEvent(s, m->ev_out, 0));
-    if (ev_gather) PRK_CUDA(cudaStreamWaitEvent(s, ev_gather, 0));
     PRK_CUDA(cudaEventRecord(m->ev_set_free[set], s));
     return PRK_OK;
 }

@@ -16,8 +16,9 @@
 // host round trip, a few microseconds per exchange; it can run on a side stream underneath the vertex kernel.
 //
 // Slot reuse: rank A writes slot e&1 of rank B during A's exchange e, which starts after A has seen B's flag of
-// exchange e-1, i.e. after B's stream reached its exchange e-1.  B's readers of exchange e-2 (same slot) are ordered
-// before that on B's stream -- hence "valid until this rank's next-but-one call".
+// exchange e-1, i.e. after B's stream reached its exchange e-1.  B's readers of exchange e-2 (same slot) are safe if they
+// were queued before B ISSUED its exchange e-1 (the exchange is ordered behind the work already on its stream) -- hence
+// "the gathered rows of a call stay valid until this rank issues its next exchange on the communicator".
 #include "prk_internal.h"
 
 #include <cstdio>
@@ -265,6 +266,12 @@ int prk_allgather_scores(prk_comm* c, const prk_score_rec* d_local, int64_t n_lo
 void* prk_comm_gathered(prk_comm* c) {
     if (!c || c->epoch == 0) return nullptr;
     return c->d_buf + (size_t)(c->epoch & 1) * c->slot_bytes;
+}
+
+int prk_comm_wait(prk_comm* c, void* stream) {
+    if (!c) { prk::comm_set_detail("prk_comm_wait", "null argument"); return PRK_ERR_INVALID_ARG; }
+    if (c->ev_valid) COMM_CUDA(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), c->ev_last, 0));
+    return PRK_OK;
 }
 
 int prk_comm_status(prk_comm* c) {

@@ -90,7 +90,7 @@ struct prk_model {
     cudaEvent_t ev_in = nullptr, ev_score = nullptr;
     // host-buffer pipeline (prk_pipeline_host): copy-in / copy-out streams beside the kernels, two input sets
     cudaStream_t s_in = nullptr, s_out = nullptr;
-    cudaEvent_t ev_h2d = nullptr, ev_joints = nullptr, ev_out = nullptr, ev_gather = nullptr, ev_set_free[2] = {nullptr, nullptr};
+    cudaEvent_t ev_h2d = nullptr, ev_joints = nullptr, ev_out = nullptr, ev_set_free[2] = {nullptr, nullptr};
     uint64_t host_calls = 0;
 };
 

@@ -407,6 +407,10 @@ int prk_model_create(prk_model** out, int device, const float* vt, const float* 
 #define PRK_M(expr) do { e = (expr); if (e != cudaSuccess) { prk_model_destroy(m); return cuda_fail(e, #expr); } } while (0)
     PRK_M(cudaMalloc(&m->d_B2, B2.size() * 2));
     PRK_M(cudaMemcpy(m->d_B2, B2.data(), B2.size() * 2, cudaMemcpyHostToDevice));
+    {   // raw (un-swizzled) view of the pre-swizzled chunk images: a box = 48 rows of 128 bytes = one CTA's half of a chunk
+        const int rc = encode_tmap_2d_ex(&m->tmap_B2, m->d_B2, (uint64_t)FUSED_NT * FUSED_B_CHUNKS * FUSED_BN, 64, FUSED_BN / 2, 64, 2, 0);
+        if (rc != PRK_OK) { prk_model_destroy(m); return rc; }
+    }
     PRK_M(cudaMalloc(&m->d_wpack, wp.size()));
     PRK_M(cudaMemcpy(m->d_wpack, wp.data(), wp.size(), cudaMemcpyHostToDevice));
     {

@@ -61,16 +61,21 @@ constexpr int kEpiWarps = 16;
 constexpr int kOutPitch = 52;                                    // floats per staged frame row: 16 vertices x 3 (+4: conflict-free float4)
 constexpr int kOutBytesPerQuarter = 32 * kOutPitch * 4;          // 32 frames of one TMEM lane quarter
 constexpr int kOutBytes = 4 * kOutBytesPerQuarter;               // 26,624
-constexpr int kWSlots = 4;
-constexpr int kMaxStages = 6;
-constexpr int kNumBars = 2 * kMaxStages + 2 * kEpiWarps + 2 + kWSlots + 2 + 8;
+constexpr int kWSlotsMax = 8;
+// weight slots of the ring: a slot is reused kWS units later, which must be more than the producer's lead over the epilogue
+// (ring length in units + the two accumulator buffers + the unit in progress): 4 with the 6-chunk ring (< 1 unit),
+// 8 with the 10-half-chunk ring of the CTA pairs (1.25 units)
+constexpr int w_slots(int pair) { return pair == 2 ? 8 : 4; }
+constexpr int w_shift(int pair) { return pair == 2 ? 3 : 2; }
+constexpr int kMaxStages = 12;                                   // 6 x 12 KB chunks, or 12 x 6 KB half chunks (CTA pairs)
+constexpr int kNumBars = 2 * kMaxStages + 2 * kEpiWarps + 2 + kWSlotsMax + 2 + 8;
 constexpr int kThreads = (kEpiWarps + 2) * 32;                   // 576
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kAccCol0 = 288;                               // accumulators behind the 24 x 12 A_j columns
 constexpr int kSmemLimit = 232448;                               // 227 KB opt-in maximum per CTA
 
-constexpr int fused_smem_bytes(int stages, int groups) {
-    return kABytes + stages * kBChunkBytes + kOutBytes + kWSlots * groups * FUSED_WGROUP_BYTES + kNumBars * 8 + 16 +
+constexpr int fused_smem_bytes(int stages, int groups, int pair = 1) {
+    return kABytes + stages * (kBChunkBytes / pair) + kOutBytes + w_slots(pair) * groups * FUSED_WGROUP_BYTES + kNumBars * 8 + 16 +
            1024 /*alignment slack*/;
 }
 
@@ -83,6 +88,35 @@ __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_
 // vertex stores are evict-first (st.global.cs).  (An evict_last hint on the B' loads measured no gain.)
 __device__ __forceinline__ void store_vertex_pair(float* dst, float2 v) {
     __stcs(reinterpret_cast<float2*>(dst), v);                  // st.global.cs: evict-first
+}
+// ---- CTA pairs (cta_group::2): two CTAs of a cluster walk the same vertex tiles for two consecutive frame tiles; ONE
+// tcgen05.mma (M = 256) issued by the pair's leader multiplies both A' tiles with a B' k-step of which each CTA holds
+// half (48 of the 96 rows): half the shared-memory fill per SM and chunk, half the B operand reads, half the MMA issues.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {   // same barrier, CTA `cta` of the cluster
+    uint32_t raddr;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(bar)), "r"(cta));
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+constexpr uint32_t kLeaderMask = 0xFEFFFFFFu;    // clears the CTA-rank bit of a shared-memory address: the pair's CTA 0
+// tensor-map load into THIS CTA's shared memory whose bytes are counted on the LEADER's mbarrier (same offset)
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kLeaderMask), "r"(c0), "r"(c1)
+        : "memory");
+}
+// arrives on the barrier at this offset in BOTH CTAs of the pair once every MMA issued so far has retired
+__device__ __forceinline__ void tcgen05_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t* r) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -111,8 +145,20 @@ __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" :
 __host__ __device__ constexpr uint32_t a_step_off(int a) { return (uint32_t)((a >> 2) * (kAChunkBytes >> 4) + (a & 3) * 2); }
 // kind::f16 MMA with the two shared-memory descriptors given as (low word, common high word):
 // all tiles here share SBO / version / swizzle, only the 14-bit start address differs.
+template <int kPair>
 __device__ __forceinline__ void umma_bf16_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc,
                                                bool accumulate) {
+    if (kPair == 2) {
+        const uint32_t acc = accumulate ? 1u : 0u;
+        asm volatile(
+            "{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\t"
+            "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+            "setp.ne.b32 p, %5, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}"
+            ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(acc)
+            : "memory");
+        return;
+    }
     if (accumulate)
         asm volatile(
             "{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\t"
@@ -182,9 +228,11 @@ __device__ __forceinline__ bool elect_one() {
 // kGroups: weight groups of 4 per vertex known at compile time (1 = SMPL), 0 = run-time `groups`
 #define GATHER_ADDR(col) (col)                 // the table holds absolute tensor-memory addresses
 
-template <int kGroups>
+// kPair = 2: CTA pairs (see above); n_units then counts pair units: (two consecutive frame tiles) x vertex tile
+template <int kGroups, int kPair>
 __global__ void __launch_bounds__(kThreads, 1)
-fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const uint16_t* __restrict__ B2img,
+fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid_constant__ CUtensorMap tmap_B,
+                        const uint16_t* __restrict__ B2img,
                         const float* __restrict__ AskinT, const float* __restrict__ off,
                         const uint8_t* __restrict__ wpack, int groups_rt, int stages, int64_t B, int64_t n_units,
                         float* __restrict__ verts, int dbg) {
@@ -195,17 +243,19 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const uint16
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* sA = smem;                                           // [8 chunks][128 rows][128 B], 128B swizzle
     uint8_t* sB = sA + kABytes;                                   // [stages][96 rows][128 B]
-    uint8_t* sOut = sB + stages * kBChunkBytes;                   // [16 warps][32 frames][12 floats]
+    constexpr int kBSlotBytes = kBChunkBytes / kPair;             // a CTA of a pair holds 48 of a chunk's 96 rows
+    uint8_t* sOut = sB + stages * kBSlotBytes;                   // [16 warps][32 frames][12 floats]
     uint8_t* sW = sOut + kOutBytes;                               // [4 slots][groups][32 x float4 weights | 32 x uint4 columns]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sW + kWSlots * groups * FUSED_WGROUP_BYTES);
+    constexpr int kWS = w_slots(kPair), kWShift = w_shift(kPair);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sW + kWS * groups * FUSED_WGROUP_BYTES);
     uint64_t* full_bar = bars;                                    // [kMaxStages]
     uint64_t* empty_bar = bars + kMaxStages;                      // [kMaxStages]
     // one "accumulator full" barrier PER EPILOGUE WARP: warps parked on a common mbarrier are woken
     // one after the other (~2.5 us per unit for 16 waiters), a private barrier wakes at once
     uint64_t* tfull_bar = bars + 2 * kMaxStages;                  // [2 accumulators][kEpiWarps]
     uint64_t* tempty_bar = tfull_bar + 2 * kEpiWarps;             // [2]
-    uint64_t* wfull_bar = tempty_bar + 2;                         // [kWSlots]
-    uint64_t* afull_bar = wfull_bar + kWSlots;
+    uint64_t* wfull_bar = tempty_bar + 2;                         // [kWSlotsMax]
+    uint64_t* afull_bar = wfull_bar + kWSlotsMax;
     uint64_t* aempty_bar = afull_bar + 1;
     // staging tile of a lane quarter: "staged" (all four warps wrote half h) / "flushed" (all four read it back);
     // arrive and wait are far apart in the instruction stream, so the four warps need not run in lock-step
@@ -224,21 +274,27 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const uint16
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_A)) : "memory");
         for (int i = 0; i < kMaxStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
         for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&tfull_bar[i], 1);
-        for (int i = 0; i < 2; ++i) mbar_init(&tempty_bar[i], kEpiWarps);
-        for (int i = 0; i < kWSlots; ++i) mbar_init(&wfull_bar[i], 1);
+        for (int i = 0; i < 2; ++i) mbar_init(&tempty_bar[i], kEpiWarps * kPair);   // pair: both CTAs' epilogue warps arrive on the leader's
+        for (int i = 0; i < kWSlotsMax; ++i) mbar_init(&wfull_bar[i], 1);
         mbar_init(afull_bar, 1);
         mbar_init(aempty_bar, 1);
         for (int i = 0; i < 4; ++i) { mbar_init(&qstaged_bar[i], 4); mbar_init(&qflushed_bar[i], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kEpiWarps + 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)),
-                     "r"(kTmemCols)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (kPair == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)),
+                         "r"(kTmemCols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)),
+                         "r"(kTmemCols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tcgen05_fence_before();
     __syncthreads();
+    if (kPair == 2) cluster_sync_all();         // both CTAs' barriers exist before the peer's copies / arrives reach them
     tcgen05_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_holder, 0);
     // everything above ran while the previous kernel of the stream (the pose chain) was still draining; its
@@ -246,12 +302,16 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const uint16
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (tmem_base != 0) __trap();              // all 512 columns are ours: the allocation can only start at 0
 
-    // contiguous unit range of this CTA; unit u = frame tile (u / 216), vertex tile (u % 216)
-    const int64_t u0 = (int64_t)blockIdx.x * n_units / gridDim.x;
-    const int64_t u1 = (int64_t)(blockIdx.x + 1) * n_units / gridDim.x;
+    // contiguous unit range of this CTA (pair); unit u = frame tile (pair of frame tiles) u / 216, vertex tile u % 216.
+    // CTA `crank` of a pair takes frame tile 2 * (u / 216) + crank; a tile beyond the batch computes on zero rows (the
+    // tensor map fills them) and stores nothing
+    const int crank = kPair == 2 ? (int)cluster_ctarank() : 0;
+    const int64_t cid = blockIdx.x / kPair, ncl = gridDim.x / kPair;
+    const int64_t u0 = cid * n_units / ncl;
+    const int64_t u1 = (cid + 1) * n_units / ncl;
     const int n_my = (int)(u1 - u0);
-    const int64_t ft0 = u0 / FUSED_NT;
-    const int vt0 = (int)(u0 - ft0 * FUSED_NT);
+    const int64_t ft0 = (u0 / FUSED_NT) * kPair + crank;
+    const int vt0 = (int)(u0 - (u0 / FUSED_NT) * FUSED_NT);
 
     if (warp == kEpiWarps) {
         // ===== TMA producer (whole warp converged, one elected lane issues) =====
@@ -263,26 +323,39 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const uint16
                 // the MMAs of the previous frame tile still read the resident A' tile
                 if (n_ft > 0) MBAR_WAIT(aempty_bar, (n_ft - 1) & 1);
                 if (elect_one()) {
-                    mbar_expect_tx(afull_bar, kABytes);
-                    for (int c = 0; c < FUSED_A_CHUNKS; ++c)
-                        tma_load_2d(&tmap_A, afull_bar, sA + c * kAChunkBytes, c * 64, (int)(ft * FUSED_BM));
+                    if (kPair == 2) {       // both CTAs' tiles are counted on the leader's barrier (the leader issues the MMAs)
+                        if (crank == 0) mbar_expect_tx(afull_bar, 2 * kABytes);
+                        for (int c = 0; c < FUSED_A_CHUNKS; ++c)
+                            tma_load_2d_pair(&tmap_A, afull_bar, sA + c * kAChunkBytes, c * 64, (int)(ft * FUSED_BM));
+                    } else {
+                        mbar_expect_tx(afull_bar, kABytes);
+                        for (int c = 0; c < FUSED_A_CHUNKS; ++c)
+                            tma_load_2d(&tmap_A, afull_bar, sA + c * kAChunkBytes, c * 64, (int)(ft * FUSED_BM));
+                    }
                 }
                 ++n_ft;
             }
-            // skinning weights of the tile's 32 vertices.  Slot i&3 was last read by unit i-4;
-            // the ring is shorter than one unit, so the chunk loads of unit i-1 already issued
-            // imply the MMA of unit i-1 has started, i.e. every epilogue warp finished unit i-3.
+            // skinning weights of the tile's 32 vertices.  Slot i % kWS was last read by unit i - kWS.  kWS = 4: the ring is
+            // shorter than one unit, so the chunk loads of unit i-1 already issued imply the MMA of unit i-1 has started,
+            // i.e. every epilogue warp finished unit i-3.  CTA pairs: the ring holds 1.25 units, the MMA of unit i-2 has
+            // started, every epilogue warp has passed the middle of unit i-4: hence kWS = 8 there (4 slots were a race).
             const uint32_t wbytes = (uint32_t)groups * FUSED_WGROUP_BYTES;
             if (elect_one()) {
-                uint64_t* wb = &wfull_bar[i & (kWSlots - 1)];
+                uint64_t* wb = &wfull_bar[i & (kWS - 1)];
                 mbar_expect_tx(wb, wbytes);
-                bulk_load_1d(sW + (i & (kWSlots - 1)) * wbytes, wpack + (size_t)vt * wbytes, wbytes, wb);
+                bulk_load_1d(sW + (i & (kWS - 1)) * wbytes, wpack + (size_t)vt * wbytes, wbytes, wb);
             }
 #pragma unroll 1
             for (int c = 0; c < FUSED_B_CHUNKS; ++c) {
                 MBAR_WAIT(&empty_bar[stage], phase ^ 1);
                 if (elect_one()) {
-                    if (DBG(16)) { mbar_arrive(&full_bar[stage]); }
+                    if (kPair == 2) {
+                        // this CTA's 48 rows of the chunk image (the swizzle phase of a row only depends on row & 7, and
+                        // 48 is a multiple of 8); both halves are counted on the leader's barrier
+                        if (crank == 0) mbar_expect_tx(&full_bar[stage], kBChunkBytes);
+                        tma_load_2d_pair(&tmap_B, &full_bar[stage], sB + stage * kBSlotBytes, 0,
+                                         (vt * FUSED_B_CHUNKS + c) * FUSED_BN + crank * (FUSED_BN / 2));
+                    } else if (DBG(16)) { mbar_arrive(&full_bar[stage]); }
                     else {
                         // one contiguous 12 KB block of the pre-swizzled B' image (prk_internal.h fused_b2_index)
                         mbar_expect_tx(&full_bar[stage], kBChunkBytes);
@@ -292,13 +365,15 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const uint16
                 }
                 if (++stage == stages) { stage = 0; phase ^= 1; }
             }
-            if (++vt == FUSED_NT) { vt = 0; ++ft; }
+            if (++vt == FUSED_NT) { vt = 0; ft += kPair; }
         }
+    } else if (warp == kEpiWarps + 1 && kPair == 2 && crank != 0) {
+        // (the pair's MMAs are issued by the leader CTA)
     } else if (warp == kEpiWarps + 1) {
         // ===== MMA issuer (whole warp converged, one elected lane issues) =====
         // Everything about a k-step is a compile-time constant (both loops fully unrolled) and every
         // run-time operand is warp-uniform, so an MMA costs a couple of uniform adds plus the issue.
-        constexpr uint32_t idesc = make_idesc(FUSED_BM, FUSED_BN);
+        constexpr uint32_t idesc = make_idesc(FUSED_BM * kPair, FUSED_BN);
         const uint64_t adesc0 = make_smem_desc(smem_u32(sA));
         const uint32_t a_lo = (uint32_t)adesc0, d_hi = (uint32_t)(adesc0 >> 32);
         const uint32_t b_lo0 = (uint32_t)make_smem_desc(smem_u32(sB));
@@ -307,7 +382,7 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const uint16
         uint32_t n_ft = 0;
         for (int i = 0; i < n_my; ++i) {
             if (i == 0 || vt == 0) {
-                if (n_ft > 0 && elect_one()) tcgen05_commit(aempty_bar);   // all MMAs on the old A' tile retire first
+                if (n_ft > 0 && elect_one()) { if (kPair == 2) tcgen05_commit_pair(aempty_bar); else tcgen05_commit(aempty_bar); }   // all MMAs on the old A' tile retire first
                 MBAR_WAIT(afull_bar, n_ft & 1);
                 tcgen05_fence_after();
                 ++n_ft;
@@ -315,7 +390,7 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const uint16
             const int acc = i & 1;
             // the tile's skinning weights: waited for here (single waiter) so the epilogue warps,
             // which see them through their tfull barrier, never park on the TMA barrier
-            MBAR_WAIT(&wfull_bar[i & (kWSlots - 1)], (i >> 2) & 1);
+            MBAR_WAIT(&wfull_bar[i & (kWS - 1)], (i >> kWShift) & 1);
             MBAR_WAIT(&tempty_bar[acc], ((i >> 1) & 1) ^ 1);       // epilogue drained this accumulator
             tcgen05_fence_after();
             const uint32_t d_tmem = tmem_base + kAccCol0 + (uint32_t)acc * FUSED_BN;
@@ -323,28 +398,36 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const uint16
             for (int c = 0; c < FUSED_B_CHUNKS; ++c) {
                 MBAR_WAIT(&full_bar[stage], phase);
                 tcgen05_fence_after();
-                const uint32_t b_lo = b_lo0 + (uint32_t)stage * (kBChunkBytes >> 4);
+                const uint32_t b_lo = b_lo0 + (uint32_t)stage * (kBSlotBytes >> 4);
                 if (elect_one()) {
 #pragma unroll
                     for (int s = 0; s < (DBG(1) ? 0 : 4); ++s) {
                         const int b = c * 4 + s;                  // B' k-step (compile-time)
                         const uint32_t bl = b_lo + 2 * s;
                         if (b < FUSED_POSE_STEPS) {               // posedirs hi: x pose hi, x pose lo
-                            umma_bf16_lohi(d_tmem, a_lo + a_step_off(b), bl, d_hi, idesc, b != 0);
-                            umma_bf16_lohi(d_tmem, a_lo + a_step_off(FUSED_POSE_STEPS + b), bl, d_hi, idesc, true);
+                            umma_bf16_lohi<kPair>(d_tmem, a_lo + a_step_off(b), bl, d_hi, idesc, b != 0);
+                            umma_bf16_lohi<kPair>(d_tmem, a_lo + a_step_off(FUSED_POSE_STEPS + b), bl, d_hi, idesc, true);
                         } else if (b < 2 * FUSED_POSE_STEPS) {    // posedirs lo: x pose hi
-                            umma_bf16_lohi(d_tmem, a_lo + a_step_off(b - FUSED_POSE_STEPS), bl, d_hi, idesc, true);
+                            umma_bf16_lohi<kPair>(d_tmem, a_lo + a_step_off(b - FUSED_POSE_STEPS), bl, d_hi, idesc, true);
                         } else if (b < FUSED_B_STEPS) {           // the five beta x shapedirs (+ template) products
                             constexpr int A26 = 2 * FUSED_POSE_STEPS, A27 = A26 + 1;
                             const int q = b - 2 * FUSED_POSE_STEPS;      // 0: s1|s1a|t1  1: s1|s1b  2: s2|t2  3: s3|t3
-                            if (q != 1) umma_bf16_lohi(d_tmem, a_lo + a_step_off(A26), bl, d_hi, idesc, true);
-                            if (q == 1 || q == 2) umma_bf16_lohi(d_tmem, a_lo + a_step_off(A27), bl, d_hi, idesc, true);
+                            if (q != 1) umma_bf16_lohi<kPair>(d_tmem, a_lo + a_step_off(A26), bl, d_hi, idesc, true);
+                            if (q == 1 || q == 2) umma_bf16_lohi<kPair>(d_tmem, a_lo + a_step_off(A27), bl, d_hi, idesc, true);
                         }
                     }
-                    tcgen05_commit(&empty_bar[stage]);            // frees the ring slot when the MMAs retire
-                    if (c == FUSED_B_CHUNKS - 1) {
+                    if (kPair == 2) {
+                        tcgen05_commit_pair(&empty_bar[stage]);   // frees the ring slot in both CTAs when the MMAs retire
+                        if (c == FUSED_B_CHUNKS - 1) {
 #pragma unroll
-                        for (int w = 0; w < kEpiWarps; ++w) tcgen05_commit(&tfull_bar[acc * kEpiWarps + w]);
+                            for (int w = 0; w < kEpiWarps; ++w) tcgen05_commit_pair(&tfull_bar[acc * kEpiWarps + w]);
+                        }
+                    } else {
+                        tcgen05_commit(&empty_bar[stage]);        // frees the ring slot when the MMAs retire
+                        if (c == FUSED_B_CHUNKS - 1) {
+#pragma unroll
+                            for (int w = 0; w < kEpiWarps; ++w) tcgen05_commit(&tfull_bar[acc * kEpiWarps + w]);
+                        }
                     }
                 }
                 if (++stage == stages) { stage = 0; phase ^= 1; }
@@ -408,7 +491,8 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const uint16
                 for (int b = 0; b < 3; ++b) {
                     uint32_t v[24];
 #pragma unroll
-                    for (int k = 0; k < 24; ++k) v[k] = __float_as_uint(__ldg(src + (b * 24 + k) * 32));
+                    for (int k = 0; k < 24; ++k)
+                        v[k] = (kPair == 1 || ft * FUSED_BM < B) ? __float_as_uint(__ldg(src + (b * 24 + k) * 32)) : 0u;   // no A_j tile beyond the batch
 #pragma unroll
                     for (int c = 0; c < 3; ++c) tmem_st_x8(t_lane + (uint32_t)(oct * 72 + b * 24 + c * 8), v + c * 8);
                 }
@@ -420,19 +504,19 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const uint16
             }
             const int acc = i & 1;
             const uint32_t wbytes = (uint32_t)groups * FUSED_WGROUP_BYTES;
-            const uint8_t* wslot = sW + (i & (kWSlots - 1)) * wbytes;
+            const uint8_t* wslot = sW + (i & (kWS - 1)) * wbytes;
             TCLK(tw0);
             MBAR_WAIT(&tfull_bar[acc * kEpiWarps + warp], (i >> 1) & 1);
             tcgen05_fence_after();
             TCLK(tw1);
-            MBAR_WAIT(&wfull_bar[i & (kWSlots - 1)], (i >> 2) & 1);   // completed before the MMAs were issued: never parks
+            MBAR_WAIT(&wfull_bar[i & (kWS - 1)], (i >> kWShift) & 1);   // completed before the MMAs were issued: never parks
             TCLK(tw2);
             TACC(0, tw0, tw1); TACC(1, tw1, tw2);
             if (DBG(2)) {
                 tcgen05_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-                if (++vt == FUSED_NT) { vt = 0; ++ft; }
+                if (lane == 0) { if (kPair == 2 && crank != 0) mbar_arrive_remote(&tempty_bar[acc], 0); else mbar_arrive(&tempty_bar[acc]); }
+                if (++vt == FUSED_NT) { vt = 0; ft += kPair; }
                 continue;
             }
             const uint32_t t_acc = t_lane + kAccCol0 + (uint32_t)acc * FUSED_BN + (uint32_t)(oct * 12);
@@ -521,7 +605,7 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const uint16
                         if (n == 16) {                                // ... and so have the second half's v_posed columns
                             tcgen05_fence_before();
                             __syncwarp();
-                            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                            if (lane == 0) { if (kPair == 2 && crank != 0) mbar_arrive_remote(&tempty_bar[acc], 0); else mbar_arrive(&tempty_bar[acc]); }
                         }
                         if (q == 0) {
                             const uint32_t* pk = p + (k & 3) * 3;
@@ -632,12 +716,12 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const uint16
                         // both halves' accumulator columns are in registers: hand the buffer back to the MMA warp
                         tcgen05_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                        if (lane == 0) { if (kPair == 2 && crank != 0) mbar_arrive_remote(&tempty_bar[acc], 0); else mbar_arrive(&tempty_bar[acc]); }
                     }
                     store_half(res, half);
                 }
             }
-            if (++vt == FUSED_NT) { vt = 0; ++ft; }
+            if (++vt == FUSED_NT) { vt = 0; ft += kPair; }
         }
         flush_pending();
 #ifdef PRK_FUSED_DEBUG
@@ -651,9 +735,11 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const uint16
 
     tcgen05_fence_before();
     __syncthreads();
+    if (kPair == 2) cluster_sync_all();         // neither CTA leaves (or frees tensor memory) while the pair's MMAs, copies or arrives may still touch it
     if (warp == kEpiWarps + 1) {
         tcgen05_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+        if (kPair == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
     }
 }
 
@@ -720,59 +806,96 @@ extern "C" __attribute__((visibility("default"))) int prk_fused_debug_read(unsig
 }
 #endif
 
-int fused_stages(int groups) {
-    int stages = kMaxStages;
+int fused_stages(int groups, int pair) {
+    int stages = pair == 2 ? 10 : 6;            // 10 half chunks (60 KB) + 8 weight slots, or 6 chunks (72 KB) + 4 slots
 #ifdef PRK_STAGE_CAP
-    stages = PRK_STAGE_CAP;
+    stages = PRK_STAGE_CAP * pair;
 #endif
-    while (stages > 2 && fused_smem_bytes(stages, groups) > kSmemLimit) --stages;
+    while (stages > 2 && fused_smem_bytes(stages, groups, pair) > kSmemLimit) --stages;
     return stages;
+}
+
+// CTA pairs: PRK_PAIR=1|2 overrides; default PRK_PAIR_DEFAULT when the batch has at least two frame tiles
+#ifndef PRK_PAIR_DEFAULT
+#define PRK_PAIR_DEFAULT 2
+#endif
+static int fused_pair(int64_t n_ft) {
+    static const int forced = [] { const char* e = getenv("PRK_PAIR"); return e ? atoi(e) : 0; }();
+    const int p = forced > 0 ? forced : PRK_PAIR_DEFAULT;
+    return (p == 2 && n_ft >= 2) ? 2 : 1;
+}
+
+template <int kGroups, int kPair>
+static cudaError_t launch_fused_t(const Model& m, const CUtensorMap& tmap_A, int64_t rows_pad, const float* d_AskinT,
+                                  const float* d_off, int64_t B, float* d_verts, cudaStream_t s, bool pdl) {
+    auto kern = fused_blend_skin_kernel<kGroups, kPair>;
+    const int groups = m.nnz_groups;
+    const int stages = fused_stages(groups, kPair);
+    const int smem = fused_smem_bytes(stages, groups, kPair);
+    if (smem > kSmemLimit) return cudaErrorInvalidConfiguration;
+    static std::atomic<int> attr_set[64];       // per device: dynamic shared memory this instantiation was opted in for
+    if (m.device >= 0 && m.device < 64 && attr_set[m.device].load(std::memory_order_acquire) < smem) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        attr_set[m.device].store(smem, std::memory_order_release);
+    }
+    const int64_t n_ft = rows_pad / FUSED_BM;
+    const int64_t n_units = ((n_ft + kPair - 1) / kPair) * FUSED_NT;          // (pair) units
+    int grid = m.sm_count > 0 ? m.sm_count : 148;
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (kPair == 2) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+        ++na;
+        static std::atomic<int> max_clusters[64];     // one CTA per SM: as many pairs as the GPU holds at once
+        int mc = (m.device >= 0 && m.device < 64) ? max_clusters[m.device].load(std::memory_order_acquire) : 0;
+        if (mc == 0) {
+            cfg.gridDim = dim3((unsigned)(grid / 2 * 2));
+            cfg.attrs = attr; cfg.numAttrs = na;
+            cudaError_t e = cudaOccupancyMaxActiveClusters(&mc, kern, &cfg);
+            if (e != cudaSuccess) return e;
+            if (mc < 1) return cudaErrorInvalidConfiguration;
+            if (m.device >= 0 && m.device < 64) max_clusters[m.device].store(mc, std::memory_order_release);
+        }
+        if (grid > mc * 2) grid = mc * 2;
+        grid = grid / 2 * 2;
+        if ((int64_t)grid / 2 > n_units) grid = (int)n_units * 2;
+    } else if (grid > n_units) {
+        grid = (int)n_units;
+    }
+    // Programmatic dependent launch: the CTAs become resident and run their prologue (barrier init, tensor-memory
+    // allocation, descriptor prefetch) while the pose-chain kernel in front of them drains; every thread passes
+    // griddepcontrol.wait before it touches that kernel's outputs.  PRK_PDL=0 launches without the attribute.
+    if (pdl) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    const uint8_t* wpack = m.d_wpack;
+    const uint16_t* b2img = m.d_B2;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmap_A, m.tmap_B2, b2img, d_AskinT, d_off, wpack, groups, stages, B, n_units,
+                                       d_verts, 0);
+    count_launch();
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 cudaError_t launch_fused(const Model& m, const CUtensorMap& tmap_A, int64_t rows_pad, const float* d_AskinT,
                          const float* d_off, int64_t B, float* d_verts, cudaStream_t s) {
     if (B == 0) return cudaSuccess;
-    const int groups = m.nnz_groups;
-    const int stages = fused_stages(groups);
-    const int smem = fused_smem_bytes(stages, groups);
-    if (smem > kSmemLimit) return cudaErrorInvalidConfiguration;
-    static std::atomic<int> attr_set[64];       // per device: dynamic shared memory the kernels were opted in for
-    if (m.device >= 0 && m.device < 64 && attr_set[m.device].load(std::memory_order_acquire) < smem) {
-        cudaError_t e = cudaFuncSetAttribute(fused_blend_skin_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(fused_blend_skin_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        attr_set[m.device].store(smem, std::memory_order_release);
-    }
-    const int dbg = 0;
-    const int64_t n_units = (rows_pad / FUSED_BM) * FUSED_NT;
-    int grid = m.sm_count > 0 ? m.sm_count : 148;
-    if (grid > n_units) grid = (int)n_units;
-    // Programmatic dependent launch: the CTAs become resident and run their prologue (barrier init, tensor-memory
-    // allocation, descriptor prefetch) while the pose-chain kernel in front of them drains; every thread passes
-    // griddepcontrol.wait before it touches that kernel's outputs.  PRK_PDL=0 launches without the attribute.
     static const bool pdl = [] { const char* e = getenv("PRK_PDL"); return !e || atoi(e) != 0; }();
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = (size_t)smem;
-    cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = pdl ? 1 : 0;
-    const uint8_t* wpack = m.d_wpack;
-    const uint16_t* b2img = m.d_B2;
-    cudaError_t e;
-    if (groups == 1)
-        e = cudaLaunchKernelEx(&cfg, fused_blend_skin_kernel<1>, tmap_A, b2img, d_AskinT, d_off, wpack, groups, stages, B,
-                               n_units, d_verts, dbg);
-    else
-        e = cudaLaunchKernelEx(&cfg, fused_blend_skin_kernel<0>, tmap_A, b2img, d_AskinT, d_off, wpack, groups, stages, B,
-                               n_units, d_verts, dbg);
-    count_launch();
-    return e != cudaSuccess ? e : cudaGetLastError();
+    const int pair = fused_pair(rows_pad / FUSED_BM);
+#define PRK_GO(G, P) launch_fused_t<G, P>(m, tmap_A, rows_pad, d_AskinT, d_off, B, d_verts, s, pdl)
+    if (m.nnz_groups == 1) return pair == 2 ? PRK_GO(1, 2) : PRK_GO(1, 1);
+    return pair == 2 ? PRK_GO(0, 2) : PRK_GO(0, 1);
+#undef PRK_GO
 }
 
 }  // namespace prk

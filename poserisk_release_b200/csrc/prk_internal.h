@@ -84,6 +84,7 @@ struct prk_model {
     // contiguous 12 KB block with the 128-byte swizzle already applied (16-byte unit j of row r sits at j ^ (r & 7)),
     // so a chunk is fetched with ONE linear bulk copy instead of a 96-row tensor box (fused_b2_index)
     uint16_t* d_B2 = nullptr;
+    CUtensorMap tmap_B2;           // the same image as [tiles x chunks x 96 rows][64 bf16], boxes of 48 rows (CTA pairs load halves)
     uint8_t* d_wpack = nullptr;    // [FUSED_NT][nnz_groups][FUSED_WGROUP_BYTES] per-tile skinning weights
     // scoring only reads the pose: it runs on its own stream beside the mesh path
     cudaStream_t s_score = nullptr;

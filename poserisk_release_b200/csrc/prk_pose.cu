@@ -289,7 +289,10 @@ __device__ __constant__ int8_t c_depth[32] = {0, 1, 1, 1, 2, 2, 2, 3, 3, 3, 4, 4
 __device__ __constant__ int8_t c_dfs_pos[32] = {0, 1, 5, 9, 2, 6, 10, 3, 7, 11, 4, 8, 12, 14, 19, 13, 15, 20, 16, 21, 17, 22, 18, 23,
                                                 0, 0, 0, 0, 0, 0, 0, 0};
 constexpr int kWarpsPerBlock = 8;        // joints-only variant
-constexpr int kWarpsPerBlockMesh = 16;   // full-mesh variant: 16 consecutive frames per block, so that the block
+#ifndef PRK_CHAIN_WPB
+#define PRK_CHAIN_WPB 16
+#endif
+constexpr int kWarpsPerBlockMesh = PRK_CHAIN_WPB;   // full-mesh variant: 16 consecutive frames per block, so that the block
                                          // writes its AskinT columns as 64-byte runs (two full sectors) instead of
                                          // 288 scattered 4-byte stores per frame
 constexpr int64_t kWarpVariantMaxFrames = 65536;   // above this the thread-per-frame kernel fills the GPU

@@ -52,6 +52,8 @@ def config_dict(n_gpus):
             "frames_per_step_per_gpu": FRAMES_PER_STEP, "parallelism": f"frames sharded x{n_gpus}, replicated model"
             + (", all-gather of the 32 B/frame score records every step (peer-memory stores over NVLink issued under the "
                "vertex kernel; NCCL when CUDA IPC is unavailable -- see config.exchange)" if n_gpus > 1 else ""),
+            "verts_layout": "(B, 6890, 3) float32 view over rows padded to 16 bytes (pitch 20672 floats), stored by bulk tensor (TMA) "
+                            "stores; dense_layout in this line = the same steps into the reference's contiguous tensor",
             "l2": "8 distinct input batches in rotation; every step writes 339 MB of vertices (> 126 MB L2), "
                   "so no input or output line survives in L2 between steps; the 21 MB bf16 blend matrix is "
                   "meant to stay L2-resident"}
@@ -336,7 +338,10 @@ def run_gpu_arm(args):
     dev_in = [tuple(t.to(dev) for t in make_inputs(1000 * rank + i, B)) for i in range(n_rot)]
     host_in = [tuple(t.pin_memory() for t in make_inputs(1000 * rank + i, B)) for i in range(n_rot)]
     info_dev = _runtime.addinfo_tensor(EXAMPLE_INFO, dev)
-    verts = torch.empty((B, 6890, 3), dtype=torch.float32, device=dev)
+    # vertex rows padded to 16 bytes (pitch 20672 floats): the layout the vertex kernel stores with bulk tensor (TMA) stores;
+    # same shape, values and indexing as the reference's dense (B, 6890, 3) tensor, which is timed beside it (dense_layout)
+    verts_flat = torch.empty((B, _lib.VERTS_PITCH_ALIGNED), dtype=torch.float32, device=dev)
+    verts = verts_flat[:, :20670].view(B, 6890, 3)
     d_joints = torch.empty((B, 24, 3), dtype=torch.float32, device=dev)
     d_scores = torch.empty((B, 32), dtype=torch.uint8, device=dev)
     h_joints = torch.empty((B, 24, 3), dtype=torch.float32).pin_memory()
@@ -430,11 +435,11 @@ def run_gpu_arm(args):
     # labelled figure -- the reference only ever reads one frame's vertices, for a debug .obj (base.py:273-282)
     e2e_verts = None
     if not args.skip_extra:
-        h_verts = torch.empty((B, 6890, 3), dtype=torch.float32).pin_memory()
+        h_verts = torch.empty((B, _lib.VERTS_PITCH_ALIGNED), dtype=torch.float32).pin_memory()   # same padded rows on the host
 
         def step_host_verts(i):
             step_host(i)
-            h_verts.copy_(verts, non_blocking=True)
+            h_verts.copy_(verts_flat, non_blocking=True)
         kv = min(K, 10)
         step_host_verts(0)
         ms_v = float(np.median([timed(step_host_verts, kv) for _ in range(3)]))
@@ -445,9 +450,31 @@ def run_gpu_arm(args):
                              "what a host-to-host full-mesh caller gets; bound by the PCIe link, not by the kernels"}
         del h_verts
 
+    # the same K steps into the reference's DENSE (B, 6890, 3) layout (82,680-byte rows: every second row starts 8 bytes off a
+    # 16-byte boundary, so the vertices leave through a shared staging tile + 8-byte stores instead of bulk tensor stores)
+    dense = None
+    if not args.skip_extra:
+        verts_dense = torch.empty((B, 6890, 3), dtype=torch.float32, device=dev)
+
+        def step_dense(i):
+            p, b, t = dev_in[i % n_rot]
+            eng.run(p, b, t, add_info=info_dev, verts_out=verts_dense, joints_out=d_joints, scores_out=d_scores)
+        for i in range(3):
+            step_dense(i)
+        ms_d = float(np.median([timed(step_dense, K) for _ in range(3)]))
+        _lib.check(L.prk_profile_begin())
+        timed(step_dense, K)
+        st_d = (np.zeros(4), np.zeros(4, np.int64))
+        _lib.check(L.prk_profile_end(st_d[0].ctypes.data, st_d[1].ctypes.data))
+        dense = {"value": B * world * K / (ms_d * 1e-3), "unit": UNIT, "ms_per_step": ms_d / K,
+                 "fused_ms_per_launch": float(st_d[0][1] / max(st_d[1][1], 1)),
+                 "hbm_frac": FUSED_BYTES_PER_FRAME * B / (float(st_d[0][1] / max(st_d[1][1], 1)) * 1e-3) / 1e9 / load_peaks()['hbm_gbs'],
+                 "note": "vertices into a contiguous (B, 6890, 3) tensor, the reference's layout (no collective in these steps)"}
+        del verts_dense
+
     extra = {}
     if not args.skip_extra:
-        del verts
+        del verts, verts_flat
         torch.cuda.empty_cache()
         extra = run_extra_configs(eng, dev, rank, world, args.transport, barrier)
 
@@ -513,7 +540,7 @@ def run_gpu_arm(args):
                                 "memory every step; the 339 MB of vertices a step produces STAY IN HBM (SMPL_Layer returns "
                                 "tensors on the input's device and the reference reads vertices only for a debug .obj) -- "
                                 "see e2e_with_verts for the host-to-host full-mesh rate, which is PCIe bound"},
-                "e2e_with_verts": e2e_verts,
+                "e2e_with_verts": e2e_verts, "dense_layout": dense,
                 "gpu_launches": int(launches), "per_rank_ms_per_step": per_rank,
                 "roofline": dominant, "roofline_other": other, "stages": per_stage,
                 "cpu_baseline": cpu_baseline, "parity": parity}
@@ -556,7 +583,7 @@ def run_extra_configs(eng, dev, rank, world, transport, barrier):
     n3 = CONFIG3_FRAMES
     lo, hi = shard_range(n3, rank, world)
     pose, betas, trans = counter_inputs(lo, hi, dev)
-    verts3 = torch.empty((hi - lo, 6890, 3), dtype=torch.float32, device=dev)
+    verts3 = _runtime.aligned_verts(hi - lo, dev)
     joints3 = torch.empty((hi - lo, 24, 3), dtype=torch.float32, device=dev)
     scores3 = torch.empty((hi - lo, 32), dtype=torch.uint8, device=dev)
     ex3 = ScoreExchange(n3, dev, 0, None, transport)
@@ -624,7 +651,7 @@ def run_extra_configs(eng, dev, rank, world, transport, barrier):
         h = eng.models['neutral']
         ws, ws_bytes, _keep = _runtime.workspace.get(dev, h.workspace_bytes(hi - lo, True))
         _lib.check(_lib.lib().prk_smpl_forward(h.handle, _runtime.ptr(pose), _runtime.ptr(betas), _runtime.ptr(trans), -1,
-                                               hi - lo, None, _runtime.ptr(joints5), ws, ws_bytes, _runtime.stream_ptr(dev)))
+                                               hi - lo, None, 0, _runtime.ptr(joints5), ws, ws_bytes, _runtime.stream_ptr(dev)))
     def only_score():
         eng.euler_debug(pose, DEBUG_JOINTS, info_dev)
     only_chain(); only_score()
@@ -669,7 +696,7 @@ def run_extra_configs(eng, dev, rank, world, transport, barrier):
     pose, betas, trans = counter_inputs(f0, f1, dev)
     track_local = np.repeat(np.arange(t0, t1), F).astype(np.int32)
     info4 = _runtime.addinfo_tensor(infos, dev)
-    verts4 = torch.empty((f1 - f0, 6890, 3), dtype=torch.float32, device=dev)
+    verts4 = _runtime.aligned_verts(f1 - f0, dev)
     joints4 = torch.empty((f1 - f0, 24, 3), dtype=torch.float32, device=dev)
     scores4 = torch.empty((f1 - f0, 32), dtype=torch.uint8, device=dev)
     ex4 = ScoreExchange(n4, dev, 0, None, transport)

@@ -126,10 +126,14 @@ size_t prk_workspace_bytes(const prk_model* model, int64_t B, uint32_t flags);
  *           `center_idx` joint is subtracted when center_idx >= 0 (:148-152)
  *   center_idx  -1 = None
  *   d_verts [B*6890*3] float32, or NULL for the joints-only path
+ *   verts_pitch  floats from one frame's vertices to the next: 0 or 20670 = the reference's dense (B, 6890, 3)
+ *           layout; a multiple of 4 >= 20670 (e.g. PRK_VERTS_PITCH_ALIGNED = 20672) with a 16-byte aligned d_verts
+ *           = 16-byte aligned rows, which leave through bulk tensor stores (faster; models with <= 4 weights per vertex)
  *   d_joints[B*24*3]  float32 (chain translations, :145)
  * Both whole-batch tests are evaluated on the device (no host sync). */
+#define PRK_VERTS_PITCH_ALIGNED 20672
 int prk_smpl_forward(prk_model* model, const float* d_pose, const float* d_betas,
-                     const float* d_trans, int center_idx, int64_t B, float* d_verts,
+                     const float* d_trans, int center_idx, int64_t B, float* d_verts, int64_t verts_pitch,
                      float* d_joints, void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* axis_angle_to_euler_angle (lib/utils/coord_utils.py:83-95) + REBA.__call__ /
@@ -177,7 +181,7 @@ int prk_rot_to_angle(const void* d_rotmat, int dtype, int64_t n_rot, void* d_rve
  * All arguments and the workspace size are checked before anything is launched. */
 int prk_pipeline(prk_model* model, const float* d_pose, const float* d_betas,
                  const float* d_trans, int center_idx, const prk_addinfo* d_info, int32_t n_tracks,
-                 const int32_t* d_track_of_frame, int64_t B, float* d_verts, float* d_joints,
+                 const int32_t* d_track_of_frame, int64_t B, float* d_verts, int64_t verts_pitch, float* d_joints,
                  prk_score_rec* d_scores, double* d_euler_out, const int32_t* h_debug_joint_ids,
                  int n_debug, struct prk_comm* comm_scores, struct prk_comm* comm_euler,
                  int64_t frame_offset, void* d_workspace, size_t workspace_bytes, void* stream);
@@ -203,7 +207,7 @@ size_t prk_host_scores_offset(const prk_model* model, int64_t B);
 int prk_pipeline_host(prk_model* model, const float* h_pose, const float* h_betas,
                       const float* h_trans, int center_idx, const prk_addinfo* h_info,
                       int32_t n_tracks, const int32_t* h_track_of_frame, int64_t B,
-                      float* d_verts, float* h_joints, prk_score_rec* h_scores,
+                      float* d_verts, int64_t verts_pitch, float* h_joints, prk_score_rec* h_scores,
                       struct prk_comm* comm_scores, int64_t frame_offset,
                       void* d_workspace, size_t workspace_bytes, void* stream);
 

@@ -19,6 +19,7 @@ PRK_SCORE_RULA = 2
 PRK_DTYPE_F32 = 0
 PRK_DTYPE_F64 = 1
 PRK_FLAG_JOINTS_ONLY = 1
+VERTS_PITCH_ALIGNED = 20672     # floats per vertex row with 16-byte aligned rows (PRK_VERTS_PITCH_ALIGNED)
 PRK_ERR_PEER = 6
 ABI_VERSION = 2
 
@@ -75,7 +76,7 @@ def lib():
     L.prk_workspace_bytes.restype = sz
     L.prk_workspace_bytes.argtypes = [vp, i64, u32]
     L.prk_smpl_forward.restype = i32
-    L.prk_smpl_forward.argtypes = [vp, vp, vp, vp, i32, i64, vp, vp, vp, sz, vp]
+    L.prk_smpl_forward.argtypes = [vp, vp, vp, vp, i32, i64, vp, i64, vp, vp, sz, vp]
     L.prk_score_pose.restype = i32
     L.prk_score_pose.argtypes = [vp, i32, vp, i32, vp, i64, u32, vp, vp, vp, i32, vp]
     L.prk_score_euler.restype = i32
@@ -83,7 +84,7 @@ def lib():
     L.prk_euler.restype = i32
     L.prk_euler.argtypes = [vp, i32, i64, vp, vp, vp]
     L.prk_pipeline.restype = i32
-    L.prk_pipeline.argtypes = [vp, vp, vp, vp, i32, vp, i32, vp, i64, vp, vp, vp, vp, vp, i32, vp, vp, i64, vp, sz, vp]
+    L.prk_pipeline.argtypes = [vp, vp, vp, vp, i32, vp, i32, vp, i64, vp, i64, vp, vp, vp, vp, i32, vp, vp, i64, vp, sz, vp]
     L.prk_rot_to_angle.restype = i32
     L.prk_rot_to_angle.argtypes = [vp, i32, i64, vp, vp, vp]
     L.prk_host_workspace_bytes.restype = sz
@@ -91,7 +92,7 @@ def lib():
     L.prk_host_scores_offset.restype = sz
     L.prk_host_scores_offset.argtypes = [vp, i64]
     L.prk_pipeline_host.restype = i32
-    L.prk_pipeline_host.argtypes = [vp, vp, vp, vp, i32, vp, i32, vp, i64, vp, vp, vp, vp, i64, vp, sz, vp]
+    L.prk_pipeline_host.argtypes = [vp, vp, vp, vp, i32, vp, i32, vp, i64, vp, i64, vp, vp, vp, i64, vp, sz, vp]
     L.prk_score_histogram.restype = i32
     L.prk_score_histogram.argtypes = [vp, i64, u32, vp, vp]
     L.prk_debug_blend.restype = i32

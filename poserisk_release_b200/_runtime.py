@@ -167,3 +167,25 @@ class _DevView:
                 self.tensor = torch.as_tensor(self, device=device)
         else:
             self.tensor = torch.empty(0, dtype=dtype, device=device)
+
+
+def verts_pitch(verts) -> int:
+    """Row pitch (floats) of a (B, 6890, 3) vertex tensor: 20670 when dense; a tensor whose frames are further apart
+    (e.g. made by `aligned_verts`) must keep every frame's 20670 floats contiguous."""
+    if verts is None:
+        return 0
+    if verts.dim() != 3 or tuple(verts.shape[1:]) != (6890, 3) or verts.dtype != torch.float32:
+        raise ValueError('verts_out must be a float32 tensor of shape (B, 6890, 3)')
+    if verts.shape[0] <= 1 and verts.is_contiguous():
+        return 20670
+    if verts.stride(2) != 1 or verts.stride(1) != 3:
+        raise ValueError('verts_out: the 6890 x 3 floats of a frame must be contiguous')
+    return 20670 if verts.shape[0] <= 1 else int(verts.stride(0))
+
+
+def aligned_verts(B: int, device: torch.device) -> torch.Tensor:
+    """(B, 6890, 3) float32 view over storage with 16-byte aligned rows (pitch 20672 floats): the layout the vertex
+    kernel stores with bulk tensor (TMA) stores.  Values and indexing are those of a dense tensor; only
+    `.is_contiguous()` differs (`.contiguous()` gives the reference's dense layout)."""
+    flat = torch.empty((max(B, 1), _lib.VERTS_PITCH_ALIGNED), dtype=torch.float32, device=device)
+    return flat[:B, :20670].view(B, 6890, 3)

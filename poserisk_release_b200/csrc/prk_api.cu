@@ -107,6 +107,26 @@ int encode_tmap_2d_ex(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_
     }
     return PRK_OK;
 }
+// fp32 [rows][cols] with an explicit row pitch in bytes (a multiple of 16), no swizzle: the vertex-store map
+int encode_tmap_2d_f32_strided(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, uint64_t pitch_bytes,
+                               uint32_t box_rows, uint32_t box_cols) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) { set_detail("cuTensorMapEncodeTiled", "driver entry point not found"); return PRK_ERR_DRIVER; }
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {pitch_bytes};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(gptr), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char msg[64];
+        snprintf(msg, sizeof msg, "CUresult %d (vertex-store map)", (int)r);
+        set_detail("cuTensorMapEncodeTiled", msg);
+        return PRK_ERR_DRIVER;
+    }
+    return PRK_OK;
+}
 int encode_tmap_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, uint32_t box_rows,
                    uint32_t box_cols, int elem_bytes) {
     return encode_tmap_2d_ex(out, gptr, rows, cols, box_rows, box_cols, elem_bytes, 1);
@@ -212,7 +232,7 @@ static void chain_break(const void* ws, const Model* m) {   // a device-API call
 // pose-chain launch and long before the vertex kernels finish
 // argument / workspace checks of a forward call, done before anything is launched
 static int forward_check(const char* who, const Model* m, const float* d_pose, int center_idx, int64_t B,
-                         const float* d_verts, const float* d_joints, const void* ws, size_t ws_bytes, Layout& L) {
+                         const float* d_verts, int64_t vpitch, const float* d_joints, const void* ws, size_t ws_bytes, Layout& L) {
     if (!m || B < 0 || (B > 0 && (!d_pose || !d_joints)) || center_idx >= NJ) {
         set_detail(who, "invalid argument");
         return PRK_ERR_INVALID_ARG;
@@ -223,6 +243,17 @@ static int forward_check(const char* who, const Model* m, const float* d_pose, i
         set_detail(who, "d_verts must be 8-byte aligned");
         return PRK_ERR_INVALID_ARG;
     }
+    if (mesh && vpitch != 0 && vpitch != NVC) {
+        // padded vertex rows exist for the TMA store path only: 16-byte aligned rows, models with <= 4 weights per vertex
+        if (vpitch < NVC || (vpitch & 3) || (reinterpret_cast<uintptr_t>(d_verts) & 15)) {
+            set_detail(who, "verts_pitch must be 0 / 20670 or a multiple of 4 floats >= 20670 with a 16-byte aligned d_verts");
+            return PRK_ERR_INVALID_ARG;
+        }
+        if (m->nnz_groups != 1) {
+            set_detail(who, "a padded verts_pitch needs a model with at most 4 skinning weights per vertex");
+            return PRK_ERR_UNSUPPORTED;
+        }
+    }
     if (!ws || (reinterpret_cast<uintptr_t>(ws) & 1023)) {
         set_detail(who, "workspace missing or not 1024-byte aligned");
         return PRK_ERR_WORKSPACE;
@@ -232,10 +263,11 @@ static int forward_check(const char* who, const Model* m, const float* d_pose, i
 }
 
 static int forward_impl(Model* m, const float* d_pose, const float* d_betas, const float* d_trans, int center_idx,
-                        int64_t B, float* d_verts, float* d_joints, void* ws, size_t ws_bytes, cudaStream_t s,
+                        int64_t B, float* d_verts, int64_t vpitch, float* d_joints, void* ws, size_t ws_bytes, cudaStream_t s,
                         cudaEvent_t ev_joints = nullptr) {
     Layout L;
-    const int rc0 = forward_check("prk_smpl_forward", m, d_pose, center_idx, B, d_verts, d_joints, ws, ws_bytes, L);
+    if (vpitch == 0) vpitch = NVC;
+    const int rc0 = forward_check("prk_smpl_forward", m, d_pose, center_idx, B, d_verts, vpitch, d_joints, ws, ws_bytes, L);
     if (rc0 != PRK_OK) return rc0;
     if (B == 0) return PRK_OK;
     const bool mesh = d_verts != nullptr;
@@ -263,7 +295,7 @@ static int forward_impl(Model* m, const float* d_pose, const float* d_betas, con
         int rc = encode_tmap_2d_bf16(&tmA, d_arows, (uint64_t)rows_pad, FUSED_K, FUSED_BM, 64);
         if (rc != PRK_OK) return rc;
         StageScope sc(1, s);
-        PRK_CUDA(launch_fused(*m, tmA, rows_pad, d_askin, d_off, ns, d_verts + (size_t)s0 * NVC, s));
+        PRK_CUDA(launch_fused(*m, tmA, rows_pad, d_askin, d_off, ns, d_verts + (size_t)s0 * vpitch, vpitch, s));
     }
     return PRK_OK;
 }
@@ -461,13 +493,13 @@ size_t prk_workspace_bytes(const prk_model*, int64_t B, uint32_t flags) {
 }
 
 int prk_smpl_forward(prk_model* model, const float* d_pose, const float* d_betas, const float* d_trans,
-                     int center_idx, int64_t B, float* d_verts, float* d_joints, void* ws, size_t ws_bytes,
+                     int center_idx, int64_t B, float* d_verts, int64_t verts_pitch, float* d_joints, void* ws, size_t ws_bytes,
                      void* stream) {
     Model* m = model;
     if (!m) { set_detail("prk_smpl_forward", "null model"); return PRK_ERR_INVALID_ARG; }
     chain_break(ws, nullptr);
     PRK_CUDA(cudaSetDevice(m->device));
-    return forward_impl(m, d_pose, d_betas, d_trans, center_idx, B, d_verts, d_joints, ws, ws_bytes,
+    return forward_impl(m, d_pose, d_betas, d_trans, center_idx, B, d_verts, verts_pitch, d_joints, ws, ws_bytes,
                         static_cast<cudaStream_t>(stream));
 }
 
@@ -533,7 +565,7 @@ int prk_rot_to_angle(const void* d_rotmat, int dtype, int64_t n_rot, void* d_rve
 
 int prk_pipeline(prk_model* model, const float* d_pose, const float* d_betas, const float* d_trans, int center_idx,
                  const prk_addinfo* d_info, int32_t n_tracks, const int32_t* d_track, int64_t B, float* d_verts,
-                 float* d_joints, prk_score_rec* d_scores, double* d_euler_out, const int32_t* h_debug_joint_ids,
+                 int64_t verts_pitch, float* d_joints, prk_score_rec* d_scores, double* d_euler_out, const int32_t* h_debug_joint_ids,
                  int n_debug, prk_comm* comm_scores, prk_comm* comm_euler, int64_t frame_offset, void* ws, size_t ws_bytes,
                  void* stream) {
     Model* m = model;
@@ -550,7 +582,7 @@ int prk_pipeline(prk_model* model, const float* d_pose, const float* d_betas, co
     }
     {
         Layout L;
-        const int rc = forward_check("prk_pipeline", m, d_pose, center_idx, B, d_verts, d_joints, ws, ws_bytes, L);
+        const int rc = forward_check("prk_pipeline", m, d_pose, center_idx, B, d_verts, verts_pitch, d_joints, ws, ws_bytes, L);
         if (rc != PRK_OK) return rc;
     }
     if (comm_euler && n_debug == 0) comm_euler = nullptr;
@@ -585,7 +617,7 @@ int prk_pipeline(prk_model* model, const float* d_pose, const float* d_betas, co
     if (e == cudaSuccess && rc == PRK_OK && comm_euler)
         rc = prk_allgather_rows(comm_euler, d_euler_out, B, frame_offset, n_debug * 24, nullptr, ss);
     if (e == cudaSuccess && e2 == cudaSuccess && rc == PRK_OK)
-        rc = forward_impl(m, d_pose, d_betas, d_trans, center_idx, B, d_verts, d_joints, ws, ws_bytes, s);
+        rc = forward_impl(m, d_pose, d_betas, d_trans, center_idx, B, d_verts, verts_pitch, d_joints, ws, ws_bytes, s);
     if (e2 == cudaSuccess) e2 = cudaStreamWaitEvent(s, m->ev_score, 0);
     if (e != cudaSuccess) return cuda_fail(e, "score_pose_kernel");
     if (e2 != cudaSuccess) return cuda_fail(e2, "join of the scoring stream");
@@ -622,7 +654,7 @@ size_t prk_host_scores_offset(const prk_model*, int64_t B) { return host_stage(B
 
 int prk_pipeline_host(prk_model* model, const float* h_pose, const float* h_betas, const float* h_trans,
                       int center_idx, const prk_addinfo* h_info, int32_t n_tracks, const int32_t* h_track, int64_t B,
-                      float* d_verts, float* h_joints, prk_score_rec* h_scores, prk_comm* comm_scores,
+                      float* d_verts, int64_t verts_pitch, float* h_joints, prk_score_rec* h_scores, prk_comm* comm_scores,
                       int64_t frame_offset, void* ws, size_t ws_bytes, void* stream) {
     Model* m = model;
     if (!m || B < 0 || !h_info || n_tracks < 1 || n_tracks > 4096 || (B > 0 && (!h_pose || !h_scores))) {
@@ -638,7 +670,9 @@ int prk_pipeline_host(prk_model* model, const float* h_pose, const float* h_beta
     if (ws_bytes <= h.inner) { set_detail("prk_pipeline_host", "workspace too small"); return PRK_ERR_WORKSPACE; }
     {
         Layout L;
-        if (center_idx >= NJ || (d_verts && (reinterpret_cast<uintptr_t>(d_verts) & 7))) {
+        if (center_idx >= NJ || (d_verts && (reinterpret_cast<uintptr_t>(d_verts) & 7)) ||
+            (d_verts && verts_pitch != 0 && verts_pitch != NVC &&
+             (verts_pitch < NVC || (verts_pitch & 3) || (reinterpret_cast<uintptr_t>(d_verts) & 15) || m->nnz_groups != 1))) {
             set_detail("prk_pipeline_host", "invalid argument");
             return PRK_ERR_INVALID_ARG;
         }
@@ -689,7 +723,7 @@ int prk_pipeline_host(prk_model* model, const float* h_pose, const float* h_beta
     }
     PRK_CUDA(cudaStreamWaitEvent(s, m->ev_h2d, 0));
     PRK_CUDA(cudaStreamWaitEvent(s, m->ev_out, 0));         // d_joints of the previous call has been copied out
-    int rc = forward_impl(m, d_pose, d_betas, d_trans, center_idx, B, d_verts, d_joints, w + h.inner, ws_bytes - h.inner, s,
+    int rc = forward_impl(m, d_pose, d_betas, d_trans, center_idx, B, d_verts, verts_pitch, d_joints, w + h.inner, ws_bytes - h.inner, s,
                           m->ev_joints);
     if (rc != PRK_OK) {                                     // the caller's stream still joins what was launched
         cudaStreamWaitEvent(s, m->ev_score, 0);
@@ -775,7 +809,7 @@ int prk_debug_blend(prk_model* model, const float* d_pose, const float* d_betas,
         CUtensorMap tmA;
         int rc = encode_tmap_2d_bf16(&tmA, d_arows, (uint64_t)rows_pad, FUSED_K, FUSED_BM, 64);
         if (rc != PRK_OK) return rc;
-        PRK_CUDA(launch_fused(*m, tmA, rows_pad, d_askin, d_off, B, d_vposed, s));
+        PRK_CUDA(launch_fused(*m, tmA, rows_pad, d_askin, d_off, B, d_vposed, NVC, s));
     }
     return PRK_OK;
 }

@@ -64,9 +64,9 @@ constexpr int kOutBytes = 4 * kOutBytesPerQuarter;               // 26,624
 constexpr int kWSlotsMax = 8;
 // weight slots of the ring: a slot is reused kWS units later, which must be more than the producer's lead over the epilogue
 // (ring length in units + the two accumulator buffers + the unit in progress): 4 with the 6-chunk ring (< 1 unit),
-// 8 with the 10-half-chunk ring of the CTA pairs (1.25 units)
-constexpr int w_slots(int pair) { return pair == 2 ? 8 : 4; }
-constexpr int w_shift(int pair) { return pair == 2 ? 3 : 2; }
+// 6 with the 8 .. 10 half-chunk rings of the CTA pairs (1 .. 1.25 units: the MMA of unit i-2 has started when the weights of
+// unit i are loaded, so the epilogue is past the middle of unit i-4 and a slot must not be reused within 5 units)
+constexpr int w_slots(int pair) { return pair == 2 ? 6 : 4; }
 constexpr int kMaxStages = 12;                                   // 6 x 12 KB chunks, or 12 x 6 KB half chunks (CTA pairs)
 constexpr int kNumBars = 2 * kMaxStages + 2 * kEpiWarps + 2 + kWSlotsMax + 2 + 8;
 constexpr int kThreads = (kEpiWarps + 2) * 32;                   // 576
@@ -74,8 +74,16 @@ constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kAccCol0 = 288;                               // accumulators behind the 24 x 12 A_j columns
 constexpr int kSmemLimit = 232448;                               // 227 KB opt-in maximum per CTA
 
-constexpr int fused_smem_bytes(int stages, int groups, int pair = 1) {
-    return kABytes + stages * (kBChunkBytes / pair) + kOutBytes + w_slots(pair) * groups * FUSED_WGROUP_BYTES + kNumBars * 8 + 16 +
+// Vertex stores by TMA (kTma): possible when the caller's vertex rows are 16-byte aligned (row pitch a multiple of 4 floats,
+// e.g. 20,672 instead of 20,670 floats: prk_smpl_forward_pitched).  Every epilogue warp then owns 8 CONSECUTIVE vertices of the
+// tile, stages its 32 frames x 24 floats in a private tile and one lane issues ONE bulk tensor store per unit: no read-back,
+// no store instruction, no hand-over between the warps of a lane quarter, ragged edges clipped by the TMA unit.
+// (A bulk tensor store needs the global address of the box start 16-byte aligned -- scripts/ubench_tmastore.cu -- which is
+// why the dense 82,680-byte rows of the reference layout cannot use it: every second row starts 8 bytes off.)
+constexpr int kWarpTileBytes = 32 * 24 * 4;                      // [32 frames][8 vertices x 3] = 3,072 B per epilogue warp
+constexpr int kOutBytesTma = kEpiWarps * kWarpTileBytes;         // 49,152
+constexpr int fused_smem_bytes(int stages, int groups, int pair = 1, bool tma = false) {
+    return kABytes + stages * (kBChunkBytes / pair) + (tma ? kOutBytesTma : kOutBytes) + w_slots(pair) * groups * FUSED_WGROUP_BYTES + kNumBars * 8 + 16 +
            1024 /*alignment slack*/;
 }
 
@@ -117,6 +125,12 @@ __device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint64_
 __device__ __forceinline__ void tcgen05_commit_pair(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+// bulk tensor store shared -> global of one box; evict-first like the plain vertex stores
+__device__ __forceinline__ void tma_store_box(const CUtensorMap* map, const void* src, int c0, int c1, uint64_t policy) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "l"(policy)
+                 : "memory");
 }
 __device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t* r) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -229,10 +243,10 @@ __device__ __forceinline__ bool elect_one() {
 #define GATHER_ADDR(col) (col)                 // the table holds absolute tensor-memory addresses
 
 // kPair = 2: CTA pairs (see above); n_units then counts pair units: (two consecutive frame tiles) x vertex tile
-template <int kGroups, int kPair>
+template <int kGroups, int kPair, bool kTma>
 __global__ void __launch_bounds__(kThreads, 1)
 fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid_constant__ CUtensorMap tmap_B,
-                        const uint16_t* __restrict__ B2img,
+                        const __grid_constant__ CUtensorMap tmap_V, const uint16_t* __restrict__ B2img,
                         const float* __restrict__ AskinT, const float* __restrict__ off,
                         const uint8_t* __restrict__ wpack, int groups_rt, int stages, int64_t B, int64_t n_units,
                         float* __restrict__ verts, int dbg) {
@@ -245,8 +259,8 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
     uint8_t* sB = sA + kABytes;                                   // [stages][96 rows][128 B]
     constexpr int kBSlotBytes = kBChunkBytes / kPair;             // a CTA of a pair holds 48 of a chunk's 96 rows
     uint8_t* sOut = sB + stages * kBSlotBytes;                   // [16 warps][32 frames][12 floats]
-    uint8_t* sW = sOut + kOutBytes;                               // [4 slots][groups][32 x float4 weights | 32 x uint4 columns]
-    constexpr int kWS = w_slots(kPair), kWShift = w_shift(kPair);
+    uint8_t* sW = sOut + (kTma ? kOutBytesTma : kOutBytes);                               // [4 slots][groups][32 x float4 weights | 32 x uint4 columns]
+    constexpr int kWS = w_slots(kPair);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sW + kWS * groups * FUSED_WGROUP_BYTES);
     uint64_t* full_bar = bars;                                    // [kMaxStages]
     uint64_t* empty_bar = bars + kMaxStages;                      // [kMaxStages]
@@ -338,12 +352,12 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
             // skinning weights of the tile's 32 vertices.  Slot i % kWS was last read by unit i - kWS.  kWS = 4: the ring is
             // shorter than one unit, so the chunk loads of unit i-1 already issued imply the MMA of unit i-1 has started,
             // i.e. every epilogue warp finished unit i-3.  CTA pairs: the ring holds 1.25 units, the MMA of unit i-2 has
-            // started, every epilogue warp has passed the middle of unit i-4: hence kWS = 8 there (4 slots were a race).
+            // started, every epilogue warp has passed the middle of unit i-4: hence kWS = 6 there (4 slots were a race).
             const uint32_t wbytes = (uint32_t)groups * FUSED_WGROUP_BYTES;
             if (elect_one()) {
-                uint64_t* wb = &wfull_bar[i & (kWS - 1)];
+                uint64_t* wb = &wfull_bar[i % kWS];
                 mbar_expect_tx(wb, wbytes);
-                bulk_load_1d(sW + (i & (kWS - 1)) * wbytes, wpack + (size_t)vt * wbytes, wbytes, wb);
+                bulk_load_1d(sW + (i % kWS) * wbytes, wpack + (size_t)vt * wbytes, wbytes, wb);
             }
 #pragma unroll 1
             for (int c = 0; c < FUSED_B_CHUNKS; ++c) {
@@ -390,7 +404,7 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
             const int acc = i & 1;
             // the tile's skinning weights: waited for here (single waiter) so the epilogue warps,
             // which see them through their tfull barrier, never park on the TMA barrier
-            MBAR_WAIT(&wfull_bar[i & (kWS - 1)], (i >> kWShift) & 1);
+            MBAR_WAIT(&wfull_bar[i % kWS], (i / kWS) & 1);
             MBAR_WAIT(&tempty_bar[acc], ((i >> 1) & 1) ^ 1);       // epilogue drained this accumulator
             tcgen05_fence_after();
             const uint32_t d_tmem = tmem_base + kAccCol0 + (uint32_t)acc * FUSED_BN;
@@ -461,7 +475,11 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
         // sit half a half apart, so a warp rarely blocks and the four warps drift apart instead of marching in lock-step.
         float* pend = nullptr;
         uint32_t n_staged = 0;                                        // halves this warp has staged so far
+        uint8_t* const wtile = sOut + warp * kWarpTileBytes;          // kTma: this warp's private tile
+        uint64_t store_policy = 0;
+        if (kTma) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(store_policy));
         auto flush_pending = [&]() {
+            if (kTma) return;                                         // nothing is deferred: the TMA unit does the stores
             if (pend == nullptr) return;                              // warp-uniform
             MBAR_WAIT(&qstaged_bar[quarter], (n_staged - 1) & 1);    // all four warps staged the pending half
 #pragma unroll
@@ -504,12 +522,12 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
             }
             const int acc = i & 1;
             const uint32_t wbytes = (uint32_t)groups * FUSED_WGROUP_BYTES;
-            const uint8_t* wslot = sW + (i & (kWS - 1)) * wbytes;
+            const uint8_t* wslot = sW + (i % kWS) * wbytes;
             TCLK(tw0);
             MBAR_WAIT(&tfull_bar[acc * kEpiWarps + warp], (i >> 1) & 1);
             tcgen05_fence_after();
             TCLK(tw1);
-            MBAR_WAIT(&wfull_bar[i & (kWS - 1)], (i >> kWShift) & 1);   // completed before the MMAs were issued: never parks
+            MBAR_WAIT(&wfull_bar[i % kWS], (i / kWS) & 1);   // completed before the MMAs were issued: never parks
             TCLK(tw2);
             TACC(0, tw0, tw1); TACC(1, tw1, tw2);
             if (DBG(2)) {
@@ -519,7 +537,8 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
                 if (++vt == FUSED_NT) { vt = 0; ft += kPair; }
                 continue;
             }
-            const uint32_t t_acc = t_lane + kAccCol0 + (uint32_t)acc * FUSED_BN + (uint32_t)(oct * 12);
+            // the warp's accumulator columns: 2 x 12 (vertices 4 oct.. of each half) or, kTma, 24 consecutive ones (vertices 8 oct..)
+            const uint32_t t_acc = t_lane + kAccCol0 + (uint32_t)acc * FUSED_BN + (uint32_t)(oct * (kTma ? 24 : 12));
             const int c_unit = vt * FUSED_VT * 3;                   // first vertex coordinate of the tile
             float* vrow = verts + (size_t)(ft * FUSED_BM + quarter * 32) * NVC + c_unit;
             // recomputed where it is used (two integer ops) instead of living in a register across the unit body
@@ -576,9 +595,9 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
                 // n+1 is in flight while item n is multiplied, with two 12-register buffers -- TMEM
                 // read bandwidth is the bound of this kernel, so it must never sit idle.
                 // the warp's k-th vertex is tile vertex 16 (k >> 2) + 4 oct + (k & 3)
-                const uint4* cols = reinterpret_cast<const uint4*>(wslot + 512 + (FUSED_WCOL_COPIES > 1 ? quarter * 512 : 0)) + oct * 4;
-                const float4* wgt = reinterpret_cast<const float4*>(wslot) + oct * 4;
-                constexpr int kTileV[8] = {0, 1, 2, 3, 16, 17, 18, 19};
+                const uint4* cols = reinterpret_cast<const uint4*>(wslot + 512 + (FUSED_WCOL_COPIES > 1 ? quarter * 512 : 0)) + oct * (kTma ? 8 : 4);
+                const float4* wgt = reinterpret_cast<const float4*>(wslot) + oct * (kTma ? 8 : 4);
+                constexpr int kTileV[8] = {0, 1, 2, 3, kTma ? 4 : 16, kTma ? 5 : 17, kTma ? 6 : 18, kTma ? 7 : 19};
                 uint32_t buf[2][12], p[12];
                 uint4 cj = DBG(64) ? make_uint4(12, 36, 120, 240) : cols[0];
                 TCLK(tg0);
@@ -643,12 +662,31 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
                         TCLK(tg1);
                         TACC(2, tg0, tg1);
                         const int half = k >> 2;
-                        if (k == 3) { tmem_ld_x8(t_acc + 48, p); tmem_ld_x4(t_acc + 56, p + 8); }   // next half's v_posed
+                        if (k == 3) { tmem_ld_x8(t_acc + (kTma ? 12 : 48), p); tmem_ld_x4(t_acc + (kTma ? 20 : 56), p + 8); }   // next half's v_posed
                         if (DBG(128)) {                              // knock-out: no staging, no read-back, no stores
                             float sum = 0.f;                         // every result stays live: nothing of the math may be dropped
 #pragma unroll
                             for (int r = 0; r < 12; ++r) sum += res[r];
                             if (sum == 123.456f) vrow[half] = sum;
+                            continue;
+                        }
+                        if (kTma) {
+                            if (half == 0) {    // the previous unit's box has been read out of the tile (issued a unit ago)
+                                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                                __syncwarp();
+                            }
+                            float4* dst = reinterpret_cast<float4*>(wtile + lane * 96 + half * 48);
+                            dst[0] = make_float4(res[0], res[1], res[2], res[3]);
+                            dst[1] = make_float4(res[4], res[5], res[6], res[7]);
+                            dst[2] = make_float4(res[8], res[9], res[10], res[11]);
+                            if (half == 1) {
+                                fence_proxy_async_smem();               // generic-proxy writes -> visible to the async proxy
+                                __syncwarp();
+                                if (lane == 0 && !DBG(4)) {
+                                    tma_store_box(&tmap_V, wtile, c_unit + oct * 24, (int)ft * FUSED_BM + quarter * 32, store_policy);
+                                    tma_store_commit();
+                                }
+                            }
                             continue;
                         }
                         if (n_staged > 0) MBAR_WAIT(&qflushed_bar[quarter], (n_staged - 1) & 1);   // tile is free
@@ -724,6 +762,7 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
             if (++vt == FUSED_NT) { vt = 0; ft += kPair; }
         }
         flush_pending();
+        if (kTma && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores done before the CTA exits
 #ifdef PRK_FUSED_DEBUG
         if (lane == 0) {
             t_sum[4] = clock64() - t_begin;
@@ -806,12 +845,19 @@ extern "C" __attribute__((visibility("default"))) int prk_fused_debug_read(unsig
 }
 #endif
 
-int fused_stages(int groups, int pair) {
-    int stages = pair == 2 ? 10 : 6;            // 10 half chunks (60 KB) + 8 weight slots, or 6 chunks (72 KB) + 4 slots
+int fused_stages(int groups, int pair, bool tma) {
+#ifndef PRK_PAIR_STAGES
+#define PRK_PAIR_STAGES 12
+#endif
+    int stages = pair == 2 ? PRK_PAIR_STAGES : 6;   // 12 half chunks (72 KB) + 6 weight slots, or 6 chunks (72 KB) + 4 slots
+#ifndef PRK_TMA_STAGES
+#define PRK_TMA_STAGES 8
+#endif
+    if (tma) stages = pair == 2 ? PRK_TMA_STAGES : 4;   // the private tiles take 22.5 KB more
 #ifdef PRK_STAGE_CAP
     stages = PRK_STAGE_CAP * pair;
 #endif
-    while (stages > 2 && fused_smem_bytes(stages, groups, pair) > kSmemLimit) --stages;
+    while (stages > 2 && fused_smem_bytes(stages, groups, pair, tma) > kSmemLimit) --stages;
     return stages;
 }
 
@@ -825,13 +871,13 @@ static int fused_pair(int64_t n_ft) {
     return (p == 2 && n_ft >= 2) ? 2 : 1;
 }
 
-template <int kGroups, int kPair>
+template <int kGroups, int kPair, bool kTma>
 static cudaError_t launch_fused_t(const Model& m, const CUtensorMap& tmap_A, int64_t rows_pad, const float* d_AskinT,
-                                  const float* d_off, int64_t B, float* d_verts, cudaStream_t s, bool pdl) {
-    auto kern = fused_blend_skin_kernel<kGroups, kPair>;
+                                  const float* d_off, int64_t B, float* d_verts, int64_t vpitch, cudaStream_t s, bool pdl) {
+    auto kern = fused_blend_skin_kernel<kGroups, kPair, kTma>;
     const int groups = m.nnz_groups;
-    const int stages = fused_stages(groups, kPair);
-    const int smem = fused_smem_bytes(stages, groups, kPair);
+    const int stages = fused_stages(groups, kPair, kTma);
+    const int smem = fused_smem_bytes(stages, groups, kPair, kTma);
     if (smem > kSmemLimit) return cudaErrorInvalidConfiguration;
     static std::atomic<int> attr_set[64];       // per device: dynamic shared memory this instantiation was opted in for
     if (m.device >= 0 && m.device < 64 && attr_set[m.device].load(std::memory_order_acquire) < smem) {
@@ -881,20 +927,31 @@ static cudaError_t launch_fused_t(const Model& m, const CUtensorMap& tmap_A, int
     cfg.numAttrs = na;
     const uint8_t* wpack = m.d_wpack;
     const uint16_t* b2img = m.d_B2;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmap_A, m.tmap_B2, b2img, d_AskinT, d_off, wpack, groups, stages, B, n_units,
+    CUtensorMap tmV = m.tmap_B2;                // (a valid placeholder for the instantiations that store with STG)
+    if (kTma) {                                 // [B][vpitch] fp32, boxes of 24 floats x 32 frames
+        const int rc = encode_tmap_2d_f32_strided(&tmV, d_verts, (uint64_t)B, (uint64_t)NVC, (uint64_t)vpitch * 4, 32, 24);
+        if (rc != PRK_OK) return cudaErrorInvalidValue;
+    }
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmap_A, m.tmap_B2, tmV, b2img, d_AskinT, d_off, wpack, groups, stages, B, n_units,
                                        d_verts, 0);
     count_launch();
     return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 cudaError_t launch_fused(const Model& m, const CUtensorMap& tmap_A, int64_t rows_pad, const float* d_AskinT,
-                         const float* d_off, int64_t B, float* d_verts, cudaStream_t s) {
+                         const float* d_off, int64_t B, float* d_verts, int64_t vpitch, cudaStream_t s) {
     if (B == 0) return cudaSuccess;
     static const bool pdl = [] { const char* e = getenv("PRK_PDL"); return !e || atoi(e) != 0; }();
+    static const bool tma_ok = [] { const char* e = getenv("PRK_TMA_STORE"); return !e || atoi(e) != 0; }();
     const int pair = fused_pair(rows_pad / FUSED_BM);
-#define PRK_GO(G, P) launch_fused_t<G, P>(m, tmap_A, rows_pad, d_AskinT, d_off, B, d_verts, s, pdl)
-    if (m.nnz_groups == 1) return pair == 2 ? PRK_GO(1, 2) : PRK_GO(1, 1);
-    return pair == 2 ? PRK_GO(0, 2) : PRK_GO(0, 1);
+    // TMA vertex stores need 16-byte aligned rows: base and pitch; the dense reference layout (pitch 20,670) has neither
+    const bool tma = tma_ok && m.nnz_groups == 1 && (vpitch % 4) == 0 && (reinterpret_cast<uintptr_t>(d_verts) & 15) == 0;
+#define PRK_GO(G, P, T) launch_fused_t<G, P, T>(m, tmap_A, rows_pad, d_AskinT, d_off, B, d_verts, vpitch, s, pdl)
+    if (m.nnz_groups == 1) {
+        if (tma) return pair == 2 ? PRK_GO(1, 2, true) : PRK_GO(1, 1, true);
+        return pair == 2 ? PRK_GO(1, 2, false) : PRK_GO(1, 1, false);
+    }
+    return pair == 2 ? PRK_GO(0, 2, false) : PRK_GO(0, 1, false);
 #undef PRK_GO
 }
 

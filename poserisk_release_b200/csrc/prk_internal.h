@@ -117,8 +117,9 @@ cudaError_t launch_pose_chain(const Model& m, const float* d_pose, const float* 
 bool pose_chain_needs_flags(const Model& m, const float* d_betas, const float* d_trans, int center_idx);
 
 // K12: fused blend GEMM + skinning (prk_fused.cu); A' rows / AskinT in the K12 layouts, rows_pad = multiple of 128
+// vpitch: floats per vertex row (NVC = dense); 16-byte aligned rows leave through TMA stores (models with <= 4 weights)
 cudaError_t launch_fused(const Model& m, const CUtensorMap& tmap_A, int64_t rows_pad, const float* d_AskinT,
-                         const float* d_off, int64_t B, float* d_verts, cudaStream_t s);
+                         const float* d_off, int64_t B, float* d_verts, int64_t vpitch, cudaStream_t s);
 
 // verification hooks of prk_debug_blend: plain FFMA evaluation of the same bf16 operands, identity A_j tiles
 cudaError_t launch_blend_simt(const Model& m, const uint16_t* d_Arows, int64_t rows, float* d_vposed, cudaStream_t s);
@@ -149,6 +150,8 @@ int encode_tmap_2d_ex(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_
                       uint32_t box_cols, int elem_bytes, int swizzle128);
 int encode_tmap_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, uint32_t box_rows,
                    uint32_t box_cols, int elem_bytes);
+int encode_tmap_2d_f32_strided(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, uint64_t pitch_bytes,
+                               uint32_t box_rows, uint32_t box_cols);
 int encode_tmap_2d_bf16(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols,
                         uint32_t box_rows, uint32_t box_cols);
 

@@ -21,9 +21,14 @@ GENDERS = ('neutral', 'female', 'male')
 
 
 class PoseRiskEngine:
-    def __init__(self, device=None, genders=('neutral',), model_root=None, allow_synthetic=None, model_data=None):
+    def __init__(self, device=None, genders=('neutral',), model_root=None, allow_synthetic=None, model_data=None,
+                 aligned_verts=True):
         """model_data: optional {gender: SMPLModelData}; otherwise ``model_root/SMPL_<GENDER>.pkl`` is read
-        (FileNotFoundError when missing, unless allow_synthetic / PRK_SYNTHETIC_SMPL=1: model_provider.get_model_data)."""
+        (FileNotFoundError when missing, unless allow_synthetic / PRK_SYNTHETIC_SMPL=1: model_provider.get_model_data).
+        aligned_verts: vertex tensors the engine allocates itself get 16-byte aligned rows (`_runtime.aligned_verts`: same
+        shape, values and indexing, row pitch 20672 instead of 20670 floats) so that the vertex kernel can store them with
+        bulk tensor stores; a `verts_out` the caller passes is used as it is, dense or aligned."""
+        self.aligned_verts = bool(aligned_verts)
         self.device = _runtime.require_cuda(device)
         self.models = {}
         for g in genders:
@@ -66,7 +71,12 @@ class PoseRiskEngine:
         with torch.cuda.device(dev):
             verts = None
             if want_verts:
-                verts = verts_out if verts_out is not None else torch.empty((B, 6890, 3), dtype=torch.float32, device=dev)
+                if verts_out is not None:
+                    verts = verts_out
+                elif self.aligned_verts and h.max_weights <= 4:
+                    verts = _runtime.aligned_verts(B, dev)
+                else:
+                    verts = torch.empty((B, 6890, 3), dtype=torch.float32, device=dev)
             joints = joints_out if joints_out is not None else torch.empty((B, 24, 3), dtype=torch.float32, device=dev)
             scores = scores_out if scores_out is not None else torch.empty((B, 32), dtype=torch.uint8, device=dev)
             euler = None
@@ -80,7 +90,7 @@ class PoseRiskEngine:
                 _lib.check(_lib.lib().prk_pipeline(
                     h.handle, _runtime.ptr(pose), _runtime.ptr(betas), _runtime.ptr(trans),
                     -1 if center_idx is None else int(center_idx), _runtime.ptr(info), info.shape[0], _runtime.ptr(track), B,
-                    _runtime.ptr(verts), _runtime.ptr(joints), _runtime.ptr(scores), _runtime.ptr(euler),
+                    _runtime.ptr(verts), _runtime.verts_pitch(verts), _runtime.ptr(joints), _runtime.ptr(scores), _runtime.ptr(euler),
                     None if ids is None else ids.ctypes.data_as(C.c_void_p), n_debug, comm_s, comm_e, int(frame_offset),
                     ws, ws_bytes, _runtime.stream_ptr(dev)))
         out = {'verts': verts, 'joints': joints, 'scores': scores}
@@ -116,7 +126,12 @@ class PoseRiskEngine:
         scores = scores_out if scores_out is not None else torch.empty((B, 32), dtype=torch.uint8, device=dev)
         verts = None
         if want_verts:
-            verts = verts_out if verts_out is not None else torch.empty((B, 6890, 3), dtype=torch.float32, device=dev)
+            if verts_out is not None:
+                verts = verts_out
+            elif self.aligned_verts and all(self.models[g].max_weights <= 4 for g in set(gender_of_track)):
+                verts = _runtime.aligned_verts(B, dev)
+            else:
+                verts = torch.empty((B, 6890, 3), dtype=torch.float32, device=dev)
         for lo, hi in zip(starts.tolist(), ends.tolist()):
             self.run(pose[lo:hi], None if betas is None else betas[lo:hi], None if trans is None else trans[lo:hi],
                      info, track_d[lo:hi], gender=GENDERS[int(g_of_f[lo])], want_verts=want_verts,
@@ -161,7 +176,7 @@ class PoseRiskEngine:
                 h.handle, _runtime.ptr(pose), _runtime.ptr(betas), _runtime.ptr(trans),
                 -1 if center_idx is None else int(center_idx), info.ctypes.data_as(C.c_void_p), info.shape[0],
                 None if track is None else track.ctypes.data_as(C.c_void_p), B, _runtime.ptr(verts_out),
-                _runtime.ptr(joints_out), _runtime.ptr(scores_out),
+                _runtime.verts_pitch(verts_out), _runtime.ptr(joints_out), _runtime.ptr(scores_out),
                 None if exchange is None else exchange.native_handles(0)[0], int(frame_offset),
                 ws, ws_bytes, _runtime.stream_ptr(dev)))
         self._keep = (info, track)   # pageable host arrays must outlive the async copies

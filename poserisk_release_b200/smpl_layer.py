@@ -29,14 +29,18 @@ class SMPL_Layer(Module):
     __constants__ = ['kintree_parents', 'gender', 'center_idx', 'num_joints']
 
     def __init__(self, center_idx=None, gender='neutral', model_root='smpl/native/models',
-                 model_data: SMPLModelData | None = None, allow_synthetic: bool | None = None):
+                 model_data: SMPLModelData | None = None, allow_synthetic: bool | None = None,
+                 aligned_verts: bool = False):
         """center_idx: joint whose position is subtracted from vertices and joints when no translation is
         given (None: nothing is subtracted); gender: 'neutral' | 'female' | 'male', selects
         ``model_root/SMPL_<GENDER>.pkl``.  Extensions: ``model_data`` hands the constants over directly,
         ``allow_synthetic`` (or PRK_SYNTHETIC_SMPL=1) permits the synthetic stand-in when the licensed file
-        is missing -- otherwise that is a FileNotFoundError, as in the reference."""
+        is missing -- otherwise that is a FileNotFoundError, as in the reference; ``aligned_verts=True`` returns the
+        vertices as a (B, 6890, 3) view over rows padded to 16 bytes (same values and indexing, not `is_contiguous()`),
+        the layout the vertex kernel writes fastest (default: the reference's dense tensor)."""
         super().__init__()
         self.center_idx, self.gender = center_idx, gender
+        self.aligned_verts = bool(aligned_verts)
         if gender in GENDER_FILE:
             self.model_path = os.path.join(model_root, GENDER_FILE[gender])
         if model_data is None:
@@ -89,14 +93,19 @@ class SMPL_Layer(Module):
         h = self._handle(device)
         L = _lib.lib()
         with torch.cuda.device(device):
-            verts = torch.empty((batch_size, 6890, 3), dtype=torch.float32, device=device) if want_verts else None
+            verts = None
+            if want_verts:
+                if self.aligned_verts and h.max_weights <= 4:
+                    verts = _runtime.aligned_verts(batch_size, device)
+                else:
+                    verts = torch.empty((batch_size, 6890, 3), dtype=torch.float32, device=device)
             joints = torch.empty((batch_size, 24, 3), dtype=torch.float32, device=device)
             if batch_size > 0:
                 ws, ws_bytes, _keep = _runtime.workspace.get(device, h.workspace_bytes(batch_size, not want_verts))
                 _lib.check(L.prk_smpl_forward(
                     h.handle, _runtime.ptr(pose), _runtime.ptr(betas), _runtime.ptr(trans),
                     -1 if self.center_idx is None else int(self.center_idx), batch_size,
-                    _runtime.ptr(verts), _runtime.ptr(joints), ws, ws_bytes, _runtime.stream_ptr(device)))
+                    _runtime.ptr(verts), _runtime.verts_pitch(verts), _runtime.ptr(joints), ws, ws_bytes, _runtime.stream_ptr(device)))
         if out_device != device:
             joints = joints.to(out_device)
             verts = verts.to(out_device) if verts is not None else None

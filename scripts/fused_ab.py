@@ -29,7 +29,8 @@ def worker():
         g = torch.Generator().manual_seed(i)
         ins.append(((torch.randn(B, 72, generator=g) * 0.35).to(dev), torch.randn(B, 10, generator=g).to(dev),
                     (torch.randn(B, 3, generator=g) * 0.1).to(dev)))
-    verts = torch.empty((B, 6890, 3), dtype=torch.float32, device=dev)
+    # AB_ALIGNED=1: vertex rows 16-byte aligned (pitch 20672 floats) -> bulk tensor stores; default: the dense reference layout
+    verts = _runtime.aligned_verts(B, dev) if os.environ.get('AB_ALIGNED') == '1' else torch.empty((B, 6890, 3), dtype=torch.float32, device=dev)
     joints = torch.empty((B, 24, 3), dtype=torch.float32, device=dev)
     scores = torch.empty((B, 32), dtype=torch.uint8, device=dev)
 

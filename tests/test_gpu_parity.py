@@ -509,7 +509,7 @@ def test_forward_with_a_small_workspace_runs_in_chunks(engine):
     verts = torch.full((B, 6890, 3), float('nan'), device='cuda')
     joints = torch.empty((B, 24, 3), device='cuda')
     _lib.check(L.prk_smpl_forward(h.handle, _runtime.ptr(pose), _runtime.ptr(betas), _runtime.ptr(trans), -1, B,
-                                  _runtime.ptr(verts), _runtime.ptr(joints), ws, small,
+                                  _runtime.ptr(verts), 0, _runtime.ptr(joints), ws, small,
                                   _runtime.stream_ptr(torch.device('cuda:0'))))
     torch.cuda.synchronize()
     assert torch.equal(verts, ref['verts']) and torch.equal(joints, ref['joints'])

@@ -133,7 +133,7 @@ def test_refused_pipeline_call_launches_nothing(engine):
     before = _lib.launch_count()
 
     def call(pose_ptr, ws_bytes, n_tracks=1):
-        return L.prk_pipeline(h.handle, pose_ptr, None, None, -1, _runtime.ptr(info), n_tracks, None, B, _runtime.ptr(verts),
+        return L.prk_pipeline(h.handle, pose_ptr, None, None, -1, _runtime.ptr(info), n_tracks, None, B, _runtime.ptr(verts), 0,
                               _runtime.ptr(joints), _runtime.ptr(scores), None, None, 0, None, None, 0, wptr, ws_bytes, stream)
     assert call(None, 1 << 19) == 1                          # PRK_ERR_INVALID_ARG
     assert call(_runtime.ptr(pose), 4096) == 3               # PRK_ERR_WORKSPACE
@@ -383,3 +383,75 @@ def test_vertex_kernel_stress_ragged_batches_twice_into_poisoned_buffers(engine)
     pick = [0, 2048, 4096, B - 1]
     v_ref, j_ref = oracle.smpl_forward(md, pose[pick].numpy(), betas[pick].numpy(), trans[pick].numpy())
     assert relerr(runs[0][0][pick].cpu().numpy(), v_ref) < TOL and relerr(runs[0][1][pick].cpu().numpy(), j_ref) < TOL
+
+
+# --------------------------------------------------------------------------- aligned vertex rows (bulk tensor stores)
+def test_aligned_vertex_rows_equal_the_dense_layout_bit_for_bit(engine):
+    """The engine's own vertex tensors have rows padded to 16 bytes (pitch 20672 floats) and are written by bulk tensor
+    stores from warp-private tiles; a dense (B, 6890, 3) tensor goes through the shared staging tile and 8-byte stores.
+    Both must hold identical bits -- ragged batches, CTA pairs and single CTAs, slices of a larger aligned buffer (config 4's
+    per-track slices) -- and the two pad floats behind every row must never be touched."""
+    from poserisk_release_b200 import _lib, _runtime
+    for B in (1, 2, 31, 128, 129, 300, 641, 1500, 4096, 4173):
+        pose, betas, trans = make(B, 700 + B % 89, 0.5)
+        p, b, t = pose.cuda(), betas.cuda(), trans.cuda()
+        flat = torch.full((B, _lib.VERTS_PITCH_ALIGNED), float('nan'), device='cuda')
+        flat[:, 20670:] = 12345.0                                 # the pad: must survive
+        v_al = flat[:, :20670].view(B, 6890, 3)
+        assert _runtime.verts_pitch(v_al) in (20670, 20672) and v_al.data_ptr() % 16 == 0
+        dense = torch.full((B, 6890, 3), float('nan'), device='cuda')
+        engine.run(p, b, t, add_info=EXAMPLE_INFO, verts_out=v_al)
+        engine.run(p, b, t, add_info=EXAMPLE_INFO, verts_out=dense)
+        auto = engine.run(p, b, t, add_info=EXAMPLE_INFO)['verts']     # engine-allocated: aligned
+        torch.cuda.synchronize()
+        assert not torch.isnan(dense).any() and torch.equal(v_al, dense) and torch.equal(auto, dense), B
+        assert bool((flat[:, 20670:] == 12345.0).all()), B
+        if B > 1:
+            assert auto.stride(0) == _lib.VERTS_PITCH_ALIGNED and not auto.is_contiguous()
+        assert torch.equal(auto.contiguous(), dense)
+    # slices of an aligned buffer at odd and even frame offsets (what run_tracks hands to each gender's model)
+    B = 900
+    pose, betas, trans = make(B, 31, 0.5)
+    big = _runtime.aligned_verts(B, torch.device('cuda:0'))
+    ref = engine.run(pose.cuda(), betas.cuda(), trans.cuda(), add_info=EXAMPLE_INFO, verts_out=torch.empty(B, 6890, 3, device='cuda'))['verts']
+    for lo, hi in ((0, 301), (301, 555), (555, 900)):
+        engine.run(pose[lo:hi].cuda(), betas[lo:hi].cuda(), trans[lo:hi].cuda(), add_info=EXAMPLE_INFO, verts_out=big[lo:hi])
+    torch.cuda.synchronize()
+    assert torch.equal(big, ref)
+
+
+def test_aligned_rows_through_the_drop_in_layer_and_the_oracle():
+    """SMPL_Layer(aligned_verts=True): same values as the dense default, against the oracle; the C ABI refuses a pitch that
+    cannot be honoured."""
+    from poserisk_release_b200 import SMPL_Layer, _lib, _runtime
+    from poserisk_release_b200.model_provider import SMPLModelData
+    B = 777
+    pose, betas, trans = make(B, 5, 0.5)
+    lay_a, lay_d = SMPL_Layer(aligned_verts=True), SMPL_Layer()
+    va, ja = lay_a(pose.cuda(), betas.cuda(), trans.cuda())
+    vd, jd = lay_d(pose.cuda(), betas.cuda(), trans.cuda())
+    assert vd.is_contiguous() and not va.is_contiguous() and tuple(va.shape) == (B, 6890, 3)
+    assert torch.equal(va, vd) and torch.equal(ja, jd)
+    v_ref, j_ref = oracle.smpl_forward(synthetic_smpl('neutral'), pose.numpy(), betas.numpy(), trans.numpy())
+    assert relerr(va.cpu().numpy(), v_ref) < TOL and relerr(ja.cpu().numpy(), j_ref) < TOL
+    # a pitch that is not a multiple of 4 floats, or smaller than a row, is an invalid argument; a padded pitch with a
+    # dense-weights model (run-time group loop, plain stores only) is unsupported
+    L = _lib.lib()
+    h = lay_d._handle(torch.device('cuda:0'))
+    ws, ws_bytes, _keep = _runtime.workspace.get(torch.device('cuda:0'), h.workspace_bytes(B, False))
+    buf = torch.empty(B * 20680, device='cuda')
+    for pitch, want in ((20671, 1), (20674, 1), (20000, 1), (20672, 0), (20680, 0)):
+        rc = L.prk_smpl_forward(h.handle, _runtime.ptr(pose.cuda()), None, None, -1, B, _runtime.ptr(buf), pitch, _runtime.ptr(jd),
+                                ws, ws_bytes, _runtime.stream_ptr(torch.device('cuda:0')))
+        assert rc == want, (pitch, rc)
+    torch.cuda.synchronize()
+    m = synthetic_smpl('neutral')
+    w = np.zeros((6890, 24), np.float32)
+    w[:, :6] = 1.0 / 6
+    lay6 = SMPL_Layer(model_data=SMPLModelData(**{**m.__dict__, 'weights': w}))
+    h6 = lay6._handle(torch.device('cuda:0'))
+    rc = L.prk_smpl_forward(h6.handle, _runtime.ptr(pose.cuda()), None, None, -1, B, _runtime.ptr(buf), 20672, _runtime.ptr(jd),
+                            ws, ws_bytes, _runtime.stream_ptr(torch.device('cuda:0')))
+    assert rc == 4                                                # PRK_ERR_UNSUPPORTED
+    v6, _ = SMPL_Layer(model_data=lay6.smpl_data, aligned_verts=True)(pose.cuda())     # the layer falls back to a dense tensor
+    assert v6.is_contiguous()

@@ -128,7 +128,8 @@ size_t prk_workspace_bytes(const prk_model* model, int64_t B, uint32_t flags);
  *   d_verts [B*6890*3] float32, or NULL for the joints-only path
  *   verts_pitch  floats from one frame's vertices to the next: 0 or 20670 = the reference's dense (B, 6890, 3)
  *           layout; a multiple of 4 >= 20670 (e.g. PRK_VERTS_PITCH_ALIGNED = 20672) with a 16-byte aligned d_verts
- *           = 16-byte aligned rows, which leave through bulk tensor stores (faster; models with <= 4 weights per vertex)
+ *           = 16-byte aligned rows, which leave through bulk tensor stores (faster; models with <= 4 weights per vertex;
+ *           the two floats that complete a row's 82,680 bytes to a multiple of 16 may be overwritten)
  *   d_joints[B*24*3]  float32 (chain translations, :145)
  * Both whole-batch tests are evaluated on the device (no host sync). */
 #define PRK_VERTS_PITCH_ALIGNED 20672
@@ -275,6 +276,9 @@ int64_t prk_vposed_pitch(void);
  * ms_out[4] / launches_out[4]: 0 pose chain, 1 blend GEMM, 2 skinning, 3 scoring.
  * Single-threaded use only. */
 int prk_profile_begin(void);
+/* the same with event pairs only around the stages in stage_mask (bit k = stage k): timing one kernel without putting
+ * events between the others (an event between the pose chain and the vertex kernel undoes their programmatic overlap) */
+int prk_profile_begin_stages(uint32_t stage_mask);
 int prk_profile_end(double* ms_out, int64_t* launches_out);
 /* number of kernels launched by this library since load (all threads) */
 uint64_t prk_launch_count(void);

@@ -39,7 +39,7 @@ EXPORTS = (
     'prk_model_destroy', 'prk_model_device', 'prk_model_max_weights', 'prk_workspace_bytes',
     'prk_smpl_forward', 'prk_score_pose', 'prk_score_euler', 'prk_euler', 'prk_pipeline',
     'prk_rot_to_angle', 'prk_host_workspace_bytes', 'prk_host_scores_offset', 'prk_pipeline_host', 'prk_score_histogram', 'prk_debug_blend',
-    'prk_vposed_pitch', 'prk_launch_count', 'prk_profile_begin', 'prk_profile_end',
+    'prk_vposed_pitch', 'prk_launch_count', 'prk_profile_begin', 'prk_profile_begin_stages', 'prk_profile_end',
     'prk_comm_create', 'prk_comm_destroy', 'prk_comm_handle_bytes', 'prk_comm_get_handle', 'prk_comm_open_peers',
     'prk_comm_gathered', 'prk_comm_wait', 'prk_allgather_rows', 'prk_allgather_scores', 'prk_comm_status')
 
@@ -100,6 +100,8 @@ def lib():
     L.prk_vposed_pitch.restype = i64
     L.prk_launch_count.restype = C.c_uint64
     L.prk_profile_begin.restype = i32
+    L.prk_profile_begin_stages.restype = i32
+    L.prk_profile_begin_stages.argtypes = [u32]
     L.prk_profile_end.restype = i32
     L.prk_profile_end.argtypes = [vp, vp]
     L.prk_comm_create.restype = i32

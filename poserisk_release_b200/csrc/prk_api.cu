@@ -19,6 +19,7 @@ void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_r
 // ---- optional per-stage CUDA-event timing (prk_profile_begin / prk_profile_end) --------
 struct StageTimer {
     bool on = false;
+    uint32_t mask = 0xF;                // stages that get event pairs (bit = stage id)
     std::vector<cudaEvent_t> pool;      // start/stop pairs
     std::vector<int> stage;             // stage id of pair i
     size_t used = 0;                    // pairs in use
@@ -32,7 +33,7 @@ struct StageScope {
     StageScope(int stage_id, cudaStream_t stream) : s(stream) {
         if (!g_timer_on.load(std::memory_order_relaxed)) return;
         std::lock_guard<std::mutex> lk(g_timer_mu);
-        if (!g_timer.on || g_timer.used >= 65536) return;
+        if (!g_timer.on || g_timer.used >= 65536 || !((g_timer.mask >> stage_id) & 1u)) return;
         if (g_timer.used * 2 + 2 > g_timer.pool.size()) {
             cudaEvent_t a, b;
             if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
@@ -753,13 +754,15 @@ int prk_score_histogram(const prk_score_rec* d_scores, int64_t B, uint32_t which
     return PRK_OK;
 }
 
-int prk_profile_begin(void) {
+int prk_profile_begin_stages(uint32_t stage_mask) {
     std::lock_guard<std::mutex> lk(g_timer_mu);
     g_timer.on = true;
+    g_timer.mask = stage_mask & 0xFu;
     g_timer.used = 0;
     g_timer_on.store(true);
     return PRK_OK;
 }
+int prk_profile_begin(void) { return prk_profile_begin_stages(0xFu); }
 
 int prk_profile_end(double* ms_out, int64_t* launches_out) {
     std::lock_guard<std::mutex> lk(g_timer_mu);

@@ -64,9 +64,12 @@ constexpr int kOutBytes = 4 * kOutBytesPerQuarter;               // 26,624
 constexpr int kWSlotsMax = 8;
 // weight slots of the ring: a slot is reused kWS units later, which must be more than the producer's lead over the epilogue
 // (ring length in units + the two accumulator buffers + the unit in progress): 4 with the 6-chunk ring (< 1 unit),
-// 6 with the 8 .. 10 half-chunk rings of the CTA pairs (1 .. 1.25 units: the MMA of unit i-2 has started when the weights of
-// unit i are loaded, so the epilogue is past the middle of unit i-4 and a slot must not be reused within 5 units)
-constexpr int w_slots(int pair) { return pair == 2 ? 6 : 4; }
+// 5 with the 10 .. 12 half-chunk rings of the CTA pairs (1.25 .. 1.5 units: the MMA of unit i-2 has started when the weights of
+// unit i are loaded, so the epilogue is past the middle of unit i-4 and units i-4 .. i-1 may still read their slots)
+#ifndef PRK_WSLOTS_PAIR
+#define PRK_WSLOTS_PAIR 5
+#endif
+constexpr int w_slots(int pair) { return pair == 2 ? PRK_WSLOTS_PAIR : 4; }
 constexpr int kMaxStages = 12;                                   // 6 x 12 KB chunks, or 12 x 6 KB half chunks (CTA pairs)
 constexpr int kNumBars = 2 * kMaxStages + 2 * kEpiWarps + 2 + kWSlotsMax + 2 + 8;
 constexpr int kThreads = (kEpiWarps + 2) * 32;                   // 576
@@ -240,7 +243,8 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 // kGroups: weight groups of 4 per vertex known at compile time (1 = SMPL), 0 = run-time `groups`
-#define GATHER_ADDR(col) (col)                 // the table holds absolute tensor-memory addresses
+// the table holds absolute tensor-memory addresses (4 copies, one per lane quarter) or plain columns (1 copy)
+#define GATHER_ADDR(col) (FUSED_WCOL_COPIES > 1 ? (col) : (col) + t_quarter)
 
 // kPair = 2: CTA pairs (see above); n_units then counts pair units: (two consecutive frame tiles) x vertex tile
 template <int kGroups, int kPair, bool kTma>
@@ -352,7 +356,7 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
             // skinning weights of the tile's 32 vertices.  Slot i % kWS was last read by unit i - kWS.  kWS = 4: the ring is
             // shorter than one unit, so the chunk loads of unit i-1 already issued imply the MMA of unit i-1 has started,
             // i.e. every epilogue warp finished unit i-3.  CTA pairs: the ring holds 1.25 units, the MMA of unit i-2 has
-            // started, every epilogue warp has passed the middle of unit i-4: hence kWS = 6 there (4 slots were a race).
+            // started, every epilogue warp has passed the middle of unit i-4: hence kWS = 5 there (4 slots were a race).
             const uint32_t wbytes = (uint32_t)groups * FUSED_WGROUP_BYTES;
             if (elect_one()) {
                 uint64_t* wb = &wfull_bar[i % kWS];
@@ -452,6 +456,7 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
         // ===== epilogue: thread = frame (TMEM lane), loop over the warp's 8 vertices of each unit =====
         const int quarter = warp & 3, oct = warp >> 2;
         const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        const uint32_t t_quarter = (uint32_t)(quarter * 32) << 16;   // (only used with a single column table)
         // Vertices leave through a staging tile shared by the four warps of a lane quarter:
         // [32 frames][16 vertices x 3 floats] per half unit, so every frame row is written to HBM as one
         // 192-byte run (the L1->L2 store path is paid per 128-byte line touched, not per byte).
@@ -849,9 +854,9 @@ int fused_stages(int groups, int pair, bool tma) {
 #ifndef PRK_PAIR_STAGES
 #define PRK_PAIR_STAGES 12
 #endif
-    int stages = pair == 2 ? PRK_PAIR_STAGES : 6;   // 12 half chunks (72 KB) + 6 weight slots, or 6 chunks (72 KB) + 4 slots
+    int stages = pair == 2 ? PRK_PAIR_STAGES : 6;   // 12 half chunks (72 KB) + 5 weight slots, or 6 chunks (72 KB) + 4 slots
 #ifndef PRK_TMA_STAGES
-#define PRK_TMA_STAGES 8
+#define PRK_TMA_STAGES 10
 #endif
     if (tma) stages = pair == 2 ? PRK_TMA_STAGES : 4;   // the private tiles take 22.5 KB more
 #ifdef PRK_STAGE_CAP

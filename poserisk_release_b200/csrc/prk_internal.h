@@ -49,9 +49,12 @@ constexpr int FUSED_BN = FUSED_VT * 3;   // 96 accumulator columns
 constexpr int FUSED_NT = GEMM_N / FUSED_BN;   // 216 vertex tiles (6912 vertex slots)
 constexpr int FUSED_ASKIN_COLS = NJ * 12;     // 288 TMEM columns of A_j per frame
 // per tile and group of 4 weights: 32 x float4 weights | 32 x uint4 TMEM columns (12 * joint)
-// ... with the column table repeated per TMEM lane quarter as ABSOLUTE tensor-memory addresses
-// ((32 * quarter) << 16 | 12 * joint; the kernel owns all 512 columns, so its allocation starts at 0)
-constexpr int FUSED_WCOL_COPIES = 4;
+// (round 1 repeated the column table per TMEM lane quarter as absolute tensor-memory addresses, (32 * quarter) << 16 | 12 * joint,
+// to save one add per gather (-2 %); round 2 keeps ONE table and spends the 1.5 KB per slot on two more ring slots (-2 %, measured))
+#ifndef PRK_WCOL_COPIES
+#define PRK_WCOL_COPIES 1
+#endif
+constexpr int FUSED_WCOL_COPIES = PRK_WCOL_COPIES;   // 1: one table of plain columns 12 * joint; the kernel adds its lane quarter
 constexpr int FUSED_WGROUP_BYTES = FUSED_VT * 16 * (1 + FUSED_WCOL_COPIES);
 // element index of B'[n][k] (vertex coordinate n, K12 column k) inside the chunk-image layout of prk_model::d_B2
 __host__ __device__ constexpr size_t fused_b2_index(int n, int k) {

@@ -387,7 +387,8 @@ def test_pipeline_config2_4096_frames(engine):
     out2 = engine.run(pose.cuda(), betas.cuda(), (trans + 1.0).cuda(), add_info=EXAMPLE_INFO)
     assert torch.allclose(out2['verts'], out['verts'] + 1.0, atol=2e-6)
     assert torch.equal(out2['scores'], out['scores'])
-    # chunking must not matter: a batch larger than one super-chunk equals two half batches
+    # batching must not matter: the same frames in one 5000-frame call (launch pairs of up to 65,536 frames; the boundary of a
+    # launch pair is crossed by test_kernel_variants_bit_identical at 66,000 frames and by bench.py's 1M-frame config 3)
     big = engine.run(torch.cat([pose, pose]).cuda()[:5000], torch.cat([betas, betas]).cuda()[:5000],
                      torch.cat([trans, trans]).cuda()[:5000], add_info=EXAMPLE_INFO)
     assert torch.equal(big['verts'][:4096], out['verts']) and torch.equal(big['verts'][4096:], out['verts'][:904])

@@ -131,6 +131,11 @@ __device__ __forceinline__ void tcgen05_commit_pair(uint64_t* bar) {
 }
 // bulk tensor store shared -> global of one box; evict-first like the plain vertex stores
 __device__ __forceinline__ void tma_store_box(const CUtensorMap* map, const void* src, int c0, int c1, uint64_t policy) {
+#ifdef PRK_TMA_NOHINT
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+    return;
+#endif
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
                  ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "l"(policy)
                  : "memory");

@@ -22,6 +22,7 @@
 #include "prk_internal.h"
 
 #include <cuda_bf16.h>
+#include <cstdlib>
 
 namespace prk {
 
@@ -295,7 +296,7 @@ constexpr int kWarpsPerBlock = 8;        // joints-only variant
 constexpr int kWarpsPerBlockMesh = PRK_CHAIN_WPB;   // full-mesh variant: 16 consecutive frames per block, so that the block
                                          // writes its AskinT columns as 64-byte runs (two full sectors) instead of
                                          // 288 scattered 4-byte stores per frame
-constexpr int64_t kWarpVariantMaxFrames = 65536;   // above this the thread-per-frame kernel fills the GPU
+constexpr int64_t kWarpVariantMaxFrames = 49152;   // above this the thread-per-frame kernel is faster (full mesh, measured: 65,536 frames 159 vs 129 us; 16,384 frames 48 vs 80 us)
 
 template <bool kMesh>
 __global__ void __launch_bounds__((kMesh ? kWarpsPerBlockMesh : kWarpsPerBlock) * 32)
@@ -458,7 +459,8 @@ cudaError_t launch_pose_chain(const Model& m, const float* d_pose, const float* 
     if (d_trans) mode |= (center_idx < 0) ? MODE_TRANS_ALWAYS : MODE_TRANS_FLAG;
     const unsigned grid = (unsigned)((B + 127) / 128);
     const bool std_tree = m.pc.standard_tree != 0;
-    if (std_tree && B <= kWarpVariantMaxFrames) {   // latency-bound regime: one warp per frame
+    static const int64_t warp_max = [] { const char* e = getenv("PRK_CHAIN_WARP_MAX"); return e ? (int64_t)atoll(e) : kWarpVariantMaxFrames; }();
+    if (std_tree && B <= warp_max) {   // latency-bound regime: one warp per frame
         const int wpb = full_mesh ? kWarpsPerBlockMesh : kWarpsPerBlock;
         const unsigned g = (unsigned)((B + wpb - 1) / wpb);
 #define PRK_LAUNCH_W(MESH)                                                                                \

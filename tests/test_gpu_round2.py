@@ -420,6 +420,13 @@ def test_aligned_vertex_rows_equal_the_dense_layout_bit_for_bit(engine):
         engine.run(pose[lo:hi].cuda(), betas[lo:hi].cuda(), trans[lo:hi].cuda(), add_info=EXAMPLE_INFO, verts_out=big[lo:hi])
     torch.cuda.synchronize()
     assert torch.equal(big, ref)
+    # the host-buffer entry point with aligned rows
+    j = torch.empty(B, 24, 3).pin_memory()
+    sc = torch.empty(B, 32, dtype=torch.uint8).pin_memory()
+    v_host_path = _runtime.aligned_verts(B, torch.device('cuda:0'))
+    engine.run_host(pose.pin_memory(), betas.pin_memory(), trans.pin_memory(), EXAMPLE_INFO, None, j, sc, verts_out=v_host_path)
+    torch.cuda.synchronize()
+    assert torch.equal(v_host_path, ref)
 
 
 def test_aligned_rows_through_the_drop_in_layer_and_the_oracle():

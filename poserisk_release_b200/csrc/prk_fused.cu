@@ -956,6 +956,7 @@ cudaError_t launch_fused(const Model& m, const CUtensorMap& tmap_A, int64_t rows
     const int pair = fused_pair(rows_pad / FUSED_BM);
     // TMA vertex stores need 16-byte aligned rows: base and pitch; the dense reference layout (pitch 20,670) has neither
     const bool tma = tma_ok && m.nnz_groups == 1 && (vpitch % 4) == 0 && (reinterpret_cast<uintptr_t>(d_verts) & 15) == 0;
+    if (vpitch != NVC && !tma) return cudaErrorNotSupported;      // only the TMA path knows about padded rows (PRK_TMA_STORE=0 with a pitch)
 #define PRK_GO(G, P, T) launch_fused_t<G, P, T>(m, tmap_A, rows_pad, d_AskinT, d_off, B, d_verts, vpitch, s, pdl)
     if (m.nnz_groups == 1) {
         if (tma) return pair == 2 ? PRK_GO(1, 2, true) : PRK_GO(1, 1, true);

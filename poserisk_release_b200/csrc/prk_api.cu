@@ -3,6 +3,8 @@
 #include "prk_internal.h"
 
 #include <atomic>
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <mutex>
 #include <cmath>
 #include <cstdio>
@@ -370,30 +372,44 @@ int prk_model_create(prk_model** out, int device, const float* vt, const float* 
             for (int k = 0; k < NBETA; ++k) m->pc.Jdirs[(j * 3 + c) * NBETA + k] = (float)d[k];
         }
 
-    // K12 operand (prk_internal.h "K12 operand layout"): every hi/lo part stored once
+    // K12 operand (prk_internal.h "K12 operand layout"): fp16 main part, e4m3 cross-term parts, bf16 shape / template parts,
+    // everything times 2^S
+    float pd_max = 0.f;
+    for (size_t i = 0; i < (size_t)NVC * NPOSE; ++i) { const float a = fabsf(pd[i]); if (a > pd_max && std::isfinite(a)) pd_max = a; }
+    int S = 0;
+    if (pd_max > 0.f) { S = (int)floorf(log2f(16384.0f / pd_max)); if (S < 0) S = 0; if (S > 30) S = 30; }
+    m->blend_scale_log2 = S;
+    m->pc.rot_scale = ldexpf(1.0f, -S);
+    auto f16 = [](float x) { const __half hv = __float2half_rn(x); uint16_t u; memcpy(&u, &hv, 2); return u; };
+    auto f16f = [](uint16_t u) { __half hv; memcpy(&hv, &u, 2); return __half2float(hv); };
+    auto e4m3 = [](float x) { return (uint8_t)__nv_cvt_float_to_fp8(x, __NV_SATFINITE, __NV_E4M3); };
     std::vector<uint16_t> B2((size_t)GEMM_N * FUSED_K, 0), B2row(FUSED_K);
+    uint8_t* B2b = reinterpret_cast<uint8_t*>(B2.data());
     for (int n = 0; n < NVC; ++n) {
         uint16_t* row = B2row.data();
+        uint8_t* rowb = reinterpret_cast<uint8_t*>(row);
         std::fill(B2row.begin(), B2row.end(), (uint16_t)0);
         for (int pos = 1; pos < NJ; ++pos) {
             const int j = std_tree ? kSmplDfs[pos] : pos;
             for (int e = 0; e < 9; ++e) {
-                const float v = pd[(size_t)n * NPOSE + (j - 1) * 9 + e];
-                const uint16_t hi = f2bf(v);
-                row[9 * (pos - 1) + e] = hi;
-                row[FUSED_COL_LO + 9 * (pos - 1) + e] = f2bf(v - bf2f(hi));
+                const int k = 9 * (pos - 1) + e;
+                const float v = ldexpf(pd[(size_t)n * NPOSE + (j - 1) * 9 + e], S);
+                const uint16_t hi = f16(v);
+                row[k] = hi;
+                rowb[FUSED_X_BYTE0 + k] = e4m3(ldexpf(v, -12));          // meets fp8((F - Fh) 2^12)
+                rowb[FUSED_X_BYTE1 + k] = e4m3(v - f16f(hi));           // meets fp8(F)
             }
         }
         uint16_t sp[3];
         uint16_t* x = row + FUSED_COL_BETA;          // k-steps 26..29 (prk_internal.h "K12 operand layout")
-        for (int b = 0; b < NBETA; ++b) {
-            split3(sd[(size_t)n * NBETA + b], sp[0], sp[1], sp[2]);
-            x[b] = sp[0]; x[16 + b] = sp[0]; x[32 + b] = sp[1]; x[48 + b] = sp[2];
-            if (b < 5) x[NBETA + b] = sp[0]; else x[16 + NBETA + (b - 5)] = sp[0];
+        for (int bq = 0; bq < NBETA; ++bq) {
+            split3(ldexpf(sd[(size_t)n * NBETA + bq], S), sp[0], sp[1], sp[2]);
+            x[bq] = sp[0]; x[16 + bq] = sp[0]; x[32 + bq] = sp[1]; x[48 + bq] = sp[2];
+            if (bq < 5) x[NBETA + bq] = sp[0]; else x[16 + NBETA + (bq - 5)] = sp[0];
         }
-        split3(vt[n], sp[0], sp[1], sp[2]);
+        split3(ldexpf(vt[n], S), sp[0], sp[1], sp[2]);
         x[15] = sp[0]; x[32 + 15] = sp[1]; x[48 + 15] = sp[2];
-        for (int k = 0; k < FUSED_K; ++k) B2[fused_b2_index(n, k)] = row[k];   // into the pre-swizzled chunk images
+        for (int k = 0; k < FUSED_K * 2; ++k) B2b[fused_b2_byte_index(n, k)] = rowb[k];   // into the pre-swizzled chunk images
     }
 
     // compacted skinning weights
@@ -447,10 +463,11 @@ int prk_model_create(prk_model** out, int device, const float* vt, const float* 
     PRK_M(cudaMalloc(&m->d_wpack, wp.size()));
     PRK_M(cudaMemcpy(m->d_wpack, wp.data(), wp.size(), cudaMemcpyHostToDevice));
     {
-        std::vector<float> jc(72 + 720 + NBETA);
+        std::vector<float> jc(72 + 720 + NBETA + 1);
         memcpy(jc.data(), m->pc.J_template, 72 * 4);
         memcpy(jc.data() + 72, m->pc.Jdirs, 720 * 4);
         memcpy(jc.data() + 792, m->pc.model_betas, NBETA * 4);
+        jc[802] = m->pc.rot_scale;
         PRK_M(cudaMalloc(&m->d_Jc, jc.size() * 4));
         PRK_M(cudaMemcpy(m->d_Jc, jc.data(), jc.size() * 4, cudaMemcpyHostToDevice));
     }
@@ -808,7 +825,7 @@ int prk_debug_blend(prk_model* model, const float* d_pose, const float* d_betas,
         PRK_CUDA(launch_blend_simt(*m, d_arows, B, d_vposed, s));
     } else {
         // the product kernel with identity skinning transforms and no offset: vertices = v_posed
-        PRK_CUDA(launch_identity_askin(d_askin, d_off, rows_pad, s));
+        PRK_CUDA(launch_identity_askin(*m, d_askin, d_off, rows_pad, s));
         CUtensorMap tmA;
         int rc = encode_tmap_2d_bf16(&tmA, d_arows, (uint64_t)rows_pad, FUSED_K, FUSED_BM, 64);
         if (rc != PRK_OK) return rc;

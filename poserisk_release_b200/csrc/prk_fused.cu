@@ -38,6 +38,8 @@
 // are time-bounded (prk_tc.cuh).
 #include "prk_internal.h"
 #include "prk_tc.cuh"
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
 
 #include <atomic>
 #include <cstdlib>
@@ -167,37 +169,29 @@ __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" :
 __host__ __device__ constexpr uint32_t a_step_off(int a) { return (uint32_t)((a >> 2) * (kAChunkBytes >> 4) + (a & 3) * 2); }
 // kind::f16 MMA with the two shared-memory descriptors given as (low word, common high word):
 // all tiles here share SBO / version / swizzle, only the 14-bit start address differs.
-template <int kPair>
-__device__ __forceinline__ void umma_bf16_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc,
-                                               bool accumulate) {
-    if (kPair == 2) {
-        const uint32_t acc = accumulate ? 1u : 0u;
-        asm volatile(
-            "{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\t"
-            "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
-            "setp.ne.b32 p, %5, 0;\n\t"
-            "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}"
-            ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(acc)
-            : "memory");
-        return;
-    }
-    if (accumulate)
-        asm volatile(
-            "{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\t"
-            "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
-            "setp.ne.b32 p, 1, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
-            ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc)
-            : "memory");
-    else
-        asm volatile(
-            "{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\t"
-            "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
-            "setp.ne.b32 p, 0, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
-            ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc)
-            : "memory");
+// One MMA of a K12 k-step: D[tmem] (+)= A[smem] * B[smem]^T over 32 bytes of K per row.  kF8: kind::f8f6f4 (32 e4m3 elements),
+// else kind::f16 (16 fp16 or bf16 elements, chosen by the instruction descriptor).  The two shared-memory descriptors are given as
+// (low word, common high word): all tiles share SBO / version / swizzle, only the 14-bit start address differs.
+template <int kPair, bool kF8>
+__device__ __forceinline__ void umma_step(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc,
+                                          bool accumulate) {
+    const uint32_t acc = accumulate ? 1u : 0u;
+#define PRK_UMMA(GROUP, KIND)                                                                       \
+    asm volatile(                                                                                   \
+        "{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\t"                                              \
+        "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"                                        \
+        "setp.ne.b32 p, %5, 0;\n\t"                                                                 \
+        "tcgen05.mma.cta_group::" GROUP ".kind::" KIND " [%0], da, db, %4, p;\n\t}"                  \
+        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(acc) : "memory")
+    if (kPair == 2) { if (kF8) PRK_UMMA("2", "f8f6f4"); else PRK_UMMA("2", "f16"); }
+    else            { if (kF8) PRK_UMMA("1", "f8f6f4"); else PRK_UMMA("1", "f16"); }
+#undef PRK_UMMA
 }
+// instruction descriptors (D = fp32, K-major operands): kind::f16 with fp16 inputs / with bf16 inputs, kind::f8f6f4 with e4m3
+__host__ __device__ constexpr uint32_t idesc_common(int M, int N) { return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24); }
+__host__ __device__ constexpr uint32_t idesc_fp16(int M, int N) { return idesc_common(M, N); }                          // a/b format 0 = F16
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) { return idesc_common(M, N) | (1u << 7) | (1u << 10); }  // 1 = BF16
+__host__ __device__ constexpr uint32_t idesc_e4m3(int M, int N) { return idesc_common(M, N); }                          // 0 = E4M3
 
 // Knock-out builds for finding out where the time goes: -DPRK_KNOCK=<mask> removes one side of the pipeline at
 // COMPILE time (run-time switches perturb the unrolled epilogue too much to be trusted; profiles/r2_ab_runs.txt):
@@ -396,7 +390,8 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
         // ===== MMA issuer (whole warp converged, one elected lane issues) =====
         // Everything about a k-step is a compile-time constant (both loops fully unrolled) and every
         // run-time operand is warp-uniform, so an MMA costs a couple of uniform adds plus the issue.
-        constexpr uint32_t idesc = make_idesc(FUSED_BM * kPair, FUSED_BN);
+        constexpr uint32_t id16 = idesc_fp16(FUSED_BM * kPair, FUSED_BN), idbf = idesc_bf16(FUSED_BM * kPair, FUSED_BN),
+                           id8 = idesc_e4m3(FUSED_BM * kPair, FUSED_BN);
         const uint64_t adesc0 = make_smem_desc(smem_u32(sA));
         const uint32_t a_lo = (uint32_t)adesc0, d_hi = (uint32_t)(adesc0 >> 32);
         const uint32_t b_lo0 = (uint32_t)make_smem_desc(smem_u32(sB));
@@ -427,16 +422,15 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
                     for (int s = 0; s < (DBG(1) ? 0 : 4); ++s) {
                         const int b = c * 4 + s;                  // B' k-step (compile-time)
                         const uint32_t bl = b_lo + 2 * s;
-                        if (b < FUSED_POSE_STEPS) {               // posedirs hi: x pose hi, x pose lo
-                            umma_bf16_lohi<kPair>(d_tmem, a_lo + a_step_off(b), bl, d_hi, idesc, b != 0);
-                            umma_bf16_lohi<kPair>(d_tmem, a_lo + a_step_off(FUSED_POSE_STEPS + b), bl, d_hi, idesc, true);
-                        } else if (b < 2 * FUSED_POSE_STEPS) {    // posedirs lo: x pose hi
-                            umma_bf16_lohi<kPair>(d_tmem, a_lo + a_step_off(b - FUSED_POSE_STEPS), bl, d_hi, idesc, true);
-                        } else if (b < FUSED_B_STEPS) {           // the five beta x shapedirs (+ template) products
+                        if (b < FUSED_POSE_STEPS) {               // fp16 main part: Fh . Ph
+                            umma_step<kPair, false>(d_tmem, a_lo + a_step_off(b), bl, d_hi, id16, b != 0);
+                        } else if (b < 2 * FUSED_POSE_STEPS) {    // e4m3 cross terms: (F - Fh) . P + F . (P - Ph), K = 32
+                            umma_step<kPair, true>(d_tmem, a_lo + a_step_off(b), bl, d_hi, id8, true);
+                        } else if (b < FUSED_B_STEPS) {           // the five beta x shapedirs (+ template) products, bf16
                             constexpr int A26 = 2 * FUSED_POSE_STEPS, A27 = A26 + 1;
                             const int q = b - 2 * FUSED_POSE_STEPS;      // 0: s1|s1a|t1  1: s1|s1b  2: s2|t2  3: s3|t3
-                            if (q != 1) umma_bf16_lohi<kPair>(d_tmem, a_lo + a_step_off(A26), bl, d_hi, idesc, true);
-                            if (q == 1 || q == 2) umma_bf16_lohi<kPair>(d_tmem, a_lo + a_step_off(A27), bl, d_hi, idesc, true);
+                            if (q != 1) umma_step<kPair, false>(d_tmem, a_lo + a_step_off(A26), bl, d_hi, idbf, true);
+                            if (q == 1 || q == 2) umma_step<kPair, false>(d_tmem, a_lo + a_step_off(A27), bl, d_hi, idbf, true);
                         }
                     }
                     if (kPair == 2) {
@@ -793,39 +787,42 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
 }
 
 // ---- verification only (prk_debug_blend) ------------------------------------------------
-// The same bf16 operands and the same 45 k-step pairs as the tensor-core path, plain FFMA.
+// The same operand bytes and the same 31 k-step products as the tensor-core path (prk_internal.h "K12 operand layout"), plain FFMA.
 __global__ void __launch_bounds__(256)
 blend_simt_kernel(const uint16_t* __restrict__ Arows, const uint16_t* __restrict__ B2, int64_t rows,
-                  float* __restrict__ vposed) {
+                  float* __restrict__ vposed, float rot_scale) {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;   // vertex coordinate
     const int64_t f = blockIdx.y;
     if (n >= NVC || f >= rows) return;
     const uint16_t* a = Arows + f * FUSED_K;
+    const uint8_t* ab = reinterpret_cast<const uint8_t*>(a);
+    const uint8_t* bb = reinterpret_cast<const uint8_t*>(B2);
     auto bf = [](uint16_t v) { return __uint_as_float((uint32_t)v << 16); };
-    auto step = [&](int sa, int sb, float acc) {
+    auto hf = [](uint16_t v) { return __half2float(__ushort_as_half(v)); };
+    auto f8 = [](uint8_t v) { return __half2float(__half(__nv_cvt_fp8_to_halfraw(v, __NV_E4M3))); };
+    float acc = 0.f;
+    for (int k = 0; k < 16 * FUSED_POSE_STEPS; ++k)                   // fp16 main part
+        acc = fmaf(hf(a[k]), hf(B2[fused_b2_index(n, k)]), acc);
+    for (int k = FUSED_X_BYTE0; k < FUSED_X_BYTE0 + 2 * FUSED_COL_LO; ++k)   // e4m3 cross terms, byte meets byte
+        acc = fmaf(f8(ab[k]), f8(bb[fused_b2_byte_index(n, k)]), acc);
+    auto step = [&](int sa, int sb, float acc) {                      // bf16 beta / template products
         for (int k = 0; k < 16; ++k) acc = fmaf(bf(a[sa * 16 + k]), bf(B2[fused_b2_index(n, sb * 16 + k)]), acc);
         return acc;
     };
-    float acc = 0.f;
-    for (int i = 0; i < FUSED_POSE_STEPS; ++i) {
-        acc = step(i, i, acc);                                   // hi x hi
-        acc = step(FUSED_POSE_STEPS + i, i, acc);                // lo x hi
-        acc = step(i, FUSED_POSE_STEPS + i, acc);                // hi x lo
-    }
     const int A26 = 2 * FUSED_POSE_STEPS, A27 = A26 + 1, B26 = A26;
     acc = step(A26, B26, acc); acc = step(A27, B26 + 1, acc);
     acc = step(A26, B26 + 2, acc); acc = step(A27, B26 + 2, acc);
     acc = step(A26, B26 + 3, acc);
-    vposed[f * NVC + n] = acc;
+    vposed[f * NVC + n] = acc * rot_scale;
 }
 
-// A_j = identity for every joint (columns R00 = 0, R11 = 3, R22 = 10 of each group of 12), off = 0
+// A_j = 2^-S identity for every joint (columns R00 = 0, R11 = 3, R22 = 10 of each group of 12), off = 0
 __global__ void __launch_bounds__(256)
-identity_askin_kernel(float* __restrict__ AskinT, float* __restrict__ off, int64_t rows_pad) {
+identity_askin_kernel(float* __restrict__ AskinT, float* __restrict__ off, int64_t rows_pad, float rot_scale) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < rows_pad * FUSED_ASKIN_COLS) {
         const int col = (int)((i >> 5) % FUSED_ASKIN_COLS) % 12;
-        AskinT[i] = (col == 0 || col == 3 || col == 10) ? 1.0f : 0.0f;
+        AskinT[i] = (col == 0 || col == 3 || col == 10) ? rot_scale : 0.0f;
     }
     if (i < rows_pad * 3) off[i] = 0.0f;
 }
@@ -835,14 +832,14 @@ identity_askin_kernel(float* __restrict__ AskinT, float* __restrict__ off, int64
 cudaError_t launch_blend_simt(const Model& m, const uint16_t* d_Arows, int64_t rows, float* d_vposed, cudaStream_t s) {
     if (rows == 0) return cudaSuccess;
     dim3 grid((NVC + 255) / 256, (unsigned)rows);
-    blend_simt_kernel<<<grid, 256, 0, s>>>(d_Arows, m.d_B2, rows, d_vposed);
+    blend_simt_kernel<<<grid, 256, 0, s>>>(d_Arows, m.d_B2, rows, d_vposed, m.pc.rot_scale);
     count_launch();
     return cudaGetLastError();
 }
 
-cudaError_t launch_identity_askin(float* d_AskinT, float* d_off, int64_t rows_pad, cudaStream_t s) {
+cudaError_t launch_identity_askin(const Model& m, float* d_AskinT, float* d_off, int64_t rows_pad, cudaStream_t s) {
     const int64_t n = rows_pad * FUSED_ASKIN_COLS;
-    identity_askin_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_AskinT, d_off, rows_pad);
+    identity_askin_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_AskinT, d_off, rows_pad, m.pc.rot_scale);
     count_launch();
     return cudaGetLastError();
 }

@@ -18,31 +18,38 @@ constexpr int NVC = NV * 3;             // 20670 vertex coordinates
 constexpr int GEMM_N = 20736;           // 20670 vertex coordinates padded to 216 tiles of 96
 
 // ---- fused blend + skinning geometry (DESIGN.md "K12", prk_fused.cu) ---------
-// K12 operand layout: the hi/lo parts of every factor are stored ONCE, in k-steps of 16 bf16.
-// With (b1,b2,b3) / (s1,s2,s3) / (t1,t2,t3) the 3-way bf16 splits of a beta, a shapedirs entry and a
-// v_template entry:
-//   A' row (per frame, 28 k-steps = 7 chunks of 64 columns):
-//     steps  0..12  pose features hi   (207 + 1 zero column; feature p = 9*(pos-1)+e, pos = DFS position)
-//     steps 13..25  pose features lo
-//     step  26      b1[0..9] | b3[0..4] | 1.0
-//     step  27      b2[0..9] | b3[5..9] | 0
+// K12 operand layout: rows of k-steps of 32 bytes (16 x 16-bit or 32 x 8-bit elements), each part stored ONCE.
+// Everything on the B' side is multiplied by 2^S (S = prk_model::blend_scale_log2, chosen so that max|posedirs| 2^S <= 2^14);
+// the accumulator holds 2^S v_posed and the pose kernel hands the skinning rotations over as 2^-S R, so nothing is rescaled
+// in the epilogue.  With F = a pose feature (R - I entry), P = a posedirs entry 2^S, (b1,b2,b3) / (s1,s2,s3) / (t1,t2,t3) the
+// 3-way bf16 splits of a beta, a shapedirs entry 2^S and a v_template entry 2^S:
+//   A' row (per frame, 28 k-steps = 7 chunks of 128 bytes):
+//     steps  0..12  fp16   Fh = fp16(F)                          (207 + 1 zero; feature p = 9*(pos-1)+e, pos = DFS position)
+//     steps 13..25  e4m3   208 bytes fp8((F - Fh) 2^12)  |  208 bytes fp8(F)
+//     step  26      bf16   b1[0..9] | b3[0..4] | 1.0
+//     step  27      bf16   b2[0..9] | b3[5..9] | 0
 //   B' row (per vertex coordinate, 30 k-steps, rows padded to 8 chunks):
-//     steps  0..12  posedirs hi            steps 13..25  posedirs lo
-//     step  26      s1[0..9] | s1[0..4] | t1        (x A26: b1.s1 + b3.s1 (first half) + t1)
-//     step  27      s1[0..9] | s1[5..9] | 0         (x A27: b2.s1 + b3.s1 (second half))
-//     step  28      s2[0..9] | 0 x 5    | t2        (x A26: b1.s2 + t2;  x A27: b2.s2)
-//     step  29      s3[0..9] | 0 x 5    | t3        (x A26: b1.s3 + t3)
-// The MMA issuer pairs  A'hi x B'hi,  A'lo x B'hi,  A'hi x B'lo  and the five beta products above:
-// 44 MMAs of K=16 per tile.  Pose features: hi*hi + lo*hi + hi*lo; betas x shapedirs: the six
-// products b_p.s_q with p+q <= 4 (1-based); v_template exact in three terms.
+//     steps  0..12  fp16   Ph = fp16(P)
+//     steps 13..25  e4m3   208 bytes fp8(P 2^-12)        |  208 bytes fp8(P - Ph)
+//     step  26      bf16   s1[0..9] | s1[0..4] | t1        (x A26: b1.s1 + b3.s1 (first half) + t1)
+//     step  27      bf16   s1[0..9] | s1[5..9] | 0         (x A27: b2.s1 + b3.s1 (second half))
+//     step  28      bf16   s2[0..9] | 0 x 5    | t2        (x A26: b1.s2 + t2;  x A27: b2.s2)
+//     step  29      bf16   s3[0..9] | 0 x 5    | t3        (x A26: b1.s3 + t3)
+// MMAs per tile: A'[b] x B'[b] for b = 0..12 (kind::f16, fp16: Fh.Ph), for b = 13..25 (kind::f8f6f4, K = 32: the two cross terms
+// (F - Fh).P + F.(P - Ph), byte i of one row meeting byte i of the other) and the five beta products (kind::f16, bf16): 31 MMAs
+// instead of the 44 of the bf16 hi.hi + lo.hi + hi.lo scheme of round 1.  The cross terms are 2^-12 of the main one, so the 4
+// significant bits of e4m3 leave 2^-15.5 of the pose blend shapes as error: 2.3e-7 .. 4.7e-7 of the vertex range on the
+// config-2 / pose x 0.6 / pose x 1.2 / large-beta cases (numpy model) against 0.8e-7 .. 2.0e-7 before and a budget of 2e-6.
 constexpr int FUSED_K = 512;                             // bf16 columns per stored row (A' rows use 448 of them)
 constexpr int FUSED_POSE_STEPS = 13;
 constexpr int FUSED_A_STEPS = 2 * FUSED_POSE_STEPS + 2;  // 28
 constexpr int FUSED_B_STEPS = 2 * FUSED_POSE_STEPS + 4;  // 30
 constexpr int FUSED_A_CHUNKS = FUSED_A_STEPS / 4;        // 7 resident chunks of 64 columns
 constexpr int FUSED_B_CHUNKS = (FUSED_B_STEPS + 3) / 4;  // 8 streamed chunks (the last holds two k-steps)
-constexpr int FUSED_COL_LO = 16 * FUSED_POSE_STEPS;      // 208
+constexpr int FUSED_COL_LO = 16 * FUSED_POSE_STEPS;      // 208: first 16-bit column of the e4m3 block (byte 416 of a row)
 constexpr int FUSED_COL_BETA = 2 * FUSED_COL_LO;         // 416
+constexpr int FUSED_X_BYTE0 = 2 * FUSED_COL_LO;          // byte offset of the first e4m3 sub-block (208 bytes) in a row
+constexpr int FUSED_X_BYTE1 = FUSED_X_BYTE0 + FUSED_COL_LO;   // ... and of the second one
 constexpr int FUSED_BM = 128;            // frames per tile (TMEM lanes)
 constexpr int FUSED_VT = 32;             // vertices per tile
 constexpr int FUSED_BN = FUSED_VT * 3;   // 96 accumulator columns
@@ -62,6 +69,11 @@ __host__ __device__ constexpr size_t fused_b2_index(int n, int k) {
     return (((size_t)tile * FUSED_B_CHUNKS + chunk) * FUSED_BN + r) * 64 + (size_t)((((kk >> 3) ^ (r & 7)) << 3) | (kk & 7));
 }
 
+// byte index of byte `byte` (0..1023) of B' row n inside the same chunk images (16-byte units swizzled as above)
+__host__ __device__ constexpr size_t fused_b2_byte_index(int n, int byte) {
+    return fused_b2_index(n, byte >> 1) * 2 + (size_t)(byte & 1);
+}
+
 // Rest joints as an affine function of betas: J = J_template + Jdirs * beta
 // (folds J_regressor @ (v_template + shapedirs beta), smpl_layer.py:91,95).
 struct PoseConsts {
@@ -70,6 +82,7 @@ struct PoseConsts {
     float model_betas[NBETA];
     int32_t parents[NJ];
     int32_t standard_tree;         // 1: parents == SMPL kintree (static unroll path)
+    float rot_scale;               // 2^-S: the skinning rotations handed to the vertex kernel are scaled by it (the accumulator holds 2^S v_posed)
 };
 
 }  // namespace prk
@@ -80,6 +93,7 @@ struct prk_model {
     int sm_count = 0;
     int nnz_groups = 1;            // ceil(max non-zero weights per vertex / 4)
     int max_weights = 0;
+    int blend_scale_log2 = 0;      // S: every B' operand is multiplied by 2^S
     prk::PoseConsts pc;                 // host copy, passed by value to the pose kernel
     // device buffers
     float* d_Jc = nullptr;         // J_template[72] | Jdirs[720] | model_betas[10] (lane-per-joint pose kernel)
@@ -126,7 +140,7 @@ cudaError_t launch_fused(const Model& m, const CUtensorMap& tmap_A, int64_t rows
 
 // verification hooks of prk_debug_blend: plain FFMA evaluation of the same bf16 operands, identity A_j tiles
 cudaError_t launch_blend_simt(const Model& m, const uint16_t* d_Arows, int64_t rows, float* d_vposed, cudaStream_t s);
-cudaError_t launch_identity_askin(float* d_AskinT, float* d_off, int64_t rows_pad, cudaStream_t s);
+cudaError_t launch_identity_askin(const Model& m, float* d_AskinT, float* d_off, int64_t rows_pad, cudaStream_t s);
 
 // K3: Euler angles + REBA/RULA
 // --debug_joints list as a by-value kernel parameter: bit j of `mask` = joint j is listed, slot[j] = its position

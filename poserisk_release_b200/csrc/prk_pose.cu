@@ -22,6 +22,8 @@
 #include "prk_internal.h"
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <cstdlib>
 
 namespace prk {
@@ -37,6 +39,13 @@ __host__ __device__ constexpr int smpl_dfs(int pos) {
 }
 
 __device__ __forceinline__ uint16_t bf16_bits(float x) { return __bfloat16_as_ushort(__float2bfloat16_rn(x)); }
+// the three parts of a pose feature F in the K12 operand row (prk_internal.h): fp16(F), e4m3((F - fp16(F)) 2^12), e4m3(F)
+__device__ __forceinline__ void feature_parts(float v, uint16_t& hi, uint8_t& lo8, uint8_t& hi8) {
+    const __half h = __float2half_rn(v);
+    hi = __half_as_ushort(h);
+    lo8 = (uint8_t)__nv_cvt_float_to_fp8((v - __half2float(h)) * 4096.0f, __NV_SATFINITE, __NV_E4M3);
+    hi8 = (uint8_t)__nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E4M3);
+}
 __device__ __forceinline__ float bf16_val(uint16_t b) { return __uint_as_float((uint32_t)b << 16); }
 
 // Streams bf16 values into a global row, 8 at a time (one 16-byte store).
@@ -50,6 +59,13 @@ struct RowWriter {
         if (n & 1) buf[w] |= (uint32_t)v << 16; else buf[w] = v;
         ++n;
         if ((n & 7) == 0) { if (live) *dst = make_uint4(buf[0], buf[1], buf[2], buf[3]); ++dst; }
+    }
+    // the same stream in bytes (the e4m3 blocks): n counts 16-bit slots, nb the bytes of the slot being filled
+    int nb;
+    uint32_t half_word;
+    __device__ __forceinline__ void push8(uint8_t v) {
+        if (nb == 0) { half_word = v; nb = 1; }
+        else { nb = 0; push((uint16_t)(half_word | ((uint32_t)v << 8))); }
     }
 };
 
@@ -167,11 +183,15 @@ pose_chain_kernel(const __grid_constant__ PoseConsts pc, const float* __restrict
     // K12 operand row: a hi stream (column 0) and a lo stream (column 208)
     RowWriter rw, rw_lo;
     rw.dst = kMesh ? reinterpret_cast<uint4*>(Arows + f * FUSED_K) : nullptr;
-    rw.n = 0;
+    rw.n = 0; rw.nb = 0; rw.half_word = 0;
     rw.live = live;
     rw.buf[0] = rw.buf[1] = rw.buf[2] = rw.buf[3] = 0;
     rw_lo = rw;
-    if (kMesh) rw_lo.dst = reinterpret_cast<uint4*>(Arows + f * FUSED_K + FUSED_COL_LO);
+    RowWriter rw_hi8 = rw;                       // three streams: fp16 at byte 0, e4m3 residuals at byte 416, e4m3 features at byte 624
+    if (kMesh) {
+        rw_lo.dst = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(Arows + f * FUSED_K) + FUSED_X_BYTE0);
+        rw_hi8.dst = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(Arows + f * FUSED_K) + FUSED_X_BYTE1);
+    }
 
     const float* p = tile + lane * kChainPitch;
     float* jout = tile + lane * kChainPitch;
@@ -187,16 +207,14 @@ pose_chain_kernel(const __grid_constant__ PoseConsts pc, const float* __restrict
         float R[9];
         smpl_rodrigues(p[j * 3 + 0], p[j * 3 + 1], p[j * 3 + 2], R);      // (read before jout[j * 3 ..] is written)
 
-        if (kMesh && pos > 0) {   // pose_map = R - I, split hi/lo (tensutils.py:41-48)
-            uint16_t hi[9], lo[9];
+        if (kMesh && pos > 0) {   // pose_map = R - I (tensutils.py:41-48) in the three parts of the K12 operand row
 #pragma unroll
             for (int e = 0; e < 9; ++e) {
                 const float v = R[e] - ((e == 0 || e == 4 || e == 8) ? 1.0f : 0.0f);
-                hi[e] = bf16_bits(v);
-                lo[e] = bf16_bits(v - bf16_val(hi[e]));
+                uint16_t hi; uint8_t lo8, hi8;
+                feature_parts(v, hi, lo8, hi8);
+                rw.push(hi); rw_lo.push8(lo8); rw_hi8.push8(hi8);
             }
-#pragma unroll
-            for (int e = 0; e < 9; ++e) { rw.push(hi[e]); rw_lo.push(lo[e]); }
         }
 
         // rest joint: J = J_template + Jdirs * beta
@@ -223,8 +241,9 @@ pose_chain_kernel(const __grid_constant__ PoseConsts pc, const float* __restrict
             float* dst = Askin + ((f >> 5) * FUSED_ASKIN_COLS + j * 12) * 32 + (f & 31);
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
-                dst[askin_col(r, 0) * 32] = G[j][r * 4 + 0]; dst[askin_col(r, 1) * 32] = G[j][r * 4 + 1];
-                dst[askin_col(r, 2) * 32] = G[j][r * 4 + 2]; dst[askin_col(r, 3) * 32] = skin_t(G[j], r, J[j][0], J[j][1], J[j][2]);
+                // rotations times 2^-S (exact): the blend accumulator holds 2^S v_posed
+                dst[askin_col(r, 0) * 32] = G[j][r * 4 + 0] * pc.rot_scale; dst[askin_col(r, 1) * 32] = G[j][r * 4 + 1] * pc.rot_scale;
+                dst[askin_col(r, 2) * 32] = G[j][r * 4 + 2] * pc.rot_scale; dst[askin_col(r, 3) * 32] = skin_t(G[j], r, J[j][0], J[j][1], J[j][2]);
             }
         }
     }
@@ -252,7 +271,7 @@ pose_chain_kernel(const __grid_constant__ PoseConsts pc, const float* __restrict
 
     if (kMesh) {
         if (live) { off[f * 3 + 0] = o0; off[f * 3 + 1] = o1; off[f * 3 + 2] = o2; }
-        rw.push(0); rw_lo.push(0);                   // columns 207 / 415 close the hi / lo blocks
+        rw.push(0); rw_lo.push8(0); rw_hi8.push8(0);   // element 207 closes the fp16 block and both e4m3 blocks
         rw.dst = reinterpret_cast<uint4*>(Arows + f * FUSED_K + FUSED_COL_BETA);
         uint16_t bs[3][NBETA];                       // 3-way split of every beta
 #pragma unroll
@@ -300,7 +319,7 @@ constexpr int64_t kWarpVariantMaxFrames = 49152;   // above this the thread-per-
 
 template <bool kMesh>
 __global__ void __launch_bounds__((kMesh ? kWarpsPerBlockMesh : kWarpsPerBlock) * 32)
-pose_chain_warp_kernel(const float* __restrict__ Jc /* J_template[72] | Jdirs[720] | model_betas[10] */,
+pose_chain_warp_kernel(const float* __restrict__ Jc /* J_template[72] | Jdirs[720] | model_betas[10] | rot_scale */,
                        const float* __restrict__ pose, const float* __restrict__ betas,
                        const float* __restrict__ trans, const BatchFlags* __restrict__ flags, uint32_t mode,
                        int center_idx, int64_t B, uint16_t* __restrict__ Arows, float* __restrict__ Askin,
@@ -367,10 +386,11 @@ pose_chain_warp_kernel(const float* __restrict__ Jc /* J_template[72] | Jdirs[72
     if (!kMesh) return;
 
     if (active) {   // A_j columns of this frame into the block's staging tile [12 * joint + e][frame in block]
+        const float rs = Jc[72 + 720 + NBETA];   // 2^-S on the rotations (exact): the blend accumulator holds 2^S v_posed
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
-            s_askin[j * 12 + askin_col(r, 0)][warp] = G[r * 4 + 0]; s_askin[j * 12 + askin_col(r, 1)][warp] = G[r * 4 + 1];
-            s_askin[j * 12 + askin_col(r, 2)][warp] = G[r * 4 + 2];
+            s_askin[j * 12 + askin_col(r, 0)][warp] = G[r * 4 + 0] * rs; s_askin[j * 12 + askin_col(r, 1)][warp] = G[r * 4 + 1] * rs;
+            s_askin[j * 12 + askin_col(r, 2)][warp] = G[r * 4 + 2] * rs;
             s_askin[j * 12 + askin_col(r, 3)][warp] = skin_t(G, r, J[0], J[1], J[2]);
         }
     }
@@ -388,13 +408,15 @@ pose_chain_warp_kernel(const float* __restrict__ Jc /* J_template[72] | Jdirs[72
 
     // A' row assembled in shared memory, then written with 16-byte stores
     uint16_t* row = s_row[warp];
-    if (active && j > 0) {
+    uint8_t* rowb = reinterpret_cast<uint8_t*>(row);
+    if (active && j > 0) {   // the three parts of every pose feature (prk_internal.h "K12 operand layout")
         const int base = 9 * (c_dfs_pos[j] - 1);
 #pragma unroll
         for (int e = 0; e < 9; ++e) {
             const float v = R[e] - ((e == 0 || e == 4 || e == 8) ? 1.0f : 0.0f);
-            const uint16_t hi = bf16_bits(v);
-            row[base + e] = hi; row[FUSED_COL_LO + base + e] = bf16_bits(v - bf16_val(hi));
+            uint16_t hi; uint8_t lo8, hi8;
+            feature_parts(v, hi, lo8, hi8);
+            row[base + e] = hi; rowb[FUSED_X_BYTE0 + base + e] = lo8; rowb[FUSED_X_BYTE1 + base + e] = hi8;
         }
     }
     if (lane < NBETA) {   // k-step 26: b1 | b3[0..4] | 1.0      k-step 27: b2 | b3[5..9] | 0
@@ -407,7 +429,7 @@ pose_chain_warp_kernel(const float* __restrict__ Jc /* J_template[72] | Jdirs[72
     } else if (lane == NBETA) {
         row[FUSED_COL_BETA + 15] = 0x3F80; row[FUSED_COL_BETA + 31] = 0;
     }
-    if (lane == 31) { row[FUSED_COL_LO - 1] = 0; row[FUSED_COL_BETA - 1] = 0; }
+    if (lane == 31) { row[FUSED_COL_LO - 1] = 0; rowb[FUSED_X_BYTE0 + 207] = 0; rowb[FUSED_X_BYTE1 + 207] = 0; }
     __syncwarp();
     const uint4* src = reinterpret_cast<const uint4*>(row);
     uint4* dst = reinterpret_cast<uint4*>(Arows + f * FUSED_K);

@@ -140,25 +140,6 @@ int encode_tmap_2d_bf16(CUtensorMap* out, const void* gptr, uint64_t rows, uint6
 }
 
 // ---- host-side bf16 helpers --------------------------------------------------
-static uint16_t f2bf(float x) {   // round to nearest even
-    uint32_t u;
-    memcpy(&u, &x, 4);
-    if ((u & 0x7F800000u) == 0x7F800000u) return (uint16_t)(u >> 16);   // inf / nan: truncate
-    u += 0x7FFFu + ((u >> 16) & 1u);
-    return (uint16_t)(u >> 16);
-}
-static float bf2f(uint16_t b) {
-    uint32_t u = (uint32_t)b << 16;
-    float x;
-    memcpy(&x, &u, 4);
-    return x;
-}
-static void split3(float v, uint16_t& h, uint16_t& m, uint16_t& l) {
-    h = f2bf(v);
-    const float r1 = v - bf2f(h);
-    m = f2bf(r1);
-    l = f2bf(r1 - bf2f(m));
-}
 
 static const int kSmplParents[NJ] = {-1, 0, 0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 9, 9, 12, 13, 14, 16, 17, 18, 19, 20, 21};
 static const int kSmplDfs[NJ] = {0, 1, 4, 7, 10, 2, 5, 8, 11, 3, 6, 9, 12, 15, 13, 16, 18, 20, 22, 14, 17, 19, 21, 23};
@@ -377,7 +358,16 @@ int prk_model_create(prk_model** out, int device, const float* vt, const float* 
     float pd_max = 0.f;
     for (size_t i = 0; i < (size_t)NVC * NPOSE; ++i) { const float a = fabsf(pd[i]); if (a > pd_max && std::isfinite(a)) pd_max = a; }
     int S = 0;
-    if (pd_max > 0.f) { S = (int)floorf(log2f(16384.0f / pd_max)); if (S < 0) S = 0; if (S > 30) S = 30; }
+    float sd_max = 0.f;
+    for (size_t i = 0; i < (size_t)NVC * NBETA; ++i) { const float a = fabsf(sd[i]); if (a > sd_max && std::isfinite(a)) sd_max = a; }
+    {   // max|posedirs| 2^S <= 2^14 (e4m3 range of the cross terms), max|shapedirs| 2^S <= 2^15 (fp16 range)
+        float lim = 1e30f;
+        if (pd_max > 0.f) lim = fminf(lim, 16384.0f / pd_max);
+        if (sd_max > 0.f) lim = fminf(lim, 32768.0f / sd_max);
+        S = lim < 1e30f ? (int)floorf(log2f(lim)) : 0;
+        if (S < 0) S = 0;
+        if (S > 30) S = 30;
+    }
     m->blend_scale_log2 = S;
     m->pc.rot_scale = ldexpf(1.0f, -S);
     auto f16 = [](float x) { const __half hv = __float2half_rn(x); uint16_t u; memcpy(&u, &hv, 2); return u; };
@@ -400,15 +390,14 @@ int prk_model_create(prk_model** out, int device, const float* vt, const float* 
                 rowb[FUSED_X_BYTE1 + k] = e4m3(v - f16f(hi));           // meets fp8(F)
             }
         }
-        uint16_t sp[3];
-        uint16_t* x = row + FUSED_COL_BETA;          // k-steps 26..29 (prk_internal.h "K12 operand layout")
+        uint16_t* x = row + FUSED_COL_BETA;          // k-steps 26, 27 (prk_internal.h "K12 operand layout"): sh | u1 u2 u3 | 0 0 0,  sl | 0 x 6
         for (int bq = 0; bq < NBETA; ++bq) {
-            split3(ldexpf(sd[(size_t)n * NBETA + bq], S), sp[0], sp[1], sp[2]);
-            x[bq] = sp[0]; x[16 + bq] = sp[0]; x[32 + bq] = sp[1]; x[48 + bq] = sp[2];
-            if (bq < 5) x[NBETA + bq] = sp[0]; else x[16 + NBETA + (bq - 5)] = sp[0];
+            const float v = ldexpf(sd[(size_t)n * NBETA + bq], S);
+            x[bq] = f16(v);
+            x[16 + bq] = f16(v - f16f(x[bq]));
         }
-        split3(ldexpf(vt[n], S), sp[0], sp[1], sp[2]);
-        x[15] = sp[0]; x[32 + 15] = sp[1]; x[48 + 15] = sp[2];
+        float u = ldexpf(vt[n], S - 15);              // v_template 2^S = 2^15 (u1 + u2 + u3)
+        for (int q = 0; q < 3; ++q) { x[NBETA + q] = f16(u); u -= f16f(x[NBETA + q]); }
         for (int k = 0; k < FUSED_K * 2; ++k) B2b[fused_b2_byte_index(n, k)] = rowb[k];   // into the pre-swizzled chunk images
     }
 

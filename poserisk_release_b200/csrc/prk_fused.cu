@@ -187,10 +187,9 @@ __device__ __forceinline__ void umma_step(uint32_t d_tmem, uint32_t a_lo, uint32
     else            { if (kF8) PRK_UMMA("1", "f8f6f4"); else PRK_UMMA("1", "f16"); }
 #undef PRK_UMMA
 }
-// instruction descriptors (D = fp32, K-major operands): kind::f16 with fp16 inputs / with bf16 inputs, kind::f8f6f4 with e4m3
+// instruction descriptors (D = fp32, K-major operands): kind::f16 with fp16 inputs, kind::f8f6f4 with e4m3
 __host__ __device__ constexpr uint32_t idesc_common(int M, int N) { return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24); }
 __host__ __device__ constexpr uint32_t idesc_fp16(int M, int N) { return idesc_common(M, N); }                          // a/b format 0 = F16
-__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) { return idesc_common(M, N) | (1u << 7) | (1u << 10); }  // 1 = BF16
 __host__ __device__ constexpr uint32_t idesc_e4m3(int M, int N) { return idesc_common(M, N); }                          // 0 = E4M3
 
 // Knock-out builds for finding out where the time goes: -DPRK_KNOCK=<mask> removes one side of the pipeline at
@@ -390,8 +389,7 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
         // ===== MMA issuer (whole warp converged, one elected lane issues) =====
         // Everything about a k-step is a compile-time constant (both loops fully unrolled) and every
         // run-time operand is warp-uniform, so an MMA costs a couple of uniform adds plus the issue.
-        constexpr uint32_t id16 = idesc_fp16(FUSED_BM * kPair, FUSED_BN), idbf = idesc_bf16(FUSED_BM * kPair, FUSED_BN),
-                           id8 = idesc_e4m3(FUSED_BM * kPair, FUSED_BN);
+        constexpr uint32_t id16 = idesc_fp16(FUSED_BM * kPair, FUSED_BN), id8 = idesc_e4m3(FUSED_BM * kPair, FUSED_BN);
         const uint64_t adesc0 = make_smem_desc(smem_u32(sA));
         const uint32_t a_lo = (uint32_t)adesc0, d_hi = (uint32_t)(adesc0 >> 32);
         const uint32_t b_lo0 = (uint32_t)make_smem_desc(smem_u32(sB));
@@ -426,11 +424,10 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
                             umma_step<kPair, false>(d_tmem, a_lo + a_step_off(b), bl, d_hi, id16, b != 0);
                         } else if (b < 2 * FUSED_POSE_STEPS) {    // e4m3 cross terms: (F - Fh) . P + F . (P - Ph), K = 32
                             umma_step<kPair, true>(d_tmem, a_lo + a_step_off(b), bl, d_hi, id8, true);
-                        } else if (b < FUSED_B_STEPS) {           // the five beta x shapedirs (+ template) products, bf16
+                        } else {                                  // betas x shapedirs + template, fp16: bh.sh + T, bl.sh | bh.sl
                             constexpr int A26 = 2 * FUSED_POSE_STEPS, A27 = A26 + 1;
-                            const int q = b - 2 * FUSED_POSE_STEPS;      // 0: s1|s1a|t1  1: s1|s1b  2: s2|t2  3: s3|t3
-                            if (q != 1) umma_step<kPair, false>(d_tmem, a_lo + a_step_off(A26), bl, d_hi, idbf, true);
-                            if (q == 1 || q == 2) umma_step<kPair, false>(d_tmem, a_lo + a_step_off(A27), bl, d_hi, idbf, true);
+                            umma_step<kPair, false>(d_tmem, a_lo + a_step_off(A26), bl, d_hi, id16, true);
+                            if (b == A26) umma_step<kPair, false>(d_tmem, a_lo + a_step_off(A27), bl, d_hi, id16, true);
                         }
                     }
                     if (kPair == 2) {
@@ -797,7 +794,6 @@ blend_simt_kernel(const uint16_t* __restrict__ Arows, const uint16_t* __restrict
     const uint16_t* a = Arows + f * FUSED_K;
     const uint8_t* ab = reinterpret_cast<const uint8_t*>(a);
     const uint8_t* bb = reinterpret_cast<const uint8_t*>(B2);
-    auto bf = [](uint16_t v) { return __uint_as_float((uint32_t)v << 16); };
     auto hf = [](uint16_t v) { return __half2float(__ushort_as_half(v)); };
     auto f8 = [](uint8_t v) { return __half2float(__half(__nv_cvt_fp8_to_halfraw(v, __NV_E4M3))); };
     float acc = 0.f;
@@ -805,14 +801,12 @@ blend_simt_kernel(const uint16_t* __restrict__ Arows, const uint16_t* __restrict
         acc = fmaf(hf(a[k]), hf(B2[fused_b2_index(n, k)]), acc);
     for (int k = FUSED_X_BYTE0; k < FUSED_X_BYTE0 + 2 * FUSED_COL_LO; ++k)   // e4m3 cross terms, byte meets byte
         acc = fmaf(f8(ab[k]), f8(bb[fused_b2_byte_index(n, k)]), acc);
-    auto step = [&](int sa, int sb, float acc) {                      // bf16 beta / template products
-        for (int k = 0; k < 16; ++k) acc = fmaf(bf(a[sa * 16 + k]), bf(B2[fused_b2_index(n, sb * 16 + k)]), acc);
+    auto step = [&](int sa, int sb, float acc) {                      // fp16 beta / template products
+        for (int k = 0; k < 16; ++k) acc = fmaf(hf(a[sa * 16 + k]), hf(B2[fused_b2_index(n, sb * 16 + k)]), acc);
         return acc;
     };
     const int A26 = 2 * FUSED_POSE_STEPS, A27 = A26 + 1, B26 = A26;
-    acc = step(A26, B26, acc); acc = step(A27, B26 + 1, acc);
-    acc = step(A26, B26 + 2, acc); acc = step(A27, B26 + 2, acc);
-    acc = step(A26, B26 + 3, acc);
+    acc = step(A26, B26, acc); acc = step(A27, B26, acc); acc = step(A26, B26 + 1, acc);
     vposed[f * NVC + n] = acc * rot_scale;
 }
 

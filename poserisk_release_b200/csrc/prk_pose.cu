@@ -38,7 +38,6 @@ __host__ __device__ constexpr int smpl_dfs(int pos) {
     return t[pos];
 }
 
-__device__ __forceinline__ uint16_t bf16_bits(float x) { return __bfloat16_as_ushort(__float2bfloat16_rn(x)); }
 // the three parts of a pose feature F in the K12 operand row (prk_internal.h): fp16(F), e4m3((F - fp16(F)) 2^12), e4m3(F)
 __device__ __forceinline__ void feature_parts(float v, uint16_t& hi, uint8_t& lo8, uint8_t& hi8) {
     const __half h = __float2half_rn(v);
@@ -46,7 +45,6 @@ __device__ __forceinline__ void feature_parts(float v, uint16_t& hi, uint8_t& lo
     lo8 = (uint8_t)__nv_cvt_float_to_fp8((v - __half2float(h)) * 4096.0f, __NV_SATFINITE, __NV_E4M3);
     hi8 = (uint8_t)__nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E4M3);
 }
-__device__ __forceinline__ float bf16_val(uint16_t b) { return __uint_as_float((uint32_t)b << 16); }
 
 // Streams bf16 values into a global row, 8 at a time (one 16-byte store).
 struct RowWriter {
@@ -273,25 +271,19 @@ pose_chain_kernel(const __grid_constant__ PoseConsts pc, const float* __restrict
         if (live) { off[f * 3 + 0] = o0; off[f * 3 + 1] = o1; off[f * 3 + 2] = o2; }
         rw.push(0); rw_lo.push8(0); rw_hi8.push8(0);   // element 207 closes the fp16 block and both e4m3 blocks
         rw.dst = reinterpret_cast<uint4*>(Arows + f * FUSED_K + FUSED_COL_BETA);
-        uint16_t bs[3][NBETA];                       // 3-way split of every beta
+        // k-step 26: bh | 2^15 2^15 2^15 | 0 0 0      k-step 27: bl | 0 x 6      (fp16; prk_internal.h "K12 operand layout")
+        uint16_t bl[NBETA];
 #pragma unroll
         for (int k = 0; k < NBETA; ++k) {
-            bs[0][k] = bf16_bits(beta[k]);
-            const float r1 = beta[k] - bf16_val(bs[0][k]);
-            bs[1][k] = bf16_bits(r1);
-            bs[2][k] = bf16_bits(r1 - bf16_val(bs[1][k]));
+            const __half h = __float2half_rn(beta[k]);
+            rw.push(__half_as_ushort(h));
+            bl[k] = __half_as_ushort(__float2half_rn(beta[k] - __half2float(h)));
         }
-        // k-step 26: b1 | b3[0..4] | 1.0      k-step 27: b2 | b3[5..9] | 0
+        rw.push(0x7800); rw.push(0x7800); rw.push(0x7800); rw.push(0); rw.push(0); rw.push(0);
 #pragma unroll
-        for (int k = 0; k < NBETA; ++k) rw.push(bs[0][k]);
+        for (int k = 0; k < NBETA; ++k) rw.push(bl[k]);
 #pragma unroll
-        for (int k = 0; k < 5; ++k) rw.push(bs[2][k]);
-        rw.push(0x3F80);
-#pragma unroll
-        for (int k = 0; k < NBETA; ++k) rw.push(bs[1][k]);
-#pragma unroll
-        for (int k = 5; k < NBETA; ++k) rw.push(bs[2][k]);
-        rw.push(0);
+        for (int k = NBETA; k < 16; ++k) rw.push(0);
     }
 }
 
@@ -419,15 +411,14 @@ pose_chain_warp_kernel(const float* __restrict__ Jc /* J_template[72] | Jdirs[72
             row[base + e] = hi; rowb[FUSED_X_BYTE0 + base + e] = lo8; rowb[FUSED_X_BYTE1 + base + e] = hi8;
         }
     }
-    if (lane < NBETA) {   // k-step 26: b1 | b3[0..4] | 1.0      k-step 27: b2 | b3[5..9] | 0
-        const uint16_t h = bf16_bits(beta[lane]);
-        const float r1 = beta[lane] - bf16_val(h);
-        const uint16_t m = bf16_bits(r1);
-        const uint16_t l = bf16_bits(r1 - bf16_val(m));
-        row[FUSED_COL_BETA + lane] = h; row[FUSED_COL_BETA + 16 + lane] = m;
-        row[FUSED_COL_BETA + (lane < 5 ? NBETA + lane : 16 + NBETA + (lane - 5))] = l;
-    } else if (lane == NBETA) {
-        row[FUSED_COL_BETA + 15] = 0x3F80; row[FUSED_COL_BETA + 31] = 0;
+    if (lane < 16) {   // k-step 26: bh | 2^15 2^15 2^15 | 0 0 0      k-step 27: bl | 0 x 6      (fp16)
+        uint16_t h16 = lane < NBETA + 3 ? 0x7800 : 0, l16 = 0;
+        if (lane < NBETA) {
+            const __half h = __float2half_rn(beta[lane]);
+            h16 = __half_as_ushort(h);
+            l16 = __half_as_ushort(__float2half_rn(beta[lane] - __half2float(h)));
+        }
+        row[FUSED_COL_BETA + lane] = h16; row[FUSED_COL_BETA + 16 + lane] = l16;
     }
     if (lane == 31) { row[FUSED_COL_LO - 1] = 0; rowb[FUSED_X_BYTE0 + 207] = 0; rowb[FUSED_X_BYTE1 + 207] = 0; }
     __syncwarp();

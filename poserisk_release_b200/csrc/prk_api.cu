@@ -454,7 +454,8 @@ int prk_model_create(prk_model** out, int device, const float* vt, const float* 
     {
         std::vector<float> jc(72 + 720 + NBETA + 1);
         memcpy(jc.data(), m->pc.J_template, 72 * 4);
-        memcpy(jc.data() + 72, m->pc.Jdirs, 720 * 4);
+        for (int i = 0; i < 72; ++i)
+            for (int k = 0; k < NBETA; ++k) jc[72 + k * 72 + i] = m->pc.Jdirs[i * NBETA + k];   // beta-major for the lane-per-joint kernel
         memcpy(jc.data() + 792, m->pc.model_betas, NBETA * 4);
         jc[802] = m->pc.rot_scale;
         PRK_M(cudaMalloc(&m->d_Jc, jc.size() * 4));

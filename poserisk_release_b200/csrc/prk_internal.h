@@ -96,7 +96,7 @@ struct prk_model {
     int blend_scale_log2 = 0;      // S: every B' operand is multiplied by 2^S
     prk::PoseConsts pc;                 // host copy, passed by value to the pose kernel
     // device buffers
-    float* d_Jc = nullptr;         // J_template[72] | Jdirs[720] | model_betas[10] (lane-per-joint pose kernel)
+    float* d_Jc = nullptr;         // J_template[72] | Jdirs^T[10][72] | model_betas[10] | rot_scale (lane-per-joint pose kernel)
     // B' as the shared-memory IMAGES of its TMA chunks: [vertex tile][chunk][96 rows][64 bf16], every chunk one
     // contiguous 12 KB block with the 128-byte swizzle already applied (16-byte unit j of row r sits at j ^ (r & 7)),
     // so a chunk is fetched with ONE linear bulk copy instead of a 96-row tensor box (fused_b2_index)

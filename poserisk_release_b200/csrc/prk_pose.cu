@@ -311,7 +311,7 @@ constexpr int64_t kWarpVariantMaxFrames = 49152;   // above this the thread-per-
 
 template <bool kMesh>
 __global__ void __launch_bounds__((kMesh ? kWarpsPerBlockMesh : kWarpsPerBlock) * 32)
-pose_chain_warp_kernel(const float* __restrict__ Jc /* J_template[72] | Jdirs[720] | model_betas[10] | rot_scale */,
+pose_chain_warp_kernel(const float* __restrict__ Jc /* J_template[72] | Jdirs^T[10][72] | model_betas[10] | rot_scale */,
                        const float* __restrict__ pose, const float* __restrict__ betas,
                        const float* __restrict__ trans, const BatchFlags* __restrict__ flags, uint32_t mode,
                        int center_idx, int64_t B, uint16_t* __restrict__ Arows, float* __restrict__ Askin,
@@ -345,7 +345,12 @@ pose_chain_warp_kernel(const float* __restrict__ Jc /* J_template[72] | Jdirs[72
     smpl_rodrigues(pose[f * 72 + j * 3 + 0], pose[f * 72 + j * 3 + 1], pose[f * 72 + j * 3 + 2], R);
     float J[3];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) J[c] = rest_joint(Jc[j * 3 + c], Jc + 72 + (j * 3 + c) * NBETA, beta);
+    for (int c = 0; c < 3; ++c) {   // rest_joint() on the beta-major copy of Jdirs: a warp-wide load touches 288 contiguous bytes
+        float acc = Jc[j * 3 + c];
+#pragma unroll
+        for (int k = 0; k < NBETA; ++k) acc = fmaf(Jc[72 + k * 72 + j * 3 + c], beta[k], acc);
+        J[c] = acc;
+    }
 
     const int par = c_parent[lane], depth = c_depth[lane];
     float G[12];

@@ -43,7 +43,8 @@ EXAMPLE_INFO = {"REBA": {"Legs_bilateral_weight_bearing/walking": 1, "Sitting": 
 # algorithmic work per frame
 FUSED_BYTES_PER_FRAME = 340 + 82680 + 288 + 32          # whole pipeline with ideal fusion: 83,340 B
 GEMM_FLOP_PER_FRAME = 2 * (10 + 207) * 20670            # 8,970,780 algorithmic blend flop
-GEMM_EXEC_FLOP_PER_FRAME = 216 * 44 * 2 * 96 * 16       # executed MMA work: 216 tiles x 44 MMAs (N=96, K=16) = 29.2 MFLOP
+GEMM_EXEC_FLOP_PER_FRAME = 216 * 29 * 2 * 96 * 16       # executed MMA work in bf16-equivalent pipe time: 216 tiles x 29 MMAs (N=96; 16 fp16 K=16
+                                                        # + 13 e4m3 K=32, which occupy the pipe like a 16-bit K=16 step) = 19.2 MFLOP (round 1: 44 bf16 MMAs, 29.2)
 
 
 def config_dict(n_gpus):
@@ -55,7 +56,7 @@ def config_dict(n_gpus):
             "verts_layout": "(B, 6890, 3) float32 view over rows padded to 16 bytes (pitch 20672 floats), stored by bulk tensor (TMA) "
                             "stores; dense_layout in this line = the same steps into the reference's contiguous tensor",
             "l2": "8 distinct input batches in rotation; every step writes 339 MB of vertices (> 126 MB L2), "
-                  "so no input or output line survives in L2 between steps; the 21 MB bf16 blend matrix is "
+                  "so no input or output line survives in L2 between steps; the 18.6 MB fp16/e4m3 blend matrix is "
                   "meant to stay L2-resident"}
 
 
@@ -544,8 +545,10 @@ def run_gpu_arm(args):
         other = {"kernel": "fused_blend_skin_kernel, blend GEMM part", "bound": "tensor", "achieved": gemm_tf,
                  "peak": tensor_peak, "unit": "TFLOP/s", "frac": gemm_tf / tensor_peak, "traffic": None,
                  "executed_mma": {"achieved": gemm_exec_tf, "frac": gemm_exec_tf / tensor_peak,
-                                  "note": "bf16 split precision (hi*hi + lo*hi + hi*lo, 3-way for betas) + N padding: "
-                                          "29.2 MFLOP executed per 8.97 MFLOP algorithmic"},
+                                  "note": "split precision: fp16 main product + e4m3 cross terms (kind::f8f6f4, K = 32, counted as one "
+                                          "16-bit K = 16 step of pipe time) + 3 fp16 beta/template steps, N padding: 19.2 MFLOP-equivalent "
+                                          "executed per 8.97 MFLOP algorithmic (round 1: 29.2; fewer executed MMAs at equal accuracy is the "
+                                          "goal here, the kernel is bound by its epilogue and the power cap, not by the tensor pipe)"},
                  "peak_source": peaks['source'] + " (sustained bf16, kernel timed inside a long step)"}
         cpu_baseline = parity = None
         if world == 1:   # bounded CPU sample of the same workload (rank 0 at N=1 only)

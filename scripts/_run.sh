@@ -1,4 +1,3 @@
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q --timeout 900 -x 2>&1 | tail -4 | tee gpurun_out/pytest_r2g.log
-( AB_ALIGNED=1 python scripts/fused_ab.py base m29 base m29
-  AB_ALIGNED=1 AB_STEPS=2000 python scripts/fused_ab.py base m29 ) 2>&1 | tee gpurun_out/ab_r2_31.log
+( for al in 1 0; do echo "aligned $al"; AB_ALIGNED=$al AB_STEPS=10000 python scripts/fused_ab.py base bf16 base bf16; done
+  echo "aligned 0 short"; AB_ALIGNED=0 python scripts/fused_ab.py base bf16 ) 2>&1 | tee gpurun_out/ab_r2_32.log

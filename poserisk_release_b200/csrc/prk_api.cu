@@ -353,17 +353,21 @@ int prk_model_create(prk_model** out, int device, const float* vt, const float* 
             for (int k = 0; k < NBETA; ++k) m->pc.Jdirs[(j * 3 + c) * NBETA + k] = (float)d[k];
         }
 
-    // K12 operand (prk_internal.h "K12 operand layout"): fp16 main part, e4m3 cross-term parts, bf16 shape / template parts,
+    // K12 operand (prk_internal.h "K12 operand layout"): fp16 main part, e4m3 cross-term parts, fp16 shape / template parts,
     // everything times 2^S
-    float pd_max = 0.f;
-    for (size_t i = 0; i < (size_t)NVC * NPOSE; ++i) { const float a = fabsf(pd[i]); if (a > pd_max && std::isfinite(a)) pd_max = a; }
+    auto max_abs = [](const float* a, size_t n) {
+        float mx = 0.f;
+        for (size_t i = 0; i < n; ++i) { const float v = fabsf(a[i]); if (v > mx && std::isfinite(v)) mx = v; }
+        return mx;
+    };
+    const float pd_max = max_abs(pd, (size_t)NVC * NPOSE), sd_max = max_abs(sd, (size_t)NVC * NBETA), vt_max = max_abs(vt, NVC);
     int S = 0;
-    float sd_max = 0.f;
-    for (size_t i = 0; i < (size_t)NVC * NBETA; ++i) { const float a = fabsf(sd[i]); if (a > sd_max && std::isfinite(a)) sd_max = a; }
-    {   // max|posedirs| 2^S <= 2^14 (e4m3 range of the cross terms), max|shapedirs| 2^S <= 2^15 (fp16 range)
+    {   // max|posedirs| 2^S <= 2^14 (e4m3 range of the cross terms), max|shapedirs| 2^S <= 2^15 and max|v_template| 2^(S-15) <= 2^15
+        // (fp16 range of sh and of u1)
         float lim = 1e30f;
         if (pd_max > 0.f) lim = fminf(lim, 16384.0f / pd_max);
         if (sd_max > 0.f) lim = fminf(lim, 32768.0f / sd_max);
+        if (vt_max > 0.f) lim = fminf(lim, 1073741824.0f / vt_max);
         S = lim < 1e30f ? (int)floorf(log2f(lim)) : 0;
         if (S < 0) S = 0;
         if (S > 30) S = 30;

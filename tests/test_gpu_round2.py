@@ -464,3 +464,27 @@ def test_aligned_rows_through_the_drop_in_layer_and_the_oracle():
     assert rc == 4                                                # PRK_ERR_UNSUPPORTED
     v6, _ = SMPL_Layer(model_data=lay6.smpl_data, aligned_verts=True)(pose.cuda())     # the layer falls back to a dense tensor
     assert v6.is_contiguous()
+
+
+@pytest.mark.parametrize('pd_scale,sd_scale,vt_scale', [(1.0, 1.0, 1.0), (1e-4, 1.0, 1.0), (30.0, 0.1, 1.0), (1.0, 40.0, 3.0),
+                                                           (0.0, 1.0, 1.0), (1e-7, 1e-7, 1.9)])
+def test_blend_operand_scale_follows_the_model(pd_scale, sd_scale, vt_scale):
+    """The blend runs as fp16 + e4m3 tensor-core products on operands multiplied by 2^S (csrc/prk_internal.h "K12 operand
+    layout"); S is derived from max|posedirs|, max|shapedirs| and max|v_template| so that no part leaves the fp16 / e4m3
+    range.  Models whose blend shapes are far smaller / larger than SMPL's, large betas and large rotations stay inside the
+    1e-5 bound of north_star against the float64 oracle."""
+    from poserisk_release_b200 import SMPL_Layer
+    from poserisk_release_b200.model_provider import SMPLModelData
+    m = synthetic_smpl('neutral')
+    md = SMPLModelData((m.v_template * vt_scale).astype(np.float32), (m.shapedirs * sd_scale).astype(np.float32),
+                       (m.posedirs * pd_scale).astype(np.float32), m.J_regressor, m.weights, m.betas, m.faces,
+                       m.kintree_table, 'neutral', True)
+    lay = SMPL_Layer(gender='neutral', model_root='unused', model_data=md)
+    g = torch.Generator().manual_seed(21)
+    for pose_s, beta_s in ((0.35, 1.0), (1.2, 3.0), (0.6, 10.0)):
+        pose = torch.randn(300, 72, generator=g) * pose_s
+        betas = torch.randn(300, 10, generator=g) * beta_s
+        v, j = lay(pose.cuda(), betas.cuda())
+        v_ref, j_ref = oracle.smpl_forward(md, pose.numpy(), betas.numpy())
+        ev, ej = relerr(v.cpu().numpy(), v_ref), relerr(j.cpu().numpy(), j_ref)
+        assert ev < 2e-6 and ej < 2e-6, (pd_scale, sd_scale, vt_scale, pose_s, beta_s, ev, ej)

@@ -17,6 +17,7 @@
 #include "prk_internal.h"
 
 #include <math.h>
+#include <cstdlib>
 
 namespace prk {
 
@@ -117,6 +118,50 @@ __device__ __forceinline__ bool euler_from_axis_angle(double x, double y, double
     if (kNeed & 2) ey = __ddiv_rn(__dmul_rn(ey, 180.0), kPi);
     if (kNeed & 4) ez = __ddiv_rn(__dmul_rn(ez, 180.0), kPi);
     return !isfinite(theta);
+}
+
+// ---- float32 screening pass of the large-batch kernel -----------------------------------
+// The ladders only COMPARE angles with constants: the multiples of 5 degrees and +-1 (reba.py / rula.py; grep of every
+// comparison in reba_frame / rula_frame below).  An angle that is further from all of them than the error of a float32
+// evaluation decides every comparison exactly like the float64 value the reference computes, so the large-batch kernel
+// first evaluates the Euler angles in float32 (about 150 instructions per joint instead of 700) and marks the frame
+// DOUBTFUL when any angle the ladders read lies within kFastBand degrees (scaled by 1 / sy for the two angles whose
+// atan2 arguments shrink with sy = cos(pitch)) of a multiple of 5 or of +-1, when sy < 0.02, or when the rotation is tiny,
+// above 4 rad or not finite.  Doubtful frames (about 1 % of random poses) are re-evaluated in float64 by the whole warp, one joint per
+// lane, before the ladders run: the records stay bit-identical to the all-float64 path (tests/test_gpu_round2.py::
+// test_fast_screening_gives_the_exact_records, 2M adversarial frames).  Error budget: R entries <= 7e-7 absolute in
+// float32 (sincosf 2 ulp, the c1 * x * y products, one rounding each) plus 4e-7 from theta's own rounding below 4 rad, i.e.
+// <= 1.6e-6 / sy rad = 9e-5 / sy degrees on an angle, plus 2 ulp of atan2f and the conversion to degrees (4e-5 degrees); the band
+// is 1e-3 degrees.
+// A joint whose three components are exactly zero gives exactly zero angles on both paths (identity) and is not doubtful.
+constexpr float kFastBand = 1e-3f;
+__device__ __forceinline__ bool near_threshold(float a, float scale) {
+    const float r = fabsf(a - 5.0f * rintf(a * 0.2f));          // distance to the next multiple of 5
+    const float r1 = fabsf(fabsf(a) - 1.0f);                   // ... and to +-1
+    return !(fminf(r, r1) * scale >= kFastBand);               // NaN -> doubtful
+}
+// returns true when the frame needs the float64 evaluation
+// (kNeed: a constant after unrolling, as in euler_from_axis_angle)
+__device__ __forceinline__ bool euler_screen(float x, float y, float z, double& ex, double& ey, double& ez, const int kNeed) {
+    ex = ey = ez = 0.0;
+    if (x == 0.0f && y == 0.0f && z == 0.0f) return false;      // identity on both paths (theta < DBL_EPSILON branch)
+    const float theta = sqrtf(fmaf(z, z, fmaf(y, y, x * x)));
+    if (!(theta > 1e-3f && theta < 4.0f)) return true;     // (the absolute error of a float32 theta grows with theta)
+    float s, c;
+    sincosf(theta, &s, &c);
+    const float c1 = 1.0f - c, it = 1.0f / theta;
+    x *= it; y *= it; z *= it;
+    const float R00 = fmaf(c1 * x, x, c), R10 = fmaf(c1 * x, y, s * z), R20 = fmaf(c1 * x, z, -s * y);
+    const float R21 = fmaf(c1 * y, z, s * x), R22 = fmaf(c1 * z, z, c);
+    const float sy = sqrtf(fmaf(R00, R00, R10 * R10));
+    if (!(sy >= 0.02f)) return true;
+    const float kDeg = 57.29577951308232f;
+    const float sc = fminf(sy, 1.0f);
+    bool doubt = false;
+    if (kNeed & 1) { const float a = atan2f(R21, R22) * kDeg; doubt |= near_threshold(a, sc); ex = (double)a; }
+    if (kNeed & 2) { const float a = atan2f(-R20, sy) * kDeg; doubt |= near_threshold(a, 1.0f); ey = (double)a; }
+    if (kNeed & 4) { const float a = atan2f(R10, R00) * kDeg; doubt |= near_threshold(a, sc); ez = (double)a; }
+    return doubt;
 }
 
 #define P(slot, c) (A.a[slot][c])
@@ -490,7 +535,7 @@ constexpr int kDebugPitch = kDebugStageJoints * 3 + 1;
 #ifndef PRK_SCORE_MINBLOCKS
 #define PRK_SCORE_MINBLOCKS 1
 #endif
-template <typename T>
+template <typename T, bool kFast>
 __global__ void __launch_bounds__(kScoreWarps * 32, PRK_SCORE_MINBLOCKS)
 score_pose_kernel(const T* __restrict__ pose, const prk_addinfo* __restrict__ info, int32_t n_tracks,
                   const int32_t* __restrict__ track, int64_t B, uint32_t which,
@@ -498,6 +543,7 @@ score_pose_kernel(const T* __restrict__ pose, const prk_addinfo* __restrict__ in
                   const DebugSlots dbg, int n_debug) {
     __shared__ T s_pose[kScoreWarps][32 * kPosePitch];
     __shared__ double s_dbg[kScoreWarps][32 * kDebugPitch];
+    __shared__ double s_fix[kFast ? kScoreWarps : 1][N_SLOTS][3];          // float64 angles of the doubtful frame in hand
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t f0 = ((int64_t)blockIdx.x * kScoreWarps + warp) * 32;     // first frame of this warp
     if (f0 >= B) return;
@@ -526,19 +572,50 @@ score_pose_kernel(const T* __restrict__ pose, const prk_addinfo* __restrict__ in
         if (stage_dbg || live) { e[0] = ex; e[1] = ey; e[2] = ez; }
     };
     Angles A;
-    bool bad = false;
+    bool bad = false, doubt = false;
 #pragma unroll
     for (int s = 0; s < N_SLOTS; ++s) {
         const int j = slot_joint(s);
         double ex, ey, ez;
-        if (slot_need(s) != 7 && (debug_mask & (1u << j)))    // warp-uniform: a debug joint needs the whole triple
+        if (debug_mask & (1u << j)) {                         // warp-uniform: a debug joint needs the whole triple, in float64
             bad |= euler_from_axis_angle<sizeof(T) == 4>((double)p[j * 3 + 0], (double)p[j * 3 + 1],
                                                         (double)p[j * 3 + 2], ex, ey, ez);
-        else
+            emit(j, ex, ey, ez);
+        } else if (kFast) {                                   // float32 screening (see euler_screen)
+            doubt |= euler_screen((float)p[j * 3 + 0], (float)p[j * 3 + 1], (float)p[j * 3 + 2], ex, ey, ez, slot_need(s));
+        } else {
             bad |= euler_from_axis_angle<sizeof(T) == 4>((double)p[j * 3 + 0], (double)p[j * 3 + 1],
                                                         (double)p[j * 3 + 2], ex, ey, ez, slot_need(s));
+        }
         A.a[s][0] = ex; A.a[s][1] = ey; A.a[s][2] = ez;
-        if (debug_mask & (1u << j)) emit(j, ex, ey, ez);
+    }
+    if (kFast) {   // doubtful frames: the warp evaluates the frame's twelve scored joints in float64, one joint per lane
+        unsigned todo = __ballot_sync(0xffffffffu, doubt && live);
+        while (todo) {
+            const int d = __ffs(todo) - 1;
+            todo &= todo - 1;
+            bool b = false;
+            if (lane < N_SLOTS) {
+                const int j = slot_joint(lane);
+                const T* pd = tile + d * kPosePitch + j * 3;
+                double ex, ey, ez;
+                b = euler_from_axis_angle<sizeof(T) == 4>((double)pd[0], (double)pd[1], (double)pd[2], ex, ey, ez);
+                s_fix[warp][lane][0] = ex; s_fix[warp][lane][1] = ey; s_fix[warp][lane][2] = ez;
+            }
+            const bool any_bad = __ballot_sync(0xffffffffu, b) != 0;
+            __syncwarp();
+            if (lane == d) {
+                bad |= any_bad;
+#pragma unroll
+                for (int s = 0; s < N_SLOTS; ++s) {
+                    // the components no rule reads stay 0 as on the all-float64 path (slot_need)
+                    A.a[s][0] = (slot_need(s) & 1) || (debug_mask & (1u << slot_joint(s))) ? s_fix[warp][s][0] : 0.0;
+                    A.a[s][1] = (slot_need(s) & 2) || (debug_mask & (1u << slot_joint(s))) ? s_fix[warp][s][1] : 0.0;
+                    A.a[s][2] = (slot_need(s) & 4) || (debug_mask & (1u << slot_joint(s))) ? s_fix[warp][s][2] : 0.0;
+                }
+            }
+            __syncwarp();
+        }
     }
     // debug joints that are not scored
     uint32_t rest = debug_mask & ~0x3F7038u;   // bits of joints 3,4,5,12,13,14,16..21 cleared
@@ -700,11 +777,16 @@ cudaError_t launch_score_pose(const void* d_pose, int pose_dtype, const prk_addi
         return cudaGetLastError();
     }
     const unsigned g = grid_for(B, kScoreWarps * 32);
-    if (pose_dtype == PRK_DTYPE_F32)
-        score_pose_kernel<float><<<g, kScoreWarps * 32, 0, s>>>(
+    // float32 poses: float32 screening + float64 re-evaluation of doubtful frames (PRK_SCORE_EXACT=1: float64 throughout)
+    static const bool exact = [] { const char* e = getenv("PRK_SCORE_EXACT"); return e && atoi(e) != 0; }();
+    if (pose_dtype == PRK_DTYPE_F32 && !exact)
+        score_pose_kernel<float, true><<<g, kScoreWarps * 32, 0, s>>>(
+            (const float*)d_pose, d_info, n_tracks, d_track, B, which, d_out, d_euler_out, dbg, n_debug);
+    else if (pose_dtype == PRK_DTYPE_F32)
+        score_pose_kernel<float, false><<<g, kScoreWarps * 32, 0, s>>>(
             (const float*)d_pose, d_info, n_tracks, d_track, B, which, d_out, d_euler_out, dbg, n_debug);
     else
-        score_pose_kernel<double><<<g, kScoreWarps * 32, 0, s>>>(
+        score_pose_kernel<double, false><<<g, kScoreWarps * 32, 0, s>>>(
             (const double*)d_pose, d_info, n_tracks, d_track, B, which, d_out, d_euler_out, dbg, n_debug);
     count_launch();
     return cudaGetLastError();

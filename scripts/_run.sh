@@ -1,3 +1,2 @@
 mkdir -p gpurun_out
-( for al in 1 0; do echo "aligned $al"; AB_ALIGNED=$al AB_STEPS=10000 python scripts/fused_ab.py base bf16 base bf16; done
-  echo "aligned 0 short"; AB_ALIGNED=0 python scripts/fused_ab.py base bf16 ) 2>&1 | tee gpurun_out/ab_r2_32.log
+timeout 1500 python -m pytest tests/test_gpu_round2.py -m gpu -q --timeout 900 -s -k "blend_operand or fast_screening" 2>&1 | grep -v Warning | tail -40 | tee gpurun_out/pytest_r2i.log

@@ -487,4 +487,53 @@ def test_blend_operand_scale_follows_the_model(pd_scale, sd_scale, vt_scale):
         v, j = lay(pose.cuda(), betas.cuda())
         v_ref, j_ref = oracle.smpl_forward(md, pose.numpy(), betas.numpy())
         ev, ej = relerr(v.cpu().numpy(), v_ref), relerr(j.cpu().numpy(), j_ref)
-        assert ev < 2e-6 and ej < 2e-6, (pd_scale, sd_scale, vt_scale, pose_s, beta_s, ev, ej)
+        # error model: the e4m3 cross terms leave 2^-15.5 of the POSE blend displacement; 2e-6 of the vertex range for
+        # SMPL-like magnitudes (displacements of centimetres), the north_star bound for blend shapes 30 x larger
+        bound = 2e-6 if pd_scale <= 1.0 else TOL
+        print(f'\n[pd x{pd_scale} sd x{sd_scale} vt x{vt_scale} pose x{pose_s} betas x{beta_s}] verts {ev:.2e} joints {ej:.2e}')
+        assert ev < bound and ej < 2e-6, (pd_scale, sd_scale, vt_scale, pose_s, beta_s, ev, ej)
+
+
+def test_fast_screening_gives_the_exact_records(engine):
+    """Large float32 batches are scored with a float32 screening pass; frames with an angle within 1e-3 degrees of a ladder
+    threshold (and tiny / large rotations, sy < 0.02) are re-evaluated in float64 (csrc/prk_score.cu euler_screen).  The
+    records must be bit-identical to the all-float64 evaluation: 1M frames whose twelve scored joints are built from Euler
+    angles sitting ON the thresholds up to offsets of 1e-7 .. 1e-2 degrees (the float32 rounding of the axis-angle vector
+    then scatters them around the threshold at the 1e-5 degree level), gimbal-lock pitches and exact zeros included.  The
+    reference evaluation is the small-batch kernel (float64 throughout, chunks of 131,072 frames), itself checked against
+    the oracle on a sample here and in test_pose_to_scores_vs_oracle."""
+    from scipy.spatial.transform import Rotation
+    from poserisk_release_b200 import _runtime
+    n = 1 << 20
+    rng = np.random.default_rng(5)
+    thr = np.array([0, 1, -1, 5, -5, 10, -10, 15, -15, 20, -20, 30, -30, 45, -45, 60, -60, 70, -70, 90, -90, 100, -100,
+                    110, -110, 180, -180, 35, 125], np.float64)
+    off = np.array([0, 1e-7, -1e-7, 1e-6, -1e-6, 1e-5, -1e-5, 1e-4, -1e-4, 5e-4, -5e-4, 9e-4, -9e-4, 1.1e-3, -1.1e-3,
+                    2e-3, -2e-3, 1e-2, -1e-2], np.float64)
+    pose = (rng.standard_normal((n, 24, 3)) * 0.5).astype(np.float32)
+    scored = [3, 4, 5, 12, 13, 14, 16, 17, 18, 19, 20, 21]
+    e = thr[rng.integers(0, len(thr), (n, 12, 3))] + off[rng.integers(0, len(off), (n, 12, 3))]
+    rnd = rng.random((n, 12, 3)) < 0.5                     # half of the components: anything
+    e = np.where(rnd, rng.uniform(-180, 180, (n, 12, 3)), e)
+    e[..., 1] = np.clip(e[..., 1], -90, 90)               # pitch; +-90 = gimbal lock (sy ~ 0)
+    rv = Rotation.from_euler('xyz', e.reshape(-1, 3), degrees=True).as_rotvec().reshape(n, 12, 3)
+    pose[:, scored] = rv.astype(np.float32)
+    pose[rng.random(n) < 0.05, 20] = 0.0                   # exact zero rotations
+    pose[rng.random(n) < 0.01, 16] *= 1e-5                 # tiny rotations
+    pose[rng.random(n) < 0.01, 17] *= 3.0                  # rotations beyond 4 rad
+    pose = torch.from_numpy(pose.reshape(n, 72)).cuda()
+    fast, _ = engine.euler_debug(pose, [], EXAMPLE_INFO)                       # one call: the large-batch kernel
+    exact = torch.cat([engine.euler_debug(pose[i:i + 131072], [], EXAMPLE_INFO)[0] for i in range(0, n, 131072)])
+    torch.cuda.synchronize()
+    diff = (fast != exact).any(dim=1)
+    assert int(diff.sum()) == 0, (int(diff.sum()), torch.nonzero(diff)[:5].tolist())
+    # with debug joints (float64 rows for them, screening for the rest)
+    ids = [12, 16, 17, 3]
+    fast_d, eul = engine.euler_debug(pose[:300000], ids, EXAMPLE_INFO)
+    assert torch.equal(fast_d, exact[:300000])
+    from poserisk_release_b200 import axis_angle_to_euler_angle
+    e_ref = axis_angle_to_euler_angle(pose[:300000].reshape(-1, 24, 3)[:, ids].reshape(-1, 3).cpu().numpy())
+    assert np.array_equal(eul.cpu().numpy().reshape(-1, 3), np.asarray(e_ref).reshape(-1, 3))
+    # and the oracle on a sample
+    ref = oracle.score_pose(pose[:20000].cpu().numpy(), EXAMPLE_INFO)
+    assert same_records(_runtime.records_to_numpy(fast[:20000]), ref).all()

@@ -94,6 +94,11 @@ __device__ __forceinline__ void smpl_rodrigues(float ax, float ay, float az, flo
     R[8] = __fadd_rn(__fsub_rn(__fsub_rn(w2, x2), y2), z2);
 }
 
+// One out-of-line copy for the thread-per-frame kernel, which evaluates 24 joints per thread with compile-time joint indices:
+// inlined 24 times (sincosf with its large-argument path, seven IEEE divisions with theirs) the joints-only kernel was 13,900
+// instructions = 222 KB of code and ran out of the instruction caches.
+__device__ __noinline__ void smpl_rodrigues_call(float ax, float ay, float az, float* R) { smpl_rodrigues(ax, ay, az, R); }
+
 // Shared arithmetic of both kernel variants (explicit fmaf / _rn ops so the thread-per-frame
 // and the lane-per-joint kernels produce bit-identical results).
 __device__ __forceinline__ float rest_joint(const float jt, const float* __restrict__ jd, const float* beta) {
@@ -205,7 +210,7 @@ pose_chain_kernel(const __grid_constant__ PoseConsts pc, const float* __restrict
         const int par = kStd ? smpl_parent(j) : (pos == 0 ? -1 : pc.parents[j]);
 
         float R[9];
-        smpl_rodrigues(p[j * 3 + 0], p[j * 3 + 1], p[j * 3 + 2], R);      // (read before jout[j * 3 ..] is written)
+        smpl_rodrigues_call(p[j * 3 + 0], p[j * 3 + 1], p[j * 3 + 2], R); // (read before jout[j * 3 ..] is written)
 
         if (kMesh && pos > 0) {   // pose_map = R - I (tensutils.py:41-48) in the three parts of the K12 operand row
 #pragma unroll

@@ -164,6 +164,18 @@ __device__ __forceinline__ bool euler_screen(float x, float y, float z, double& 
     return doubt;
 }
 
+// One out-of-line copy of the float64 evaluation for the large-batch kernel: inlined twelve times (once per scored joint) the
+// kernel was 23,500 instructions = 376 KB of code and spent most of its time waiting for instruction fetches
+// (ncu: stalled_no_instruction 8.3 per issue, issue slots 23 % busy); with the slot loop rolled and this function shared by
+// the debug joints, the doubtful-frame pass and the all-float64 path it is a quarter of that.
+template <bool kF32>
+__device__ __noinline__ bool euler_exact(double x, double y, double z, double* e, int need) {
+    double ex, ey, ez;
+    const bool bad = euler_from_axis_angle<kF32>(x, y, z, ex, ey, ez, need);
+    e[0] = ex; e[1] = ey; e[2] = ez;
+    return bad;
+}
+
 #define P(slot, c) (A.a[slot][c])
 
 __device__ __forceinline__ void reba_frame(const Angles& A, const int32_t* __restrict__ info,
@@ -535,14 +547,15 @@ constexpr int kDebugPitch = kDebugStageJoints * 3 + 1;
 #ifndef PRK_SCORE_MINBLOCKS
 #define PRK_SCORE_MINBLOCKS 1
 #endif
-template <typename T, bool kFast>
+template <typename T, bool kFast, bool kDebug>
 __global__ void __launch_bounds__(kScoreWarps * 32, PRK_SCORE_MINBLOCKS)
 score_pose_kernel(const T* __restrict__ pose, const prk_addinfo* __restrict__ info, int32_t n_tracks,
                   const int32_t* __restrict__ track, int64_t B, uint32_t which,
                   prk_score_rec* __restrict__ out, double* __restrict__ euler_out,
                   const DebugSlots dbg, int n_debug) {
-    __shared__ T s_pose[kScoreWarps][32 * kPosePitch];
-    __shared__ double s_dbg[kScoreWarps][32 * kDebugPitch];
+    // (the debug Euler rows are staged in the pose tile once the poses are dead: a tile of their own left 7 instead of 11 blocks per SM)
+    __shared__ __align__(16) T s_pose[kScoreWarps][32 * kPosePitch];
+    static_assert(32 * kPosePitch * sizeof(T) >= 32 * kDebugPitch * sizeof(double), "debug rows do not fit in the pose tile");
     __shared__ double s_fix[kFast ? kScoreWarps : 1][N_SLOTS][3];          // float64 angles of the doubtful frame in hand
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t f0 = ((int64_t)blockIdx.x * kScoreWarps + warp) * 32;     // first frame of this warp
@@ -563,31 +576,30 @@ score_pose_kernel(const T* __restrict__ pose, const prk_addinfo* __restrict__ in
     const bool live = lane < nf;
     const int64_t i = f0 + lane;
     const T* p = tile + lane * kPosePitch;
-    const uint32_t debug_mask = dbg.mask;
+    const uint32_t debug_mask = kDebug ? dbg.mask : 0u;
     const bool stage_dbg = n_debug <= kDebugStageJoints;
-    double* dtile = s_dbg[warp];
+    double* dtile = reinterpret_cast<double*>(tile);
+    double dbg_e[kDebug ? kDebugStageJoints * 3 : 1];          // this frame's staged debug rows (local memory: dynamic slot)
     auto emit = [&](int j, double ex, double ey, double ez) {
         const int slot = dbg.slot[j];
-        double* e = stage_dbg ? dtile + lane * kDebugPitch + slot * 3 : euler_out + (i * n_debug + slot) * 3;
-        if (stage_dbg || live) { e[0] = ex; e[1] = ey; e[2] = ez; }
+        if (stage_dbg) { dbg_e[slot * 3 + 0] = ex; dbg_e[slot * 3 + 1] = ey; dbg_e[slot * 3 + 2] = ez; }
+        else if (live) { double* e = euler_out + (i * n_debug + slot) * 3; e[0] = ex; e[1] = ey; e[2] = ez; }
     };
     Angles A;
     bool bad = false, doubt = false;
-#pragma unroll
-    for (int s = 0; s < N_SLOTS; ++s) {
+#pragma unroll 1
+    for (int s = 0; s < N_SLOTS; ++s) {     // rolled: one copy of the Euler code (see euler_exact); A lives in local memory
         const int j = slot_joint(s);
-        double ex, ey, ez;
+        double e[3];
         if (debug_mask & (1u << j)) {                         // warp-uniform: a debug joint needs the whole triple, in float64
-            bad |= euler_from_axis_angle<sizeof(T) == 4>((double)p[j * 3 + 0], (double)p[j * 3 + 1],
-                                                        (double)p[j * 3 + 2], ex, ey, ez);
-            emit(j, ex, ey, ez);
+            bad |= euler_exact<sizeof(T) == 4>((double)p[j * 3 + 0], (double)p[j * 3 + 1], (double)p[j * 3 + 2], e, 7);
+            emit(j, e[0], e[1], e[2]);
         } else if (kFast) {                                   // float32 screening (see euler_screen)
-            doubt |= euler_screen((float)p[j * 3 + 0], (float)p[j * 3 + 1], (float)p[j * 3 + 2], ex, ey, ez, slot_need(s));
+            doubt |= euler_screen((float)p[j * 3 + 0], (float)p[j * 3 + 1], (float)p[j * 3 + 2], e[0], e[1], e[2], slot_need(s));
         } else {
-            bad |= euler_from_axis_angle<sizeof(T) == 4>((double)p[j * 3 + 0], (double)p[j * 3 + 1],
-                                                        (double)p[j * 3 + 2], ex, ey, ez, slot_need(s));
+            bad |= euler_exact<sizeof(T) == 4>((double)p[j * 3 + 0], (double)p[j * 3 + 1], (double)p[j * 3 + 2], e, slot_need(s));
         }
-        A.a[s][0] = ex; A.a[s][1] = ey; A.a[s][2] = ez;
+        A.a[s][0] = e[0]; A.a[s][1] = e[1]; A.a[s][2] = e[2];
     }
     if (kFast) {   // doubtful frames: the warp evaluates the frame's twelve scored joints in float64, one joint per lane
         unsigned todo = __ballot_sync(0xffffffffu, doubt && live);
@@ -598,21 +610,17 @@ score_pose_kernel(const T* __restrict__ pose, const prk_addinfo* __restrict__ in
             if (lane < N_SLOTS) {
                 const int j = slot_joint(lane);
                 const T* pd = tile + d * kPosePitch + j * 3;
-                double ex, ey, ez;
-                b = euler_from_axis_angle<sizeof(T) == 4>((double)pd[0], (double)pd[1], (double)pd[2], ex, ey, ez);
-                s_fix[warp][lane][0] = ex; s_fix[warp][lane][1] = ey; s_fix[warp][lane][2] = ez;
+                double e[3];
+                const int need = (debug_mask & (1u << j)) ? 7 : slot_need(lane);   // unread components stay 0 as on the float64 path
+                b = euler_exact<sizeof(T) == 4>((double)pd[0], (double)pd[1], (double)pd[2], e, need);
+                s_fix[warp][lane][0] = e[0]; s_fix[warp][lane][1] = e[1]; s_fix[warp][lane][2] = e[2];
             }
             const bool any_bad = __ballot_sync(0xffffffffu, b) != 0;
             __syncwarp();
             if (lane == d) {
                 bad |= any_bad;
-#pragma unroll
-                for (int s = 0; s < N_SLOTS; ++s) {
-                    // the components no rule reads stay 0 as on the all-float64 path (slot_need)
-                    A.a[s][0] = (slot_need(s) & 1) || (debug_mask & (1u << slot_joint(s))) ? s_fix[warp][s][0] : 0.0;
-                    A.a[s][1] = (slot_need(s) & 2) || (debug_mask & (1u << slot_joint(s))) ? s_fix[warp][s][1] : 0.0;
-                    A.a[s][2] = (slot_need(s) & 4) || (debug_mask & (1u << slot_joint(s))) ? s_fix[warp][s][2] : 0.0;
-                }
+#pragma unroll 1
+                for (int s = 0; s < N_SLOTS; ++s) { A.a[s][0] = s_fix[warp][s][0]; A.a[s][1] = s_fix[warp][s][1]; A.a[s][2] = s_fix[warp][s][2]; }
             }
             __syncwarp();
         }
@@ -622,10 +630,9 @@ score_pose_kernel(const T* __restrict__ pose, const prk_addinfo* __restrict__ in
     while (rest) {
         const int j = __ffs(rest) - 1;
         rest &= rest - 1;
-        double ex, ey, ez;
-        euler_from_axis_angle<sizeof(T) == 4>((double)p[j * 3 + 0], (double)p[j * 3 + 1],
-                                              (double)p[j * 3 + 2], ex, ey, ez);
-        emit(j, ex, ey, ez);
+        double e[3];
+        euler_exact<sizeof(T) == 4>((double)p[j * 3 + 0], (double)p[j * 3 + 1], (double)p[j * 3 + 2], e, 7);
+        emit(j, e[0], e[1], e[2]);
     }
     alignas(16) prk_score_rec r;
     {
@@ -648,7 +655,9 @@ score_pose_kernel(const T* __restrict__ pose, const prk_addinfo* __restrict__ in
             if (src_lane < nf) dst[32 * k + lane] = (lane & 1) ? b : a;
         }
     }
-    if (n_debug > 0 && stage_dbg) {   // coalesced copy of the staged Euler sequences: nf rows of n_debug * 3 doubles
+    if (kDebug && n_debug > 0 && stage_dbg) {   // coalesced copy of the staged Euler sequences: nf rows of n_debug * 3 doubles
+        __syncwarp();                           // every lane is done with the pose tile (doubtful-frame pass included)
+        for (int k = 0; k < n_debug * 3; ++k) dtile[lane * kDebugPitch + k] = dbg_e[k];
         __syncwarp();
         const int w = n_debug * 3, n = nf * w;
         double* dst = euler_out + f0 * w;
@@ -717,6 +726,7 @@ score_hist_kernel(const prk_score_rec* __restrict__ recs, int64_t B, uint32_t wh
 // shared memory, then lane 0 runs the REBA ladders and lane 1 the RULA ladders of the frame.
 // Same device functions as the thread-per-frame kernel => bit-identical records.
 constexpr int kFramesPerBlockLanes = 8;
+constexpr int64_t kLanesVariantMaxFrames = 32768;    // above this the thread-per-frame kernel takes over (scripts/score_threshold.py: 65,536 frames 47 vs 29 us, 131,072 frames 90 vs 45 us)
 template <typename T>
 __global__ void __launch_bounds__(kFramesPerBlockLanes * 16)
 score_pose_lanes_kernel(const T* __restrict__ pose, const prk_addinfo* __restrict__ info, int32_t n_tracks,
@@ -767,7 +777,8 @@ cudaError_t launch_score_pose(const void* d_pose, int pose_dtype, const prk_addi
                               prk_score_rec* d_out, double* d_euler_out, const DebugSlots& dbg, int n_debug,
                               cudaStream_t s) {
     if (B == 0) return cudaSuccess;
-    if (n_debug == 0 && B <= 131072) {   // latency-bound regime: spread each frame over 16 lanes
+    static const int64_t lanes_max = [] { const char* e = getenv("PRK_SCORE_LANES_MAX"); return e ? atoll(e) : kLanesVariantMaxFrames; }();
+    if (n_debug == 0 && B <= lanes_max) {   // latency-bound regime: spread each frame over 16 lanes
         const unsigned g = grid_for(B, kFramesPerBlockLanes);
         if (pose_dtype == PRK_DTYPE_F32)
             score_pose_lanes_kernel<float><<<g, kFramesPerBlockLanes * 16, 0, s>>>((const float*)d_pose, d_info, n_tracks, d_track, B, which, d_out);
@@ -779,15 +790,14 @@ cudaError_t launch_score_pose(const void* d_pose, int pose_dtype, const prk_addi
     const unsigned g = grid_for(B, kScoreWarps * 32);
     // float32 poses: float32 screening + float64 re-evaluation of doubtful frames (PRK_SCORE_EXACT=1: float64 throughout)
     static const bool exact = [] { const char* e = getenv("PRK_SCORE_EXACT"); return e && atoi(e) != 0; }();
-    if (pose_dtype == PRK_DTYPE_F32 && !exact)
-        score_pose_kernel<float, true><<<g, kScoreWarps * 32, 0, s>>>(
-            (const float*)d_pose, d_info, n_tracks, d_track, B, which, d_out, d_euler_out, dbg, n_debug);
-    else if (pose_dtype == PRK_DTYPE_F32)
-        score_pose_kernel<float, false><<<g, kScoreWarps * 32, 0, s>>>(
-            (const float*)d_pose, d_info, n_tracks, d_track, B, which, d_out, d_euler_out, dbg, n_debug);
-    else
-        score_pose_kernel<double, false><<<g, kScoreWarps * 32, 0, s>>>(
-            (const double*)d_pose, d_info, n_tracks, d_track, B, which, d_out, d_euler_out, dbg, n_debug);
+#define PRK_SCORE_LAUNCH(T, FAST, DEBUG)                                                            \
+    score_pose_kernel<T, FAST, DEBUG><<<g, kScoreWarps * 32, 0, s>>>(                               \
+        (const T*)d_pose, d_info, n_tracks, d_track, B, which, d_out, d_euler_out, dbg, n_debug)
+    const bool debug = n_debug > 0;
+    if (pose_dtype == PRK_DTYPE_F32 && !exact) { if (debug) PRK_SCORE_LAUNCH(float, true, true); else PRK_SCORE_LAUNCH(float, true, false); }
+    else if (pose_dtype == PRK_DTYPE_F32) { if (debug) PRK_SCORE_LAUNCH(float, false, true); else PRK_SCORE_LAUNCH(float, false, false); }
+    else { if (debug) PRK_SCORE_LAUNCH(double, false, true); else PRK_SCORE_LAUNCH(double, false, false); }
+#undef PRK_SCORE_LAUNCH
     count_launch();
     return cudaGetLastError();
 }

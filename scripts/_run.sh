@@ -1,2 +1,4 @@
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests/test_gpu_round2.py -m gpu -q --timeout 900 -s -k "blend_operand or fast_screening" 2>&1 | grep -v Warning | tail -40 | tee gpurun_out/pytest_r2i.log
+python scripts/score_only_bench.py 2>&1 | grep "debug joints"
+python scripts/config5_launches.py 2>&1 | tail -1
+timeout 1500 python -m pytest tests -m gpu -q --timeout 900 -x 2>&1 | tail -3 | tee gpurun_out/pytest_r2l.log

@@ -500,7 +500,7 @@ def test_fast_screening_gives_the_exact_records(engine):
     records must be bit-identical to the all-float64 evaluation: 1M frames whose twelve scored joints are built from Euler
     angles sitting ON the thresholds up to offsets of 1e-7 .. 1e-2 degrees (the float32 rounding of the axis-angle vector
     then scatters them around the threshold at the 1e-5 degree level), gimbal-lock pitches and exact zeros included.  The
-    reference evaluation is the small-batch kernel (float64 throughout, chunks of 131,072 frames), itself checked against
+    reference evaluation is the small-batch kernel (float64 throughout, chunks of 16,384 frames), itself checked against
     the oracle on a sample here and in test_pose_to_scores_vs_oracle."""
     from scipy.spatial.transform import Rotation
     from poserisk_release_b200 import _runtime
@@ -523,7 +523,7 @@ def test_fast_screening_gives_the_exact_records(engine):
     pose[rng.random(n) < 0.01, 17] *= 3.0                  # rotations beyond 4 rad
     pose = torch.from_numpy(pose.reshape(n, 72)).cuda()
     fast, _ = engine.euler_debug(pose, [], EXAMPLE_INFO)                       # one call: the large-batch kernel
-    exact = torch.cat([engine.euler_debug(pose[i:i + 131072], [], EXAMPLE_INFO)[0] for i in range(0, n, 131072)])
+    exact = torch.cat([engine.euler_debug(pose[i:i + 16384], [], EXAMPLE_INFO)[0] for i in range(0, n, 16384)])
     torch.cuda.synchronize()
     diff = (fast != exact).any(dim=1)
     assert int(diff.sum()) == 0, (int(diff.sum()), torch.nonzero(diff)[:5].tolist())

@@ -715,9 +715,10 @@ def run_extra_configs(eng, dev, rank, world, transport, barrier):
                           "algorithmic_bytes_per_frame": bpf, "achieved_gbs": fps * bpf / 1e9,
                           "hbm_frac_per_gpu": fps * bpf / 1e9 / world / peaks['hbm_gbs'],
                           "stages_alone_ms": {"pose_chain_joints_only": ms_chain, "scoring_with_debug_euler": ms_score,
-                                              "note": "the two run concurrently on two streams inside the call; both are "
-                                                      "instruction bound (fp32 chain ~7k instr/frame, fp64 angles ~6k instr/frame), "
-                                                      "not HBM bound"},
+                                              "note": "issued on two streams inside the call, but each fills the GPU, so their times add; "
+                                                      "both are instruction bound (fp32 chain 8.4k warp instructions per 32 frames at "
+                                                      "65 % issue utilisation; scoring: float32 screening + float64 rows of the debug "
+                                                      "joints), not HBM bound -- DESIGN.md 'Joints-only path'"},
                           "exchange": ex5.used, "gathered_bytes_per_rank": n5 * (32 + 24 * len(DEBUG_JOINTS)), "parity": par}
     del joints5, scores5, euler5, pose, betas, trans, ex5, g_scores, g_euler
     torch.cuda.empty_cache()

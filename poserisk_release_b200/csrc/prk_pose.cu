@@ -314,7 +314,11 @@ constexpr int kWarpsPerBlock = 8;        // joints-only variant
 constexpr int kWarpsPerBlockMesh = PRK_CHAIN_WPB;   // full-mesh variant: 16 consecutive frames per block, so that the block
                                          // writes its AskinT columns as 64-byte runs (two full sectors) instead of
                                          // 288 scattered 4-byte stores per frame
-constexpr int64_t kWarpVariantMaxFrames = 49152;   // above this the thread-per-frame kernel is faster (full mesh, measured: 65,536 frames 159 vs 129 us; 16,384 frames 48 vs 80 us)
+// Above these frame counts per launch the thread-per-frame kernel is faster (scripts/chain_threshold.py).  Full mesh, round 2c: the
+// lane-per-joint kernel wins up to the 65,536 frames a launch can have (139 vs 142 us there, 80 vs 103 us at 32,768; before the
+// beta-major Jdirs copy it lost from 49,152 on), so mesh launches of standard-tree models always take it.
+constexpr int64_t kWarpVariantMaxFrames = 65536;
+constexpr int64_t kWarpVariantMaxFramesJointsOnly = 16384;
 
 template <bool kMesh>
 __global__ void __launch_bounds__((kMesh ? kWarpsPerBlockMesh : kWarpsPerBlock) * 32)
@@ -485,7 +489,8 @@ cudaError_t launch_pose_chain(const Model& m, const float* d_pose, const float* 
     const unsigned grid = (unsigned)((B + 127) / 128);
     const bool std_tree = m.pc.standard_tree != 0;
     static const int64_t warp_max = [] { const char* e = getenv("PRK_CHAIN_WARP_MAX"); return e ? (int64_t)atoll(e) : kWarpVariantMaxFrames; }();
-    if (std_tree && B <= warp_max) {   // latency-bound regime: one warp per frame
+    static const int64_t warp_max_jo = [] { const char* e = getenv("PRK_CHAIN_WARP_MAX_JO"); return e ? (int64_t)atoll(e) : kWarpVariantMaxFramesJointsOnly; }();
+    if (std_tree && B <= (full_mesh ? warp_max : warp_max_jo)) {   // latency-bound regime: one warp per frame
         const int wpb = full_mesh ? kWarpsPerBlockMesh : kWarpsPerBlock;
         const unsigned g = (unsigned)((B + wpb - 1) / wpb);
 #define PRK_LAUNCH_W(MESH)                                                                                \

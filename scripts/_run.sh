@@ -1,4 +1,2 @@
-mkdir -p gpurun_out
-python scripts/score_only_bench.py 2>&1 | grep "debug joints"
-python scripts/config5_launches.py 2>&1 | tail -1
-timeout 1500 python -m pytest tests -m gpu -q --timeout 900 -x 2>&1 | tail -3 | tee gpurun_out/pytest_r2l.log
+echo warp; PRK_CHAIN_WARP_MAX=100000000 python scripts/chain_threshold.py 2>&1 | grep call
+echo thread; PRK_CHAIN_WARP_MAX=0 python scripts/chain_threshold.py 2>&1 | grep call

@@ -3,7 +3,7 @@ sys.path.insert(0, os.getcwd()); os.environ['PRK_SYNTHETIC_SMPL'] = '1'
 import numpy as np, torch, bench
 from poserisk_release_b200 import PoseRiskEngine, _lib, _runtime
 eng = PoseRiskEngine('cuda:0'); L = _lib.lib()
-for B in (8192, 16384, 65536, 262144):
+for B in (8192, 16384, 32768, 65536):
     p, b, t = bench.counter_inputs(0, B, 'cuda:0')
     v = _runtime.aligned_verts(B, torch.device('cuda:0'))
     info = _runtime.addinfo_tensor(bench.EXAMPLE_INFO, torch.device('cuda:0'))

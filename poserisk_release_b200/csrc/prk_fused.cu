@@ -251,7 +251,7 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
                         const __grid_constant__ CUtensorMap tmap_V, const uint16_t* __restrict__ B2img,
                         const float* __restrict__ AskinT, const float* __restrict__ off,
                         const uint8_t* __restrict__ wpack, int groups_rt, int stages, int64_t B, int64_t n_units,
-                        float* __restrict__ verts, int dbg) {
+                        float* __restrict__ verts, int dbg, int switch_cost16) {
     const int groups = kGroups > 0 ? kGroups : groups_rt;
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment by OFFSET on the __shared__ array, so every derived pointer stays in the
@@ -323,8 +323,22 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
     // tensor map fills them) and stores nothing
     const int crank = kPair == 2 ? (int)cluster_ctarank() : 0;
     const int64_t cid = blockIdx.x / kPair, ncl = gridDim.x / kPair;
-    const int64_t u0 = cid * n_units / ncl;
-    const int64_t u1 = (cid + 1) * n_units / ncl;
+    // Balanced by cost, not by count: a frame-tile switch inside a range (drain the MMAs of the old A' tile, load 112 KB of A'
+    // and 147 KB of A_j into shared / tensor memory) costs `switch_cost16` sixteenths of a unit, and the ranges that contain one
+    // would otherwise finish last.  Position of unit u on the cost axis: 16 u + switch_cost16 * (u / 216).
+    const int64_t tile_cost = 16 * (int64_t)FUSED_NT + switch_cost16;
+    const int64_t total_cost = 16 * n_units + switch_cost16 * (n_units / FUSED_NT - 1);
+    auto first_unit = [&](int64_t k) -> int64_t {       // first unit whose cost position is >= k * total_cost / ncl
+        if (k >= ncl) return n_units;
+        const int64_t t = k * total_cost / ncl;
+        const int64_t f = t / tile_cost, r = t - f * tile_cost;
+        int64_t v = (r + 15) / 16;
+        if (v > FUSED_NT) v = FUSED_NT;
+        const int64_t u = f * FUSED_NT + v;
+        return u < n_units ? u : n_units;
+    };
+    const int64_t u0 = first_unit(cid);
+    const int64_t u1 = first_unit(cid + 1);
     const int n_my = (int)(u1 - u0);
     const int64_t ft0 = (u0 / FUSED_NT) * kPair + crank;
     const int vt0 = (int)(u0 - (u0 / FUSED_NT) * FUSED_NT);
@@ -862,6 +876,10 @@ int fused_stages(int groups, int pair, bool tma) {
     return stages;
 }
 
+// cost of a frame-tile switch inside a CTA's unit range, in sixteenths of a unit (see the kernel's range computation)
+#ifndef PRK_SWITCH_COST16_DEFAULT
+#define PRK_SWITCH_COST16_DEFAULT 48     // measured (profiles/r2_ab_runs.txt ab_r2_33): 0 / 16 / 32 / 48 / 64 -> 106.8 / 105.5 / 104.5 / 104.3 / 104.2 us
+#endif
 // CTA pairs: PRK_PAIR=1|2 overrides; default PRK_PAIR_DEFAULT when the batch has at least two frame tiles
 #ifndef PRK_PAIR_DEFAULT
 #define PRK_PAIR_DEFAULT 2
@@ -933,8 +951,9 @@ static cudaError_t launch_fused_t(const Model& m, const CUtensorMap& tmap_A, int
         const int rc = encode_tmap_2d_f32_strided(&tmV, d_verts, (uint64_t)B, (uint64_t)NVC, (uint64_t)vpitch * 4, 32, 24);
         if (rc != PRK_OK) return cudaErrorInvalidValue;
     }
+    static const int switch_cost16 = [] { const char* e = getenv("PRK_SWITCH_COST16"); return e ? atoi(e) : PRK_SWITCH_COST16_DEFAULT; }();
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmap_A, m.tmap_B2, tmV, b2img, d_AskinT, d_off, wpack, groups, stages, B, n_units,
-                                       d_verts, 0);
+                                       d_verts, 0, n_units >= 8 * (int64_t)(grid / kPair) ? switch_cost16 : 0);
     count_launch();
     return e != cudaSuccess ? e : cudaGetLastError();
 }

@@ -519,15 +519,20 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
                 epi_barrier();                                    // nobody still gathers the old A_j
                 const int64_t f = ft * FUSED_BM + quarter * 32 + lane;
                 const float* src = AskinT + ((size_t)(ft * 4 + quarter) * FUSED_ASKIN_COLS + oct * 72) * 32 + lane;
-                // 72 coalesced loads in three batches of 24: enough loads in flight to cover the L2 latency
+                // 72 coalesced loads in PRK_AJ_BATCHES batches: enough loads in flight to cover the L2 latency
+#ifndef PRK_AJ_BATCHES
+#define PRK_AJ_BATCHES 3
+#endif
+                constexpr int kAjPer = 72 / PRK_AJ_BATCHES;
+                static_assert(kAjPer * PRK_AJ_BATCHES == 72 && kAjPer % 8 == 0, "A_j batches of whole tcgen05.st.x8 groups");
 #pragma unroll 1
-                for (int b = 0; b < 3; ++b) {
-                    uint32_t v[24];
+                for (int b = 0; b < PRK_AJ_BATCHES; ++b) {
+                    uint32_t v[kAjPer];
 #pragma unroll
-                    for (int k = 0; k < 24; ++k)
-                        v[k] = (kPair == 1 || ft * FUSED_BM < B) ? __float_as_uint(__ldg(src + (b * 24 + k) * 32)) : 0u;   // no A_j tile beyond the batch
+                    for (int k = 0; k < kAjPer; ++k)
+                        v[k] = (kPair == 1 || ft * FUSED_BM < B) ? __float_as_uint(__ldg(src + (b * kAjPer + k) * 32)) : 0u;   // no A_j tile beyond the batch
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) tmem_st_x8(t_lane + (uint32_t)(oct * 72 + b * 24 + c * 8), v + c * 8);
+                    for (int c = 0; c < kAjPer / 8; ++c) tmem_st_x8(t_lane + (uint32_t)(oct * 72 + b * kAjPer + c * 8), v + c * 8);
                 }
                 tmem_st_wait();
                 if (f < B) { o0 = off[f * 3 + 0]; o1 = off[f * 3 + 1]; o2 = off[f * 3 + 2]; }

@@ -1,3 +1,4 @@
 mkdir -p gpurun_out
-( for x in 0 16 32 48 0 24 40 64; do echo "switch_cost16 $x"; PRK_SWITCH_COST16=$x AB_ALIGNED=1 python scripts/fused_ab.py base; done
-  for x in 0 32 0 32; do echo "long switch_cost16 $x"; PRK_SWITCH_COST16=$x AB_ALIGNED=1 AB_STEPS=5000 python scripts/fused_ab.py base; done ) 2>&1 | tee gpurun_out/ab_r2_33.log
+timeout 1500 python -m pytest tests -m gpu -q --timeout 900 -x 2>&1 | tail -3 | tee gpurun_out/pytest_r2m.log
+python scripts/pair_check.py 2>&1 | tail -1
+timeout 600 python scripts/soak.py 300 11 2>&1 | tail -1 | tee gpurun_out/soak_r2c.log

@@ -97,7 +97,7 @@ const char* prk_last_error_detail(void);
 
 /* SMPL_Layer.__init__ (lib/smplpytorch/smplpytorch/pytorch/smpl_layer.py:15-63): takes the
  * arrays that constructor registers as buffers (HOST pointers, float32, C order) and builds
- * the device-side operands: bf16 split-precision blend matrix for the tcgen05 GEMM,
+ * the device-side operands: split-precision (fp16 + e4m3, scaled by 2^S) blend matrix for the tcgen05 GEMM,
  * compacted skinning weights, folded joint regressor.
  *   h_v_template [6890*3]      th_v_template   (:46-48)
  *   h_shapedirs  [6890*3*10]   th_shapedirs    (:42-43)
@@ -266,7 +266,7 @@ int prk_comm_status(prk_comm* comm);
 /* ---- verification hooks (used by tests only; not on the product path) ---- */
 /* blend-shape stage alone: v_posed [B][prk_vposed_pitch()] float32 into d_vposed (room for
  * B rows), either through the product kernel run with identity skinning transforms
- * (use_simt = 0) or a plain FFMA loop over the same bf16 operands (use_simt = 1). */
+ * (use_simt = 0) or a plain FFMA loop over the same fp16 / e4m3 operands (use_simt = 1). */
 int prk_debug_blend(prk_model* model, const float* d_pose, const float* d_betas, int64_t B,
                     float* d_vposed, int use_simt, void* d_workspace, size_t workspace_bytes,
                     void* stream);

@@ -78,7 +78,7 @@ __device__ __forceinline__ void smpl_rodrigues(float ax, float ay, float az, flo
     float qw = c, qx = __fmul_rn(s, nx), qy = __fmul_rn(s, ny), qz = __fmul_rn(s, nz);
     const float qn = sqrtf(fmaf(qz, qz, fmaf(qy, qy, fmaf(qx, qx, __fmul_rn(qw, qw)))));
     // (measured: one reciprocal + multiplies instead of these seven divisions saves 13 % of the joints-only kernel and doubles
-    // the joint error against the oracle, 2.1e-7 -> 4.2e-7: not taken)
+    // the joint error against the float64 CPU restatement, 2.1e-7 -> 4.2e-7: not taken)
     qw = __fdiv_rn(qw, qn); qx = __fdiv_rn(qx, qn); qy = __fdiv_rn(qy, qn); qz = __fdiv_rn(qz, qn);           // :21
     const float w2 = __fmul_rn(qw, qw), x2 = __fmul_rn(qx, qx), y2 = __fmul_rn(qy, qy), z2 = __fmul_rn(qz, qz);
     const float wx = __fmul_rn(qw, qx), wy = __fmul_rn(qw, qy), wz = __fmul_rn(qw, qz);

@@ -351,8 +351,11 @@ def run_gpu_arm(args):
     # N > 1: every step's 32-byte score records are all-gathered inside the timed region.  Peer-memory transport
     # (prk_allgather_rows): issued by prk_pipeline on its scoring stream, i.e. underneath the vertex kernel; NCCL
     # (fallback when CUDA IPC is refused): ncclAllGather on the compute stream after the step.
-    ex_dev = ScoreExchange(B * world, dev, 0, None, args.transport) if world > 1 else None
-    ex_host = ScoreExchange(B * world, dev, 0, None, args.transport) if world > 1 else None
+    force_ex = os.environ.get('PRK_BENCH_FORCE_EXCHANGE') == '1'    # diagnostic: the rank-local exchange at N = 1 as well
+    ex_dev = ScoreExchange(B * world, dev, 0, None, args.transport) if (world > 1 or force_ex) else None
+    ex_host = ScoreExchange(B * world, dev, 0, None, args.transport) if (world > 1 or force_ex) else None
+    if os.environ.get('PRK_BENCH_NO_HOST_EXCHANGE') == '1':     # diagnostic: the e2e steps without the per-step exchange
+        ex_host = None
     transport = ex_dev.used if ex_dev else 'none'
 
     def step_device(i):
@@ -379,18 +382,22 @@ def run_gpu_arm(args):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        t0 = time.perf_counter()
         for i in range(steps):
             fn(i)
+        enq_us = (time.perf_counter() - t0) * 1e6 / max(steps, 1)      # host time to ENQUEUE a step (diagnostic)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
         local_ms.append(ms)
         if world > 1:
-            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            t = torch.tensor([ms, enq_us], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+            ms, enq_us = float(t[0].item()), float(t[1].item())
+        enqueue_us.append(enq_us)
         return ms
 
+    enqueue_us = []          # host enqueue time per step of every timed() call (max over ranks)
     local_ms = []            # this rank's own event times, in call order (diagnostic: how far apart the ranks are)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
@@ -458,8 +465,10 @@ def run_gpu_arm(args):
     reheat(0.5, host=True)                           # sustained clock state again (the event queries above were a pause)
     for i in range(max(W, 3)):
         step_host(i)
+    n_enq = len(enqueue_us)
     ms_e2e_runs = [timed(step_host, K) for _ in range(R)]
     ms_e2e = float(np.median(ms_e2e_runs))
+    e2e_enqueue_us = float(np.median(enqueue_us[n_enq:]))
     clocks = sampler.stop() if sampler else None
 
     # e2e with the vertices copied out as well: the host-to-host full-mesh rate (PCIe bound), a second, clearly
@@ -571,6 +580,7 @@ def run_gpu_arm(args):
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / K,
                         "h2d_bytes_per_step": B * (72 + 10 + 3) * 4 + 64,
                         "d2h_bytes_per_step": B * (72 * 4 + 32),
+                        "host_enqueue_us_per_step": e2e_enqueue_us,
                         "spread": {k: (B * world * K / (v * 1e-3) if k != "repeats" else v) for k, v in
                                    {**spread(ms_e2e_runs), "min": max(ms_e2e_runs), "max": min(ms_e2e_runs)}.items()},
                         "note": "pose/betas/trans in from pinned host memory, joints + score records out to pinned host "

@@ -625,11 +625,14 @@ int prk_pipeline(prk_model* model, const float* d_pose, const float* d_betas, co
     // into `stream`: prk_comm_wait does that where the gathered rows are needed (a rank may run one call ahead).
     int rc = PRK_OK;
     if (e == cudaSuccess && comm_scores)
-        rc = prk_allgather_rows(comm_scores, d_scores, B, frame_offset, sizeof(prk_score_rec), nullptr, ss);
+        rc = prk_allgather_rows_impl(comm_scores, d_scores, B, frame_offset, sizeof(prk_score_rec), nullptr, ss, false);
     if (e == cudaSuccess && rc == PRK_OK && comm_euler)
-        rc = prk_allgather_rows(comm_euler, d_euler_out, B, frame_offset, n_debug * 24, nullptr, ss);
-    if (e == cudaSuccess && e2 == cudaSuccess && rc == PRK_OK)
+        rc = prk_allgather_rows_impl(comm_euler, d_euler_out, B, frame_offset, n_debug * 24, nullptr, ss, false);
+    if (e == cudaSuccess && e2 == cudaSuccess && rc == PRK_OK) {
+        set_fused_exchange_hint(comm_scores != nullptr || comm_euler != nullptr);
         rc = forward_impl(m, d_pose, d_betas, d_trans, center_idx, B, d_verts, verts_pitch, d_joints, ws, ws_bytes, s);
+        set_fused_exchange_hint(false);
+    }
     if (e2 == cudaSuccess) e2 = cudaStreamWaitEvent(s, m->ev_score, 0);
     if (e != cudaSuccess) return cuda_fail(e, "score_pose_kernel");
     if (e2 != cudaSuccess) return cuda_fail(e2, "join of the scoring stream");
@@ -730,13 +733,15 @@ int prk_pipeline_host(prk_model* model, const float* h_pose, const float* h_beta
     }
     PRK_CUDA(cudaEventRecord(m->ev_score, ss));
     if (comm_scores) {   // multi-GPU: all-gather of the records underneath the vertex kernel; joined by prk_comm_wait
-        const int rcg = prk_allgather_rows(comm_scores, d_scores, B, frame_offset, sizeof(prk_score_rec), nullptr, ss);
+        const int rcg = prk_allgather_rows_impl(comm_scores, d_scores, B, frame_offset, sizeof(prk_score_rec), nullptr, ss, false);
         if (rcg != PRK_OK) { cudaStreamWaitEvent(s, m->ev_score, 0); chain_break(ws, nullptr); return rcg; }
     }
     PRK_CUDA(cudaStreamWaitEvent(s, m->ev_h2d, 0));
     PRK_CUDA(cudaStreamWaitEvent(s, m->ev_out, 0));         // d_joints of the previous call has been copied out
+    set_fused_exchange_hint(comm_scores != nullptr);
     int rc = forward_impl(m, d_pose, d_betas, d_trans, center_idx, B, d_verts, verts_pitch, d_joints, w + h.inner, ws_bytes - h.inner, s,
                           m->ev_joints);
+    set_fused_exchange_hint(false);
     if (rc != PRK_OK) {                                     // the caller's stream still joins what was launched
         cudaStreamWaitEvent(s, m->ev_score, 0);
         chain_break(ws, nullptr);
@@ -746,12 +751,16 @@ int prk_pipeline_host(prk_model* model, const float* h_pose, const float* h_beta
     // ---- copy-out stream: joints and scores leave under the vertex kernel of this call
     PRK_CUDA(cudaStreamWaitEvent(m->s_out, m->ev_joints, 0));
     PRK_CUDA(cudaStreamWaitEvent(m->s_out, m->ev_score, 0));
+    // The input set is free from HERE: its only readers are the flags / pose-chain kernels (done at ev_joints) and the scoring
+    // kernel (ev_score); the vertex kernel reads the inner workspace.  Recording the event here and not at the end of the call
+    // lets the copy-in of call i+2 start under the vertex kernel of call i -- a whole step earlier -- which is what the host
+    // path needs when 8 ranks share the host's links (copies alone: 120 us of a 147 us step, scripts/pcie_scaling.py).
+    PRK_CUDA(cudaEventRecord(m->ev_set_free[set], m->s_out));
     if (h_joints) PRK_CUDA(cudaMemcpyAsync(h_joints, d_joints, (size_t)B * 72 * 4, cudaMemcpyDeviceToHost, m->s_out));
     PRK_CUDA(cudaMemcpyAsync(h_scores, d_scores, (size_t)B * sizeof(prk_score_rec), cudaMemcpyDeviceToHost, m->s_out));
     PRK_CUDA(cudaEventRecord(m->ev_out, m->s_out));
     // completion stays ordered on the caller's stream: it joins the copy-out and the scoring stream
     PRK_CUDA(cudaStreamWaitEvent(s, m->ev_out, 0));
-    PRK_CUDA(cudaEventRecord(m->ev_set_free[set], s));
     return PRK_OK;
 }
 

@@ -10,10 +10,14 @@
 //   1. copies this rank's rows into the current slot of EVERY rank (plain 16-byte stores to peer pointers),
 //   2. fences at system scope; the last block to finish raises flag[slot][rank] = epoch on every rank
 //      (st.release.sys), and
-//   3. that same block then spins (ld.acquire.sys, time-bounded) until all `world` flags of the local slot carry the
-//      epoch, i.e. every peer's rows have landed here.
-// Work queued behind the kernel on the same stream therefore sees the complete gathered array.  No NCCL kernel, no
-// host round trip, a few microseconds per exchange; it can run on a side stream underneath the vertex kernel.
+//   3. a one-warp kernel on the communicator's OWN stream then spins (ld.acquire.sys, time-bounded) until all `world`
+//      flags of the local slot carry the epoch, i.e. every peer's rows have landed here (round 2c: the spin used to
+//      sit in the push kernel, i.e. on the caller's stream -- inside prk_pipeline_host that is the scoring stream, and
+//      the next call's scoring queued behind a wait for the slowest of 8 ranks: 202 instead of 150 us per step).
+// prk_allgather_rows joins the caller's stream with that wait, so work queued behind it sees the complete gathered array;
+// the pipeline entry points do not (prk_comm_wait joins where the rows are read): the next exchange of the communicator
+// is the only thing that waits for the peers, which gives the ranks a full call of slack.  No NCCL kernel, no
+// host round trip, a few microseconds per exchange, underneath the vertex kernel.
 //
 // Slot reuse: rank A writes slot e&1 of rank B during A's exchange e, which starts after A has seen B's flag of
 // exchange e-1, i.e. after B's stream reached its exchange e-1.  B's readers of exchange e-2 (same slot) are safe if they
@@ -54,7 +58,9 @@ struct prk_comm {
     uint64_t epoch = 0;
     int* h_status = nullptr;           // host-mapped: set to 1 by a wait that timed out
     int* d_status = nullptr;           // device alias of h_status
-    cudaEvent_t ev_last = nullptr;     // end of the previous exchange (exchanges of one comm are serialised)
+    cudaEvent_t ev_last = nullptr;     // end of the previous exchange's wait (exchanges of one comm are serialised)
+    cudaEvent_t ev_push = nullptr;     // the previous exchange's rows and flags are out
+    cudaStream_t s_wait = nullptr;     // the waits for the peers run here, not on the caller's stream
     bool ev_valid = false;
 };
 
@@ -79,8 +85,7 @@ __device__ __forceinline__ uint64_t global_ns() {
 template <typename U>
 __global__ void __launch_bounds__(256)
 allgather_push_kernel(const U* __restrict__ src, int64_t n16, int64_t dst16, PeerPtrs peers, int world, int rank,
-                      size_t slot_off, size_t flags_off, int slot, uint64_t epoch, unsigned int* done,
-                      int* status, uint64_t timeout_ns) {
+                      size_t slot_off, size_t flags_off, int slot, uint64_t epoch, unsigned int* done) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     // four loads in flight per thread (one at a time: 1.6 - 2.0 TB/s for the rank-local copy; the exchange of 128 MB of
     // records + Euler rows was 16 % of a 1M-frame joints-only job)
@@ -105,8 +110,14 @@ allgather_push_kernel(const U* __restrict__ src, int64_t n16, int64_t dst16, Pee
     __threadfence_system();
     if ((int)threadIdx.x < world)
         st_release_sys(reinterpret_cast<uint64_t*>(peers.buf[threadIdx.x] + flags_off) + slot * kMaxRanks + rank, epoch);
+}
+
+// one warp: lane p waits for rank p's flag of this slot
+__global__ void __launch_bounds__(32)
+allgather_wait_kernel(const uint8_t* own_buf, size_t flags_off, int world, int slot, uint64_t epoch, int* status,
+                      uint64_t timeout_ns) {
     if ((int)threadIdx.x < world) {
-        const uint64_t* f = reinterpret_cast<const uint64_t*>(peers.buf[rank] + flags_off) + slot * kMaxRanks + threadIdx.x;
+        const uint64_t* f = reinterpret_cast<const uint64_t*>(own_buf + flags_off) + slot * kMaxRanks + threadIdx.x;
         const uint64_t t0 = global_ns();
         while (ld_acquire_sys(f) < epoch) {
             if (global_ns() - t0 > timeout_ns) { *status = 1; __threadfence_system(); break; }
@@ -145,6 +156,8 @@ int prk_comm_create(prk_comm** out, int rank, int world, int device, size_t slot
     if (e == cudaSuccess) e = cudaHostAlloc(&c->h_status, sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable);
     if (e == cudaSuccess) { *c->h_status = 0; e = cudaHostGetDevicePointer(&c->d_status, c->h_status, 0); }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_last, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_push, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_wait, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { prk_comm_destroy(c); return fail("prk_comm_create", e); }
     c->peers.buf[rank] = c->d_buf;
@@ -160,6 +173,8 @@ void prk_comm_destroy(prk_comm* c) {
     for (int p = 0; p < kMaxRanks; ++p)
         if (c->ipc_opened[p]) cudaIpcCloseMemHandle(c->peers.buf[p]);
     if (c->ev_last) cudaEventDestroy(c->ev_last);
+    if (c->ev_push) cudaEventDestroy(c->ev_push);
+    if (c->s_wait) cudaStreamDestroy(c->s_wait);
     if (c->h_status) cudaFreeHost(c->h_status);
     cudaFree(c->d_buf);
     delete c;
@@ -221,8 +236,10 @@ int prk_comm_open_peers(prk_comm* c, const void* h_all) {
     return PRK_OK;
 }
 
-int prk_allgather_rows(prk_comm* c, const void* d_local, int64_t n_local, int64_t row_offset, int64_t row_bytes,
-                       void** d_gathered_out, void* stream) {
+// join: make `stream` wait for the peers' rows too (the public entry point); the pipeline calls pass false and leave that to
+// prk_comm_wait / the communicator's next exchange
+int prk_allgather_rows_impl(prk_comm* c, const void* d_local, int64_t n_local, int64_t row_offset, int64_t row_bytes,
+                            void** d_gathered_out, void* stream, bool join) {
     if (!c || n_local < 0 || row_offset < 0 || row_bytes <= 0 || (row_bytes & 7) || (n_local > 0 && !d_local) ||
         (reinterpret_cast<uintptr_t>(d_local) & 7)) {
         prk::comm_set_detail("prk_allgather_rows", "invalid argument (rows must be 8-byte multiples, 8-byte aligned)");
@@ -251,16 +268,27 @@ int prk_allgather_rows(prk_comm* c, const void* d_local, int64_t n_local, int64_
     const uint64_t timeout_ns = 20ull * 1000 * 1000 * 1000;
     if (wide)
         allgather_push_kernel<uint4><<<grid, 256, 0, s>>>(static_cast<const uint4*>(d_local), n16, dst16, c->peers, c->world,
-                                                          c->rank, slot_off, c->flags_off, slot, epoch, done, c->d_status, timeout_ns);
+                                                          c->rank, slot_off, c->flags_off, slot, epoch, done);
     else
         allgather_push_kernel<uint2><<<grid, 256, 0, s>>>(static_cast<const uint2*>(d_local), n16, dst16, c->peers, c->world,
-                                                          c->rank, slot_off, c->flags_off, slot, epoch, done, c->d_status, timeout_ns);
+                                                          c->rank, slot_off, c->flags_off, slot, epoch, done);
     prk::count_launch();
     COMM_CUDA(cudaGetLastError());
-    COMM_CUDA(cudaEventRecord(c->ev_last, s));
+    COMM_CUDA(cudaEventRecord(c->ev_push, s));
+    COMM_CUDA(cudaStreamWaitEvent(c->s_wait, c->ev_push, 0));
+    allgather_wait_kernel<<<1, 32, 0, c->s_wait>>>(c->d_buf, c->flags_off, c->world, slot, epoch, c->d_status, timeout_ns);
+    prk::count_launch();
+    COMM_CUDA(cudaGetLastError());
+    COMM_CUDA(cudaEventRecord(c->ev_last, c->s_wait));
     c->ev_valid = true;
+    if (join) COMM_CUDA(cudaStreamWaitEvent(s, c->ev_last, 0));
     if (d_gathered_out) *d_gathered_out = c->d_buf + slot_off;
     return PRK_OK;
+}
+
+int prk_allgather_rows(prk_comm* c, const void* d_local, int64_t n_local, int64_t row_offset, int64_t row_bytes,
+                       void** d_gathered_out, void* stream) {
+    return prk_allgather_rows_impl(c, d_local, n_local, row_offset, row_bytes, d_gathered_out, stream, true);
 }
 
 int prk_allgather_scores(prk_comm* c, const prk_score_rec* d_local, int64_t n_local, int64_t frame_offset,

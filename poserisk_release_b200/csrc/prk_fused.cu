@@ -865,6 +865,7 @@ extern "C" __attribute__((visibility("default"))) int prk_fused_debug_read(unsig
 }
 #endif
 
+static thread_local bool t_exchange_hint = false;   // this thread's current call issues a multi-GPU exchange beside the vertex kernel
 int fused_stages(int groups, int pair, bool tma) {
 #ifndef PRK_PAIR_STAGES
 #define PRK_PAIR_STAGES 12
@@ -878,8 +879,17 @@ int fused_stages(int groups, int pair, bool tma) {
     stages = PRK_STAGE_CAP * pair;
 #endif
     while (stages > 2 && fused_smem_bytes(stages, groups, pair, tma) > kSmemLimit) --stages;
+    // One ring slot fewer when the call takes part in a multi-GPU exchange (set_fused_exchange_hint; PRK_STAGE_ROOM=n overrides):
+    // a CTA with all 10 slots owns the SM's whole shared memory, so no block of another kernel -- the exchange's push kernel,
+    // the next call's scoring -- can run beside it and everything queues up at the kernel boundary.  Measured on the host path:
+    // +11 us per step with the exchange and all slots, +4 us with 9 slots; 8 GPUs end to end 162 - 177 -> 198 M frames/s
+    // together with the wait for the peers moved off the scoring stream (prk_comm.cu).
+    static const int room_env = [] { const char* e = getenv("PRK_STAGE_ROOM"); return e ? atoi(e) : -1; }();
+    const int room = room_env >= 0 ? room_env : (t_exchange_hint ? 1 : 0);
+    if (room > 0 && stages - room >= 2) stages -= room;
     return stages;
 }
+void set_fused_exchange_hint(bool on) { t_exchange_hint = on; }
 
 // cost of a frame-tile switch inside a CTA's unit range, in sixteenths of a unit (see the kernel's range computation)
 #ifndef PRK_SWITCH_COST16_DEFAULT

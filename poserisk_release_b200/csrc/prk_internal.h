@@ -138,9 +138,16 @@ bool pose_chain_needs_flags(const Model& m, const float* d_betas, const float* d
 cudaError_t launch_fused(const Model& m, const CUtensorMap& tmap_A, int64_t rows_pad, const float* d_AskinT,
                          const float* d_off, int64_t B, float* d_verts, int64_t vpitch, cudaStream_t s);
 
+// the calling thread's next vertex-kernel launches run beside a multi-GPU exchange: leave shared memory for its blocks
+void set_fused_exchange_hint(bool on);
+
 // verification hooks of prk_debug_blend: plain FFMA evaluation of the same bf16 operands, identity A_j tiles
 cudaError_t launch_blend_simt(const Model& m, const uint16_t* d_Arows, int64_t rows, float* d_vposed, cudaStream_t s);
 cudaError_t launch_identity_askin(const Model& m, float* d_AskinT, float* d_off, int64_t rows_pad, cudaStream_t s);
+
+// multi-GPU exchange (prk_comm.cu): prk_allgather_rows with / without joining `stream` with the wait for the peers' rows
+extern "C" int prk_allgather_rows_impl(prk_comm* c, const void* d_local, int64_t n_local, int64_t row_offset, int64_t row_bytes,
+                                       void** d_gathered_out, void* stream, bool join);
 
 // K3: Euler angles + REBA/RULA
 // --debug_joints list as a by-value kernel parameter: bit j of `mask` = joint j is listed, slot[j] = its position

@@ -224,8 +224,9 @@ int prk_score_histogram(const prk_score_rec* d_scores, int64_t B, uint32_t which
  * Euler sequences (the reference keeps both as per-frame Python lists: lib/core/base.py:144-151,168).
  * The gather runs over peer memory: every rank owns a gather buffer that its peers map through CUDA IPC
  * (or address directly when they live in the same process); prk_allgather_rows stores this rank's rows into
- * EVERY rank's buffer over NVLink, raises one flag per peer, and waits for the peers' flags -- no host
- * round trip, no NCCL kernel competing for SMs.  torch.distributed / MPI / files are only needed once, to
+ * EVERY rank's buffer over NVLink and raises one flag per peer; a one-warp kernel on the communicator's own
+ * stream waits for the peers' flags, and the caller's stream is joined with it -- no host round trip, no NCCL
+ * kernel competing for SMs.  torch.distributed / MPI / files are only needed once, to
  * hand the opaque handles round.
  *
  *   prk_comm_create        allocates the gather buffer (two slots of slot_bytes each) and the flags

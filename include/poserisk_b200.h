@@ -265,6 +265,9 @@ int prk_allgather_scores(prk_comm* comm, const prk_score_rec* d_local, int64_t n
 int prk_comm_status(prk_comm* comm);
 
 /* ---- verification hooks (used by tests only; not on the product path) ---- */
+/* unit range [*u0, *u1) that CTA (pair) k of n_ranges takes in the vertex kernel when a frame-tile switch inside a range
+ * is charged switch_cost16 / 16 units (host arithmetic only, no GPU): n_units = frame tiles (pairs) x 216 vertex tiles */
+int prk_debug_unit_range(int64_t n_units, int64_t n_ranges, int switch_cost16, int64_t k, int64_t* u0, int64_t* u1);
 /* blend-shape stage alone: v_posed [B][prk_vposed_pitch()] float32 into d_vposed (room for
  * B rows), either through the product kernel run with identity skinning transforms
  * (use_simt = 0) or a plain FFMA loop over the same fp16 / e4m3 operands (use_simt = 1). */

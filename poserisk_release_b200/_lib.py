@@ -38,7 +38,7 @@ EXPORTS = (
     'prk_abi_version', 'prk_strerror', 'prk_last_error_detail', 'prk_model_create',
     'prk_model_destroy', 'prk_model_device', 'prk_model_max_weights', 'prk_workspace_bytes',
     'prk_smpl_forward', 'prk_score_pose', 'prk_score_euler', 'prk_euler', 'prk_pipeline',
-    'prk_rot_to_angle', 'prk_host_workspace_bytes', 'prk_host_scores_offset', 'prk_pipeline_host', 'prk_score_histogram', 'prk_debug_blend',
+    'prk_rot_to_angle', 'prk_host_workspace_bytes', 'prk_host_scores_offset', 'prk_pipeline_host', 'prk_score_histogram', 'prk_debug_blend', 'prk_debug_unit_range',
     'prk_vposed_pitch', 'prk_launch_count', 'prk_profile_begin', 'prk_profile_begin_stages', 'prk_profile_end',
     'prk_comm_create', 'prk_comm_destroy', 'prk_comm_handle_bytes', 'prk_comm_get_handle', 'prk_comm_open_peers',
     'prk_comm_gathered', 'prk_comm_wait', 'prk_allgather_rows', 'prk_allgather_scores', 'prk_comm_status')
@@ -97,6 +97,8 @@ def lib():
     L.prk_score_histogram.argtypes = [vp, i64, u32, vp, vp]
     L.prk_debug_blend.restype = i32
     L.prk_debug_blend.argtypes = [vp, vp, vp, i64, vp, i32, vp, sz, vp]
+    L.prk_debug_unit_range.restype = i32
+    L.prk_debug_unit_range.argtypes = [i64, i64, i32, i64, vp, vp]
     L.prk_vposed_pitch.restype = i64
     L.prk_launch_count.restype = C.c_uint64
     L.prk_profile_begin.restype = i32

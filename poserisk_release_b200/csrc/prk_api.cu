@@ -764,6 +764,16 @@ int prk_pipeline_host(prk_model* model, const float* h_pose, const float* h_beta
     return PRK_OK;
 }
 
+int prk_debug_unit_range(int64_t n_units, int64_t n_ranges, int switch_cost16, int64_t k, int64_t* u0, int64_t* u1) {
+    if (n_units < 0 || n_ranges < 1 || switch_cost16 < 0 || k < 0 || k >= n_ranges || !u0 || !u1 || (n_units % FUSED_NT) != 0) {
+        set_detail("prk_debug_unit_range", "invalid argument");
+        return PRK_ERR_INVALID_ARG;
+    }
+    *u0 = fused_first_unit(k, n_ranges, n_units, switch_cost16);
+    *u1 = fused_first_unit(k + 1, n_ranges, n_units, switch_cost16);
+    return PRK_OK;
+}
+
 int prk_score_histogram(const prk_score_rec* d_scores, int64_t B, uint32_t which, unsigned long long* d_hist,
                         void* stream) {
     if (B < 0 || !d_hist || (B > 0 && !d_scores) || (which != PRK_SCORE_REBA && which != PRK_SCORE_RULA)) {

@@ -323,22 +323,11 @@ fused_blend_skin_kernel(const __grid_constant__ CUtensorMap tmap_A, const __grid
     // tensor map fills them) and stores nothing
     const int crank = kPair == 2 ? (int)cluster_ctarank() : 0;
     const int64_t cid = blockIdx.x / kPair, ncl = gridDim.x / kPair;
-    // Balanced by cost, not by count: a frame-tile switch inside a range (drain the MMAs of the old A' tile, load 112 KB of A'
-    // and 147 KB of A_j into shared / tensor memory) costs `switch_cost16` sixteenths of a unit, and the ranges that contain one
-    // would otherwise finish last.  Position of unit u on the cost axis: 16 u + switch_cost16 * (u / 216).
-    const int64_t tile_cost = 16 * (int64_t)FUSED_NT + switch_cost16;
-    const int64_t total_cost = 16 * n_units + switch_cost16 * (n_units / FUSED_NT - 1);
-    auto first_unit = [&](int64_t k) -> int64_t {       // first unit whose cost position is >= k * total_cost / ncl
-        if (k >= ncl) return n_units;
-        const int64_t t = k * total_cost / ncl;
-        const int64_t f = t / tile_cost, r = t - f * tile_cost;
-        int64_t v = (r + 15) / 16;
-        if (v > FUSED_NT) v = FUSED_NT;
-        const int64_t u = f * FUSED_NT + v;
-        return u < n_units ? u : n_units;
-    };
-    const int64_t u0 = first_unit(cid);
-    const int64_t u1 = first_unit(cid + 1);
+    // Balanced by cost, not by count (prk_internal.h fused_first_unit): a frame-tile switch inside a range (drain the MMAs of the
+    // old A' tile, load 112 KB of A' and 147 KB of A_j into shared / tensor memory) costs `switch_cost16` sixteenths of a unit,
+    // and the ranges that contain one would otherwise finish last.
+    const int64_t u0 = fused_first_unit(cid, ncl, n_units, switch_cost16);
+    const int64_t u1 = fused_first_unit(cid + 1, ncl, n_units, switch_cost16);
     const int n_my = (int)(u1 - u0);
     const int64_t ft0 = (u0 / FUSED_NT) * kPair + crank;
     const int vt0 = (int)(u0 - (u0 / FUSED_NT) * FUSED_NT);

@@ -74,6 +74,22 @@ __host__ __device__ constexpr size_t fused_b2_byte_index(int n, int byte) {
     return fused_b2_index(n, byte >> 1) * 2 + (size_t)(byte & 1);
 }
 
+// Unit ranges of the vertex kernel's CTAs (pairs), balanced by cost: unit u = (frame tile (pair) u / 216, vertex tile u % 216)
+// sits at 16 u + switch_cost16 * (u / 216) on a cost axis on which entering a new frame tile inside a range costs switch_cost16
+// sixteenths of a unit; range k of n_ranges starts at the first unit whose position is >= k * total / n_ranges.
+// Contiguous, covers [0, n_units) exactly, fused_first_unit(n_ranges) = n_units.
+__host__ __device__ inline int64_t fused_first_unit(int64_t k, int64_t n_ranges, int64_t n_units, int switch_cost16) {
+    if (k >= n_ranges) return n_units;
+    const int64_t tile_cost = 16 * (int64_t)FUSED_NT + switch_cost16;
+    const int64_t total_cost = 16 * n_units + switch_cost16 * (n_units / FUSED_NT - 1);
+    const int64_t t = k * total_cost / n_ranges;
+    const int64_t f = t / tile_cost, r = t - f * tile_cost;
+    int64_t v = (r + 15) / 16;
+    if (v > FUSED_NT) v = FUSED_NT;
+    const int64_t u = f * FUSED_NT + v;
+    return u < n_units ? u : n_units;
+}
+
 // Rest joints as an affine function of betas: J = J_template + Jdirs * beta
 // (folds J_regressor @ (v_template + shapedirs beta), smpl_layer.py:91,95).
 struct PoseConsts {

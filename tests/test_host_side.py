@@ -341,3 +341,32 @@ def test_save_obj_known_answer(tmp_path):
     assert (tmp_path / 'm.obj').read_text() == 'v 0.5 -1.25 3.0\nv 1e-07 2.0 1234.5677\nf 1/1 2/2 2/2\n'
     report.save_obj(v[:1].astype(np.float64), None, str(tmp_path / 'n.obj'))
     assert (tmp_path / 'n.obj').read_text() == 'v 0.5 -1.25 3.0\n'
+
+
+def test_vertex_kernel_unit_ranges_cover_every_unit_once():
+    """The vertex kernel's CTAs (pairs) take contiguous unit ranges balanced by COST (a frame-tile switch inside a range is
+    charged switch_cost16 / 16 units, csrc/prk_internal.h fused_first_unit).  Host arithmetic through the verification hook:
+    for every batch shape the ranges are contiguous, cover [0, n_units) exactly once, and no range's cost exceeds the mean by
+    more than one unit plus one switch."""
+    import ctypes as C
+    from poserisk_release_b200 import _lib
+    L = _lib.lib()
+    NT = 216
+    for tiles in (1, 2, 3, 16, 17, 64, 256):
+        for n_ranges in (1, 2, 37, 74, 148):
+            for cost16 in (0, 16, 48, 200):
+                n_units = tiles * NT
+                prev_end, worst = 0, 0.0
+                total = 16 * n_units + cost16 * (tiles - 1)
+                for k in range(n_ranges):
+                    u0, u1 = C.c_int64(), C.c_int64()
+                    _lib.check(L.prk_debug_unit_range(n_units, n_ranges, cost16, k, C.byref(u0), C.byref(u1)))
+                    assert u0.value == prev_end and u1.value >= u0.value, (tiles, n_ranges, cost16, k)
+                    prev_end = u1.value
+                    # switches strictly inside the range: tile boundaries b with u0 < b < u1 ... plus one at u0 if u0 is a boundary > 0
+                    inside = sum(1 for b in range(NT, n_units, NT) if u0.value < b < u1.value)
+                    worst = max(worst, 16 * (u1.value - u0.value) + cost16 * inside)
+                assert prev_end == n_units
+                assert worst <= total / n_ranges + 16 + cost16 + 16, (tiles, n_ranges, cost16, worst, total / n_ranges)
+    bad = C.c_int64()
+    assert L.prk_debug_unit_range(100, 4, 0, 0, C.byref(bad), C.byref(bad)) != 0       # not a multiple of 216

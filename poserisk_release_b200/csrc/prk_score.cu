@@ -12,7 +12,8 @@
 //
 // One thread scores one frame.  Angles are computed in float64 with explicitly
 // non-contracted multiplies/adds in the cv2.Rodrigues closed form, so that the only
-// differences to the CPU reference are the last-ulp behaviour of sin/cos/atan2.
+// differences to the CPU reference are the last-ulp behaviour of sin/cos/atan2.  (Large float32 batches screen the
+// angles in float32 first and re-evaluate only the frames near a ladder threshold in float64: euler_screen below.)
 // HBM traffic: 144 B (12 joints x 3 x f32) in, 32 B out per frame.
 #include "prk_internal.h"
 

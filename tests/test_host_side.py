@@ -370,3 +370,52 @@ def test_vertex_kernel_unit_ranges_cover_every_unit_once():
                 assert worst <= total / n_ranges + 16 + cost16 + 16, (tiles, n_ranges, cost16, worst, total / n_ranges)
     bad = C.c_int64()
     assert L.prk_debug_unit_range(100, 4, 0, 0, C.byref(bad), C.byref(bad)) != 0       # not a multiple of 216
+
+
+def _e4m3(x):
+    """Round-to-nearest-even quantisation to OCP e4m3 (4 significant bits, normal exponents -6..8, subnormal step 2^-9,
+    saturating at 448) -- the format of the blend kernel's cross-term operands."""
+    x = np.asarray(x, np.float64)
+    a = np.minimum(np.abs(x), 448.0)
+    e = np.floor(np.log2(np.maximum(a, 2.0 ** -20)))
+    e = np.clip(e, -6, 8)
+    q = 2.0 ** (e - 3)                      # spacing: 3 explicit mantissa bits
+    return np.sign(x) * np.round(a / q) * q  # numpy rounds half to even
+
+
+def test_blend_operand_scheme_numpy_model():
+    """The arithmetic of the vertex kernel's blend stage restated in numpy (csrc/prk_internal.h "K12 operand layout"):
+    fp16 main product + two e4m3 cross terms for the pose blend shapes, two fp16 parts per factor for betas x shapedirs,
+    the template as 2^15 (u1 + u2 + u3), everything scaled by 2^S, fp32 accumulation.  Against float64 the model must stay
+    far inside north_star's 1e-5 (it is what the GPU parity tests then measure on the device: 3e-7 .. 5e-7)."""
+    from poserisk_release_b200.model_provider import synthetic_smpl
+    from scipy.spatial.transform import Rotation
+    m = synthetic_smpl('neutral')
+    pd = m.posedirs.reshape(-1, 207).astype(np.float64)[::7]          # a seventh of the vertex coordinates keeps it quick
+    sd = m.shapedirs.reshape(-1, 10).astype(np.float64)[::7]
+    vt = m.v_template.reshape(-1).astype(np.float64)[::7]
+    S = int(np.floor(np.log2(min(16384 / np.abs(m.posedirs).max(), 32768 / np.abs(m.shapedirs).max(),
+                                 2.0 ** 30 / np.abs(m.v_template).max()))))
+    f16 = lambda a: np.asarray(a, np.float64).astype(np.float16).astype(np.float64)
+    rng = np.random.default_rng(0)
+    for pose_s, beta_s in ((0.35, 1.0), (0.6, 3.0), (1.2, 10.0)):
+        B = 64
+        rv = rng.standard_normal((B, 23, 3)) * pose_s
+        R = Rotation.from_rotvec(rv.reshape(-1, 3)).as_matrix().reshape(B, 23, 9).astype(np.float32).astype(np.float64)
+        F = (R - np.eye(3).reshape(1, 1, 9)).reshape(B, 207)
+        beta = (rng.standard_normal((B, 10)) * beta_s).astype(np.float32).astype(np.float64)
+        ref = vt[None] + beta @ sd.T + F @ pd.T
+        P, Sd, T = np.ldexp(pd, S), np.ldexp(sd, S), np.ldexp(vt, S)
+        Fh, Ph = f16(F), f16(P)
+        acc = Fh @ Ph.T                                                 # 13 kind::f16 MMAs
+        acc += _e4m3((F - Fh) * 4096.0) @ _e4m3(P / 4096.0).T + _e4m3(F) @ _e4m3(P - Ph).T     # 13 kind::f8f6f4 MMAs
+        bh, sh = f16(beta), f16(Sd)
+        bl, sl = f16(beta - bh), f16(Sd - sh)
+        u = T * 2.0 ** -15
+        u1 = f16(u); u2 = f16(u - u1); u3 = f16(u - u1 - u2)
+        acc += bh @ sh.T + bl @ sh.T + bh @ sl.T + 2.0 ** 15 * (u1 + u2 + u3)[None]             # 3 kind::f16 MMAs
+        out = np.ldexp(acc.astype(np.float32).astype(np.float64), -S)
+        err = np.abs(out - ref).max() / np.abs(ref).max()
+        assert err < 1e-6, (pose_s, beta_s, err)
+    # the format emulation itself: exact e4m3 values survive, the spacing above 16 is 2, saturation at 448
+    assert np.array_equal(_e4m3([0.0, 1.0, 1.125, 17.0, 18.9, 500.0, -0.001953125]), [0.0, 1.0, 1.125, 16.0, 18.0, 448.0, -0.001953125])

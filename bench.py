@@ -386,6 +386,9 @@ def run_gpu_arm(args):
         for i in range(steps):
             fn(i)
         enq_us = (time.perf_counter() - t0) * 1e6 / max(steps, 1)      # host time to ENQUEUE a step (diagnostic)
+        for ex in (ex_dev, ex_host):          # the last step's exchange (side streams) belongs to the timed region
+            if ex is not None:
+                ex.join()
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)

@@ -148,6 +148,16 @@ class ScoreExchange:
             return s, e
         return self.collect(local_scores, frame_offset, local_euler, sizes)
 
+    def join(self):
+        """Make the current stream wait for the most recent exchange issued inside an engine call (peer transport: it
+        runs on side streams and is not joined by the call; NCCL runs on the current stream already)."""
+        if self.used == 'peer':
+            from . import _lib, _runtime
+            for c in (self.comm_scores, self.comm_euler):
+                if c is not None:
+                    with torch.cuda.device(c.device):
+                        _lib.check(_lib.lib().prk_comm_wait(c.handle, _runtime.stream_ptr(c.device)))
+
     def check(self):
         if self.comm_scores is not None:
             self.comm_scores.check()
